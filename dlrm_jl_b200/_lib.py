@@ -1,0 +1,86 @@
+"""ctypes binding of libdlrm_b200.so (the C ABI declared in include/dlrm_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdlrm_b200.so")
+
+OK, EINVAL, ECUDA, ENOMEM, EOOB, ESTATE = 0, 1, 2, 3, 4, 5
+_STATUS_NAMES = {EINVAL: "DLRMB_EINVAL", ECUDA: "DLRMB_ECUDA", ENOMEM: "DLRMB_ENOMEM",
+                 EOOB: "DLRMB_EOOB", ESTATE: "DLRMB_ESTATE"}
+
+
+class DLRMB200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{_STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+_idx_args = [_vp, _i32, _i32, _i32, _i32]  # idx, idx_bytes, idx_base, B, P
+
+# name -> (restype, argtypes); every symbol include/dlrm_b200.h declares
+SIGNATURES = {
+    "dlrmb_abi_version": (_i32, []),
+    "dlrmb_last_error": (C.c_char_p, []),
+    "dlrmb_launch_count": (_i64, []),
+    "dlrmb_tables_create": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, C.POINTER(_vp)]),
+    "dlrmb_tables_destroy": (_i32, [_vp]),
+    "dlrmb_tables_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
+    "dlrmb_tables_upload": (_i32, [_vp, _i32, _vp]),
+    "dlrmb_tables_download": (_i32, [_vp, _i32, _vp]),
+    "dlrmb_tables_device_ptr": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "dlrmb_tables_init_uniform": (_i32, [_vp, C.c_uint64, _vp]),
+    "dlrmb_tables_sync": (_i32, [_vp]),
+    "dlrmb_embedding_fwd": (_i32, [_vp, *_idx_args, _vp, _i32, _i32, _vp]),
+    "dlrmb_interaction_fwd": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dlrmb_interaction_bwd": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "dlrmb_embedding_sort": (_i32, [_vp, *_idx_args, _vp]),
+    "dlrmb_embedding_update_sorted": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp]),
+    "dlrmb_embedding_bwd_sgd": (_i32, [_vp, *_idx_args, _vp, _i32, _i32, _f32, _vp]),
+    "dlrmb_sort_dedup_export": (_i32, [_vp, _i32, _vp, _vp, _vp, C.POINTER(_i32)]),
+    "dlrmb_check_indices": (_i32, [_vp, *_idx_args, _i32]),
+    "dlrmb_embedding_fwd_host": (_i32, [_vp, *_idx_args, _vp, _i32, _i32]),
+    "dlrmb_interaction_fwd_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "dlrmb_interaction_bwd_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dlrmb_embedding_bwd_sgd_host": (_i32, [_vp, *_idx_args, _vp, _i32, _i32, _f32]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every declared symbol (raises if any is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DLRMB200Error(
+            ESTATE,
+            f"{LIB_PATH} not found: build it with `python -m dlrm_jl_b200.csrc.build` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dlrmb_abi_version() != 1:
+        raise DLRMB200Error(ESTATE, f"ABI version mismatch: library has {lib.dlrmb_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        msg = load().dlrmb_last_error()
+        raise DLRMB200Error(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+def launch_count() -> int:
+    return int(load().dlrmb_launch_count())

@@ -1,0 +1,119 @@
+// Internal declarations shared by the translation units of libdlrm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "dlrm_b200.h"
+
+namespace dlrmb {
+
+// ---- error plumbing ----------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define DLRMB_CUDA(expr)                                                                    \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::dlrmb::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,         \
+                               cudaGetErrorString(_e));                                     \
+            return (_e == cudaErrorMemoryAllocation) ? DLRMB_ENOMEM : DLRMB_ECUDA;          \
+        }                                                                                   \
+    } while (0)
+
+#define DLRMB_REQUIRE(cond, ...)                                                            \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            ::dlrmb::set_error(__VA_ARGS__);                                                \
+            return DLRMB_EINVAL;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define DLRMB_LAUNCH_CHECK()                                                                \
+    do {                                                                                    \
+        ::dlrmb::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+        DLRMB_CUDA(cudaGetLastError());                                                     \
+    } while (0)
+
+// ---- table storage -----------------------------------------------------------------------
+struct TableDesc {
+    float* base;   // [rows][D] f32 in HBM, 256-byte aligned
+    int64_t rows;
+};
+
+// Geometry of the sorted-stream reduction (update.cu): every lane group walks TILE
+// consecutive entries of the per-table sorted (row id, position) stream.
+constexpr int kUpdateTile = 16;
+// Largest per-table lookup count the single-CTA shared-memory sort handles (sort.cu).
+constexpr int kSmemSortMax = 4096;
+
+}  // namespace dlrmb
+
+struct dlrmb_tables {
+    int device = 0;
+    int ntab = 0;
+    int D = 0;
+    int sm_count = 148;
+    int64_t max_lookups = 0;   // max B*P per table
+    int64_t total_rows = 0;
+    int64_t max_rows = 0;
+    int64_t* h_rows = nullptr;       // host copy
+    int64_t* h_offsets = nullptr;    // element offsets of each table inside `slab`
+    float* slab = nullptr;           // all tables, one allocation
+    dlrmb::TableDesc* d_desc = nullptr;
+    cudaStream_t own_stream = nullptr;
+
+    // sort / update workspace (all [ntab][max_lookups] unless noted)
+    uint32_t* keys[2] = {nullptr, nullptr};   // 0-based row ids, ping-pong
+    uint32_t* pos[2] = {nullptr, nullptr};    // flat position b*P+p, ping-pong
+    uint32_t* tile_hist = nullptr;            // radix: [ntab][256][tiles]
+    int sorted_buf = 0;                       // which ping-pong half holds the sorted stream
+    int64_t radix_tiles_cap = 0;
+    float* partial = nullptr;                 // [ntab][tiles][2][D] boundary partial sums
+    uint8_t* tile_flags = nullptr;            // [ntab][tiles] boundary flags
+    int64_t partial_tiles_cap = 0;
+    // dedup export scratch
+    int32_t* d_seg = nullptr;                 // [max_lookups + 1]
+    int64_t* d_uniq = nullptr;                // [max_lookups]
+    int32_t* d_nuniq = nullptr;
+
+    // state of the last sort
+    bool sorted_valid = false;
+    int sorted_B = 0, sorted_P = 0;
+
+    // host-entry-point staging (device side), grown on demand
+    void* stage_idx = nullptr;  size_t stage_idx_bytes = 0;
+    float* stage_a = nullptr;   size_t stage_a_bytes = 0;
+    float* stage_b = nullptr;   size_t stage_b_bytes = 0;
+    float* stage_c = nullptr;   size_t stage_c_bytes = 0;
+    float* stage_d = nullptr;   size_t stage_d_bytes = 0;
+};
+
+namespace dlrmb {
+
+// kernels' host-side launchers (each returns a dlrmb_status)
+int launch_lookup(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                  float* out, int slots, int slot0, cudaStream_t s);
+int launch_interaction_fwd(float* T, const float* x, int B, int F, int d, int pad_to_mul,
+                           float* out, int sm_count, cudaStream_t s);
+int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
+                           float* dT, float* dx, int sm_count, cudaStream_t s);
+int launch_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                cudaStream_t s);
+int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s);
+int launch_dedup_export(dlrmb_tables* t, int k, cudaStream_t s);
+int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s);
+int launch_check_indices(dlrmb_tables* t, const void* d_idx, int idx_bytes, int idx_base, int B,
+                         int P, cudaStream_t s, long long* bad_table, long long* bad_pos,
+                         long long* bad_val);
+int device_sm_count(int device);
+int64_t update_tiles_cap(int ntab, int D, int64_t max_lookups, int sm_count);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
+int ensure_smem_attr(const void* func, int bytes, unsigned long long* done_mask);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace dlrmb

@@ -1,0 +1,413 @@
+// Dot-product feature interaction, forward and backward, as batched small-Gram kernels.
+//
+// Replaces DotInteraction forward (DLRM.jl src/model/interact.jl:394-411: fast_vcat :271-281,
+// process_batches :449-467, process_slice! :338-362, gemmavx! :318-326,
+// triangular_slice_kernel! :64-75) and its pullback (dot_back :424-436, process_batches_back
+// :469-489, triangular_slice_back_fuse_add_transpose_kernel! :154-173, sumavx :329-336).
+//
+// Forward, per sample b:  out[b] = [ x_b ; <T_b[i], T_b[j]> for j = 1..F-1, i = 0..j-1 ; 0-pad ]
+//   flat position of pair i<j is d + j(j-1)/2 + i.
+// Backward, per sample b: S symmetric F x F with zero diagonal from dOut[b][d:], then
+//   dT_b[f] = sum_j S[j][f] * T_b[j],  dx_b = dOut[b][:d] + dT_b[0].
+//
+// Both are HBM-bound at DLRM shapes (5-12 flop/byte, below the fp32 FMA ridge), so the work
+// stays on the FP32 FMA pipe (TF32 tensor cores would break the 1e-5 tolerance) and the design
+// goal is one read of T and one write of the result per sample:
+//   - a CTA owns NS consecutive samples; their T rows are one contiguous global range, staged
+//     into shared memory with 16-byte cp.async copies (row stride padded by 4 floats so the
+//     128-bit operand reads of different rows spread across the bank groups);
+//   - forward: each thread owns a TB x TB register block of the Gram lower triangle and walks
+//     k in float4 steps; results are staged in shared memory so that the CTA's output, which
+//     is again one contiguous global range, is written fully coalesced;
+//   - backward: each thread owns 4 features x one float4 of k, reads one float4 of T and one
+//     float4 of S per j (16 FMAs per two 128-bit shared loads) and writes dT as float4.
+#include "common.cuh"
+
+namespace dlrmb {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+static inline int interaction_width(int F, int d, int pad_to_mul) {
+    int unpadded = d + F * (F - 1) / 2;
+    return (unpadded + pad_to_mul - 1) / pad_to_mul * pad_to_mul;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int TB>
+__global__ void __launch_bounds__(256)
+interaction_fwd_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int F, int d,
+                       int width, float* __restrict__ out, int NS, int nblk) {
+    extern __shared__ float4 smem4[];
+    const int d4 = d >> 2;
+    const int ldt4 = d4 + 1;              // row stride in float4 (4 floats of padding)
+    const int Fp = nblk * TB;             // rows incl. zero padding
+    const int nt = nblk * (nblk + 1) / 2; // register-block tasks per sample
+    float4* Ts = smem4;                                   // [NS][Fp][ldt4]
+    float* Os = reinterpret_cast<float*>(Ts + (size_t)NS * Fp * ldt4);  // [NS][width]
+    unsigned char* pr = reinterpret_cast<unsigned char*>(Os + (size_t)NS * width);  // [nt][2]
+
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * NS;
+    const int ns = min(NS, B - s0);
+
+    // block-pair table: task q -> (bi >= bj)
+    for (int q = tid; q < nt; q += blockDim.x) {
+        int bi = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
+        while (bi * (bi + 1) / 2 > q) --bi;
+        pr[2 * q] = (unsigned char)bi;
+        pr[2 * q + 1] = (unsigned char)(q - bi * (bi + 1) / 2);
+    }
+    // stage T (slot 0 from x when given), zero the padding rows
+    const int chunks = ns * Fp * d4;
+    for (int i = tid; i < chunks; i += blockDim.x) {
+        int c = i % d4;
+        int r = i / d4;
+        int f = r % Fp;
+        int s = r / Fp;
+        float4* dst = Ts + ((size_t)s * Fp + f) * ldt4 + c;
+        if (f < F) {
+            const float* src = (x != nullptr && f == 0) ? x + (size_t)(s0 + s) * d + 4 * c
+                                                        : T + ((size_t)(s0 + s) * F + f) * d + 4 * c;
+            cp_async16(dst, src);
+        } else {
+            *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // x passthrough: out[b][0:d] = T[b][0]; also fast_vcat into T when x came separately
+    for (int i = tid; i < ns * d4; i += blockDim.x) {
+        int c = i % d4, s = i / d4;
+        float4 v = Ts[(size_t)s * Fp * ldt4 + c];
+        float* o = Os + (size_t)s * width + 4 * c;
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        if (x != nullptr) reinterpret_cast<float4*>(T + (size_t)(s0 + s) * F * d)[c] = v;
+    }
+    const int npair = F * (F - 1) / 2;
+    for (int i = tid; i < ns * (width - d - npair); i += blockDim.x) {
+        int padw = width - d - npair;
+        int s = i / padw, c = i % padw;
+        Os[(size_t)s * width + d + npair + c] = 0.f;
+    }
+
+    // Gram blocks
+    for (int task = tid; task < ns * nt; task += blockDim.x) {
+        const int s = task / nt;
+        const int q = task - s * nt;
+        const int bi = pr[2 * q], bj = pr[2 * q + 1];
+        const float4* A = Ts + ((size_t)s * Fp + bi * TB) * ldt4;
+        const float4* Bm = Ts + ((size_t)s * Fp + bj * TB) * ldt4;
+        float acc[TB][TB];
+#pragma unroll
+        for (int r = 0; r < TB; ++r)
+#pragma unroll
+            for (int c = 0; c < TB; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < d4; ++k) {
+            float4 a[TB], b[TB];
+#pragma unroll
+            for (int r = 0; r < TB; ++r) a[r] = A[r * ldt4 + k];
+#pragma unroll
+            for (int c = 0; c < TB; ++c) b[c] = Bm[c * ldt4 + k];
+#pragma unroll
+            for (int r = 0; r < TB; ++r)
+#pragma unroll
+                for (int c = 0; c < TB; ++c) {
+                    float v = acc[r][c];
+                    v = fmaf(a[r].x, b[c].x, v);
+                    v = fmaf(a[r].y, b[c].y, v);
+                    v = fmaf(a[r].z, b[c].z, v);
+                    v = fmaf(a[r].w, b[c].w, v);
+                    acc[r][c] = v;
+                }
+        }
+        float* o = Os + (size_t)s * width + d;
+#pragma unroll
+        for (int r = 0; r < TB; ++r)
+#pragma unroll
+            for (int c = 0; c < TB; ++c) {
+                int j = bi * TB + r, i = bj * TB + c;
+                if (i < j && j < F) o[j * (j - 1) / 2 + i] = acc[r][c];
+            }
+    }
+    __syncthreads();
+
+    // coalesced store of the CTA's contiguous output range
+    float* og = out + (size_t)s0 * width;
+    const int total = ns * width;
+    for (int i = tid; i < total; i += blockDim.x) og[i] = Os[i];
+}
+
+// Any shape (d not a multiple of 4, unaligned buffers): one thread per output element.
+__global__ void __launch_bounds__(256)
+interaction_fwd_generic_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int F,
+                               int d, int width, float* __restrict__ out) {
+    const int npair = F * (F - 1) / 2;
+    const int64_t total = (int64_t)B * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int b = (int)(e / width);
+        int c = (int)(e - (int64_t)b * width);
+        const float* Tb = T + (size_t)b * F * d;
+        const float* r0 = x ? x + (size_t)b * d : Tb;
+        float v = 0.f;
+        if (c < d) {
+            v = r0[c];
+        } else if (c < d + npair) {
+            int m = c - d;
+            int j = (int)((sqrtf(8.f * m + 1.f) + 1.f) * 0.5f);
+            while (j * (j - 1) / 2 > m) --j;
+            while ((j + 1) * j / 2 <= m) ++j;
+            int i = m - j * (j - 1) / 2;
+            const float* ri = (i == 0) ? r0 : Tb + (size_t)i * d;
+            const float* rj = Tb + (size_t)j * d;
+            for (int k = 0; k < d; ++k) v = fmaf(ri[k], rj[k], v);
+        }
+        out[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+copy_x_into_slot0_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int F, int d) {
+    const int64_t total = (int64_t)B * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = e / d;
+        T[b * F * d + (e - b * d)] = x[e];
+    }
+}
+
+int ensure_smem_attr(const void* func, int bytes, unsigned long long* done_mask) {
+    int dev = 0;
+    DLRMB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(*done_mask & bit)) {
+        DLRMB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        *done_mask |= bit;
+    }
+    return DLRMB_OK;
+}
+
+struct TilePlan {
+    int ns, threads;
+    size_t smem;
+};
+
+// Pick samples-per-CTA and CTA size so the task count fills whole rounds of the CTA and at
+// least two CTAs fit an SM.
+static TilePlan plan_tiles(int B, int tasks_per_sample, size_t smem_per_sample, size_t smem_fixed,
+                           int sm_count) {
+    TilePlan best{1, 128, smem_per_sample + smem_fixed};
+    double best_score = -1.0;
+    const size_t budget = 100 * 1024;
+    for (int ns = 1; ns <= 32; ++ns) {
+        size_t smem = ns * smem_per_sample + smem_fixed;
+        if (smem > budget && ns > 1) break;
+        for (int threads = 128; threads <= 256; threads += 32) {
+            int tasks = ns * tasks_per_sample;
+            int rounds = (tasks + threads - 1) / threads;
+            double eff = (double)tasks / ((double)rounds * threads);
+            // prefer enough CTAs to cover the machine twice, then larger tiles
+            int64_t ctas = (B + ns - 1) / ns;
+            double fill = ctas >= 2 * sm_count ? 1.0 : (double)ctas / (2.0 * sm_count);
+            double score = eff * (0.5 + 0.5 * fill) + 0.002 * ns;
+            if (score > best_score) {
+                best_score = score;
+                best = TilePlan{ns, threads, smem};
+            }
+        }
+    }
+    return best;
+}
+
+template <int TB>
+static int launch_fwd_tb(float* T, const float* x, int B, int F, int d, int width, float* out,
+                         int sm_count, cudaStream_t s) {
+    const int nblk = (F + TB - 1) / TB;
+    const int nt = nblk * (nblk + 1) / 2;
+    const int Fp = nblk * TB;
+    size_t per_sample = ((size_t)Fp * (d / 4 + 1) * 4 + width) * sizeof(float);
+    size_t fixed = (size_t)nt * 2 + 16;
+    TilePlan p = plan_tiles(B, nt, per_sample, fixed, sm_count);
+    DLRMB_REQUIRE(p.smem <= 200 * 1024, "interaction tile needs %zu bytes of shared memory", p.smem);
+    static unsigned long long attr_done = 0;
+    int rc = ensure_smem_attr((const void*)interaction_fwd_kernel<TB>, 200 * 1024, &attr_done);
+    if (rc) return rc;
+    int grid = (B + p.ns - 1) / p.ns;
+    interaction_fwd_kernel<TB><<<grid, p.threads, p.smem, s>>>(T, x, B, F, d, width, out, p.ns, nblk);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+int launch_interaction_fwd(float* T, const float* x, int B, int F, int d, int pad_to_mul,
+                           float* out, int sm_count, cudaStream_t s) {
+    const int width = interaction_width(F, d, pad_to_mul);
+    const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(T) & 15) == 0) &&
+                         (x == nullptr || (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (!aligned || F < 2) {
+        int64_t total = (int64_t)B * width;
+        int64_t blocks = ceil_div64(total, 256);
+        if (blocks > sm_count * 16) blocks = sm_count * 16;
+        interaction_fwd_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(T, x, B, F, d, width, out);
+        DLRMB_LAUNCH_CHECK();
+        if (x != nullptr) {
+            int64_t b2 = ceil_div64((int64_t)B * d, 256);
+            if (b2 > sm_count * 16) b2 = sm_count * 16;
+            copy_x_into_slot0_kernel<<<(unsigned)b2, 256, 0, s>>>(T, x, B, F, d);
+            DLRMB_LAUNCH_CHECK();
+        }
+        return DLRMB_OK;
+    }
+    // register-block edge: the one that wastes the fewest FMAs on padding / diagonal blocks
+    auto cost = [&](int tb) {
+        int nb = (F + tb - 1) / tb;
+        return (double)(nb * (nb + 1) / 2) * tb * (tb + 1.5);
+    };
+    int tb = 2;
+    if (cost(3) < cost(tb)) tb = 3;
+    if (cost(4) < cost(tb)) tb = 4;
+    if (tb == 2) return launch_fwd_tb<2>(T, x, B, F, d, width, out, sm_count, s);
+    if (tb == 3) return launch_fwd_tb<3>(T, x, B, F, d, width, out, sm_count, s);
+    return launch_fwd_tb<4>(T, x, B, F, d, width, out, sm_count, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+interaction_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int F,
+                       int d, int width, float* __restrict__ dT, float* __restrict__ dx, int NS) {
+    extern __shared__ float4 smem4[];
+    const int d4 = d >> 2;
+    const int ldt4 = d4 + 1;
+    const int Fp = (F + 3) & ~3;   // S rows padded to a float4 multiple
+    const int nfb = Fp >> 2;
+    float4* Ts = smem4;                                           // [NS][F][ldt4]
+    float4* Ss = Ts + (size_t)NS * F * ldt4;                      // [NS][F][Fp/4]
+    float* Gs = reinterpret_cast<float*>(Ss + (size_t)NS * F * nfb);  // [NS][width]
+
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * NS;
+    const int ns = min(NS, B - s0);
+    const int npair = F * (F - 1) / 2;
+
+    // stage T (16-byte async copies) and dOut (contiguous, 4-byte aligned only)
+    for (int i = tid; i < ns * F * d4; i += blockDim.x) {
+        int c = i % d4, r = i / d4;
+        cp_async16(Ts + (size_t)r * ldt4 + c, T + ((size_t)s0 * F + r) * d + 4 * c);
+    }
+    const float* gg = dOut + (size_t)s0 * width;
+    for (int i = tid; i < ns * width; i += blockDim.x) Gs[i] = __ldg(gg + i);
+    cp_async_wait_all();
+    __syncthreads();
+
+    // S[j][f] = g[d + pair(j, f)], zero diagonal and zero padding columns
+    float* Sf = reinterpret_cast<float*>(Ss);
+    for (int i = tid; i < ns * F * Fp; i += blockDim.x) {
+        int f = i % Fp;
+        int r = i / Fp;
+        int j = r % F;
+        int s = r / F;
+        float v = 0.f;
+        if (f < F && f != j) {
+            int hi = max(j, f), lo = min(j, f);
+            v = Gs[(size_t)s * width + d + hi * (hi - 1) / 2 + lo];
+        }
+        Sf[i] = v;
+    }
+    __syncthreads();
+    (void)npair;
+
+    const int per_sample = nfb * d4;
+    for (int task = tid; task < ns * per_sample; task += blockDim.x) {
+        const int s = task / per_sample;
+        const int rem = task - s * per_sample;
+        const int fb = rem / d4;
+        const int k = rem - fb * d4;
+        const float4* Tp = Ts + (size_t)s * F * ldt4 + k;
+        const float4* Sp = Ss + (size_t)s * F * nfb + fb;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll 3
+        for (int j = 0; j < F; ++j) {
+            const float4 t = Tp[(size_t)j * ldt4];
+            const float4 sv = Sp[(size_t)j * nfb];
+            a0.x = fmaf(sv.x, t.x, a0.x); a0.y = fmaf(sv.x, t.y, a0.y); a0.z = fmaf(sv.x, t.z, a0.z); a0.w = fmaf(sv.x, t.w, a0.w);
+            a1.x = fmaf(sv.y, t.x, a1.x); a1.y = fmaf(sv.y, t.y, a1.y); a1.z = fmaf(sv.y, t.z, a1.z); a1.w = fmaf(sv.y, t.w, a1.w);
+            a2.x = fmaf(sv.z, t.x, a2.x); a2.y = fmaf(sv.z, t.y, a2.y); a2.z = fmaf(sv.z, t.z, a2.z); a2.w = fmaf(sv.z, t.w, a2.w);
+            a3.x = fmaf(sv.w, t.x, a3.x); a3.y = fmaf(sv.w, t.y, a3.y); a3.z = fmaf(sv.w, t.z, a3.z); a3.w = fmaf(sv.w, t.w, a3.w);
+        }
+        const int f0 = fb * 4;
+        float4* o = reinterpret_cast<float4*>(dT + ((size_t)(s0 + s) * F + f0) * d) + k;
+        o[0] = a0;
+        if (f0 + 1 < F) o[d4] = a1;
+        if (f0 + 2 < F) o[2 * d4] = a2;
+        if (f0 + 3 < F) o[3 * d4] = a3;
+        if (fb == 0) {
+            const float* g = Gs + (size_t)s * width + 4 * k;
+            float4 r = make_float4(__fadd_rn(g[0], a0.x), __fadd_rn(g[1], a0.y), __fadd_rn(g[2], a0.z), __fadd_rn(g[3], a0.w));
+            reinterpret_cast<float4*>(dx + (size_t)(s0 + s) * d)[k] = r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+interaction_bwd_generic_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B,
+                               int F, int d, int width, float* __restrict__ dT, float* __restrict__ dx) {
+    const int64_t total = (int64_t)B * F * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(e % d);
+        int64_t r = e / d;
+        int f = (int)(r % F);
+        int64_t b = r / F;
+        const float* g = dOut + b * width;
+        const float* Tb = T + b * F * d;
+        float acc = 0.f;
+        for (int j = 0; j < F; ++j) {
+            if (j == f) continue;
+            int hi = max(j, f), lo = min(j, f);
+            acc = fmaf(g[d + hi * (hi - 1) / 2 + lo], Tb[(size_t)j * d + k], acc);
+        }
+        dT[e] = acc;
+        if (f == 0) dx[b * d + k] = __fadd_rn(g[k], acc);
+    }
+}
+
+int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
+                           float* dT, float* dx, int sm_count, cudaStream_t s) {
+    const int width = interaction_width(F, d, pad_to_mul);
+    const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(T) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(dT) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+    if (!aligned) {
+        int64_t blocks = ceil_div64((int64_t)B * F * d, 256);
+        if (blocks > sm_count * 16) blocks = sm_count * 16;
+        interaction_bwd_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(dOut, T, B, F, d, width, dT, dx);
+        DLRMB_LAUNCH_CHECK();
+        return DLRMB_OK;
+    }
+    const int d4 = d / 4;
+    const int Fp = (F + 3) & ~3;
+    size_t per_sample = ((size_t)F * (d4 + 1) * 4 + (size_t)F * Fp + width) * sizeof(float);
+    TilePlan p = plan_tiles(B, (Fp / 4) * d4, per_sample, 16, sm_count);
+    DLRMB_REQUIRE(p.smem <= 200 * 1024, "interaction tile needs %zu bytes of shared memory", p.smem);
+    static unsigned long long attr_done = 0;
+    int rc = ensure_smem_attr((const void*)interaction_bwd_kernel, 200 * 1024, &attr_done);
+    if (rc) return rc;
+    int grid = (B + p.ns - 1) / p.ns;
+    interaction_bwd_kernel<<<grid, p.threads, p.smem, s>>>(dOut, T, B, F, d, width, dT, dx, p.ns);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+}  // namespace dlrmb

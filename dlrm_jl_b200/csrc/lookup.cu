@@ -1,0 +1,230 @@
+// Embedding lookup: gather + sum-pool of rows for every table in one launch.
+//
+// Replaces maplookup(PreallocationStrategy, tables, sparse) (DLRM.jl src/model/model.jl:161;
+// semantics pinned by test/model/model.jl:265-271 and the `concatenated_result` golden).
+//
+// HBM-bound: per (table, sample) one D*4-byte row read per pooled index and one D*4-byte
+// write.  Mapping: grid.y = table, and inside a table one thread per 16-byte chunk of an
+// output row (chunk index fastest), so a row is read and written by D/4 consecutive lanes as
+// whole 128-byte lines; the index of a row is fetched once per lane group through L1.
+// Memory-level parallelism comes from U independent (index -> row) chains per thread when
+// P == 1 and from a 4-deep unrolled pooling loop when P > 1.  The pooled sum runs in ascending
+// p, so results are bit-identical to the CPU restatement.
+#include "common.cuh"
+
+namespace dlrmb {
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> {
+    using type = float4;
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ float4 add(float4 a, float4 b) {
+        return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+    }
+};
+template <> struct Vec<1> {
+    using type = float;
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+
+// P == 1: plain gather.  U independent chains per thread.
+template <typename IdxT, int VEC, int U>
+__global__ void __launch_bounds__(256)
+lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
+                     uint32_t B, uint32_t C, float* __restrict__ out, int slots, int slot0) {
+    using V = typename Vec<VEC>::type;
+    const int k = blockIdx.y;
+    const float* __restrict__ tb = desc[k].base;
+    const IdxT* __restrict__ ik = idx + (size_t)k * B;
+    const uint32_t n = B * C;
+    const uint32_t step = gridDim.x * blockDim.x;
+    const size_t D = (size_t)C * VEC;
+    float* __restrict__ ob = out + (size_t)(slot0 + k) * D;
+    const size_t ostride = (size_t)slots * D;
+
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step * U) {
+        int64_t row[U];
+        uint32_t b[U], c[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t tt = t + (uint32_t)u * step;
+            ok[u] = tt < n;
+            b[u] = tt / C;
+            c[u] = tt - b[u] * C;
+            row[u] = ok[u] ? (int64_t)__ldg(ik + b[u]) - idx_base : 0;
+        }
+        V v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) v[u] = __ldg(reinterpret_cast<const V*>(tb + (size_t)row[u] * D) + c[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) reinterpret_cast<V*>(ob + (size_t)b[u] * ostride)[c[u]] = v[u];
+    }
+}
+
+// P > 1: gather + sum-pool, ascending p.
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256)
+lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
+                   uint32_t B, uint32_t P, uint32_t C, float* __restrict__ out, int slots, int slot0) {
+    using V = typename Vec<VEC>::type;
+    const int k = blockIdx.y;
+    const float* __restrict__ tb = desc[k].base;
+    const IdxT* __restrict__ ik = idx + (size_t)k * B * P;
+    const uint32_t n = B * C;
+    const uint32_t step = gridDim.x * blockDim.x;
+    const size_t D = (size_t)C * VEC;
+    float* __restrict__ ob = out + (size_t)(slot0 + k) * D;
+    const size_t ostride = (size_t)slots * D;
+
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step) {
+        const uint32_t b = t / C;
+        const uint32_t c = t - b * C;
+        const IdxT* __restrict__ ip = ik + (size_t)b * P;
+        V acc = Vec<VEC>::zero();
+        uint32_t p = 0;
+        for (; p + 4 <= P; p += 4) {
+            int64_t r0 = (int64_t)__ldg(ip + p) - idx_base;
+            int64_t r1 = (int64_t)__ldg(ip + p + 1) - idx_base;
+            int64_t r2 = (int64_t)__ldg(ip + p + 2) - idx_base;
+            int64_t r3 = (int64_t)__ldg(ip + p + 3) - idx_base;
+            V v0 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r0 * D) + c);
+            V v1 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r1 * D) + c);
+            V v2 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r2 * D) + c);
+            V v3 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r3 * D) + c);
+            acc = Vec<VEC>::add(acc, v0);
+            acc = Vec<VEC>::add(acc, v1);
+            acc = Vec<VEC>::add(acc, v2);
+            acc = Vec<VEC>::add(acc, v3);
+        }
+        for (; p < P; ++p) {
+            int64_t r = (int64_t)__ldg(ip + p) - idx_base;
+            acc = Vec<VEC>::add(acc, __ldg(reinterpret_cast<const V*>(tb + (size_t)r * D) + c));
+        }
+        reinterpret_cast<V*>(ob + (size_t)b * ostride)[c] = acc;
+    }
+}
+
+template <typename IdxT, int VEC>
+static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, float* out,
+                           int slots, int slot0, cudaStream_t s) {
+    const uint32_t C = t->D / VEC;
+    const int64_t n = (int64_t)B * C;
+    DLRMB_REQUIRE(n < (1ll << 30), "B * D too large for one lookup launch (%lld chunks)", (long long)n);
+    constexpr int U = 4;
+    const int per_block = 256 * (P == 1 ? U : 1);
+    int64_t bx = ceil_div64(n, per_block);
+    const int64_t cap = (int64_t)t->sm_count * 32;
+    if (bx * t->ntab > cap) bx = cap / t->ntab > 0 ? cap / t->ntab : 1;
+    dim3 grid((unsigned)bx, (unsigned)t->ntab);
+    if (P == 1)
+        lookup_gather_kernel<IdxT, VEC, U><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, out, slots, slot0);
+    else
+        lookup_pool_kernel<IdxT, VEC><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, out, slots, slot0);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+int launch_lookup(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                  float* out, int slots, int slot0, cudaStream_t s) {
+    const bool vec4 = (t->D % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (idx_bytes == 4) {
+        const uint32_t* p = static_cast<const uint32_t*>(idx);
+        return vec4 ? launch_lookup_t<uint32_t, 4>(t, p, idx_base, B, P, out, slots, slot0, s)
+                    : launch_lookup_t<uint32_t, 1>(t, p, idx_base, B, P, out, slots, slot0, s);
+    }
+    const int64_t* p = static_cast<const int64_t*>(idx);
+    return vec4 ? launch_lookup_t<int64_t, 4>(t, p, idx_base, B, P, out, slots, slot0, s)
+                : launch_lookup_t<int64_t, 1>(t, p, idx_base, B, P, out, slots, slot0, s);
+}
+
+// ---- ScaledUniform init (src/model/model.jl:61-65): U(-1/sqrt(rows), 1/sqrt(rows)) ------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+init_uniform_kernel(float* __restrict__ base, int64_t elems, float scale, uint64_t stream_seed) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += step) {
+        uint64_t h = mix64(stream_seed ^ mix64((uint64_t)i));
+        float u = (float)(h >> 40) * (1.0f / 16777216.0f);  // [0, 1) on 24 bits
+        base[i] = (2.0f * u - 1.0f) * scale;
+    }
+}
+
+int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s) {
+    for (int k = 0; k < t->ntab; ++k) {
+        int64_t elems = t->h_rows[k] * (int64_t)t->D;
+        float scale = 1.0f / sqrtf((float)t->h_rows[k]);
+        int64_t blocks = ceil_div64(elems, 256 * 8);
+        int64_t cap = (int64_t)t->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        uint64_t stream_seed = seed * 0x9E3779B97F4A7C15ull + (uint64_t)(k + 1) * 0xD1B54A32D192ED03ull;
+        init_uniform_kernel<<<(unsigned)blocks, 256, 0, s>>>(t->slab + t->h_offsets[k], elems, scale, stream_seed);
+        DLRMB_LAUNCH_CHECK();
+    }
+    return DLRMB_OK;
+}
+
+// ---- optional range check (the reference's hot loops are @inbounds; this is the debug aid) ---
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+check_indices_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
+                     int64_t L, unsigned long long* __restrict__ bad /* smallest (table << 40 | pos) */) {
+    const int k = blockIdx.y;
+    const int64_t rows = desc[k].rows;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += step) {
+        int64_t r = (int64_t)idx[(size_t)k * L + i] - idx_base;
+        if (r < 0 || r >= rows) {
+            unsigned long long code = ((unsigned long long)k << 40) | (unsigned long long)i;
+            atomicMin(&bad[0], code);
+        }
+    }
+}
+
+int launch_check_indices(dlrmb_tables* t, const void* d_idx, int idx_bytes, int idx_base, int B,
+                         int P, cudaStream_t s, long long* bad_table, long long* bad_pos,
+                         long long* bad_val) {
+    unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(t->d_uniq);  // scratch reuse
+    unsigned long long init[2] = {~0ull, 0ull};
+    DLRMB_CUDA(cudaMemcpyAsync(d_bad, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    const int64_t L = (int64_t)B * P;
+    int64_t bx = ceil_div64(L, 256 * 4);
+    if (bx > t->sm_count * 8) bx = t->sm_count * 8;
+    dim3 grid((unsigned)bx, (unsigned)t->ntab);
+    if (idx_bytes == 4)
+        check_indices_kernel<uint32_t><<<grid, 256, 0, s>>>(t->d_desc, (const uint32_t*)d_idx, idx_base, L, d_bad);
+    else
+        check_indices_kernel<int64_t><<<grid, 256, 0, s>>>(t->d_desc, (const int64_t*)d_idx, idx_base, L, d_bad);
+    DLRMB_LAUNCH_CHECK();
+    unsigned long long h[2];
+    DLRMB_CUDA(cudaMemcpyAsync(h, d_bad, sizeof(h), cudaMemcpyDeviceToHost, s));
+    DLRMB_CUDA(cudaStreamSynchronize(s));
+    if (h[0] == ~0ull) {
+        *bad_table = -1;
+        return DLRMB_OK;
+    }
+    *bad_table = (long long)(h[0] >> 40);
+    *bad_pos = (long long)(h[0] & ((1ull << 40) - 1));
+    const char* src = (const char*)d_idx + ((size_t)*bad_table * L + (size_t)*bad_pos) * idx_bytes;
+    int64_t v64 = 0;
+    uint32_t v32 = 0;
+    if (idx_bytes == 4) {
+        DLRMB_CUDA(cudaMemcpy(&v32, src, 4, cudaMemcpyDeviceToHost));
+        v64 = v32;
+    } else {
+        DLRMB_CUDA(cudaMemcpy(&v64, src, 8, cudaMemcpyDeviceToHost));
+    }
+    *bad_val = (long long)v64;
+    return DLRMB_OK;
+}
+
+}  // namespace dlrmb

@@ -1,0 +1,299 @@
+// Index sort / dedup for the sparse-gradient update.
+//
+// Role in the reference: EmbeddingTables.SparseIndexer, the per-table dictionary that
+// compacts duplicate row ids before EmbeddingTables.update! (DLRM.jl src/train/train.jl:107-115,
+// 276-290).  Here the dictionary is replaced by a stable sort of (row id, flat position) pairs per
+// table, which makes duplicates adjacent and fixes their accumulation order (ascending flat
+// position) so the update is deterministic without floating-point atomics.
+//
+// Two paths, chosen per call from L = B*P:
+//   * L <= kSmemSortMax: one CTA per table sorts (row id << 32 | position) composites with a
+//     bitonic network held entirely in shared memory; a single launch covers all tables.
+//   * larger L: least-significant-digit radix sort, 8-bit digits, tiles of 2048 keys, all tables
+//     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
+//     (digit, tile) -> stable scatter whose in-tile ranks come from warp match_any + per-warp
+//     digit counters in shared memory.  The sort arrays of a whole batch fit L2 (126 MB), so the
+//     passes run at L2 rather than HBM speed.
+// Output: keys[sorted_buf] (ascending 0-based row ids) and pos[sorted_buf] (the stable
+// permutation), both [ntab][max_lookups].
+#include "common.cuh"
+
+namespace dlrmb {
+
+// ---------------------------------------------------------------------------------------------
+// small path: bitonic sort in shared memory, one CTA per table
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(1024)
+sort_small_kernel(const IdxT* __restrict__ idx, int idx_base, int L, int n /* pow2 >= L */,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap) {
+    __shared__ unsigned long long sk[kSmemSortMax];
+    const int k = blockIdx.x;
+    const IdxT* __restrict__ ik = idx + (size_t)k * L;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned long long v = ~0ull;
+        if (i < L) {
+            uint32_t key = (uint32_t)((int64_t)ik[i] - idx_base);
+            v = ((unsigned long long)key << 32) | (uint32_t)i;
+        }
+        sk[i] = v;
+    }
+    __syncthreads();
+    const int half = n >> 1;
+    for (int kk = 2; kk <= n; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < half; i += blockDim.x) {
+                int lo = 2 * i - (i & (j - 1));
+                int hi = lo + j;
+                bool up = (lo & kk) == 0;
+                unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == up) {
+                    sk[lo] = b;
+                    sk[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    uint32_t* ko = keys_out + (size_t)k * cap;
+    uint32_t* po = pos_out + (size_t)k * cap;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        unsigned long long v = sk[i];
+        ko[i] = (uint32_t)(v >> 32);
+        po[i] = (uint32_t)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// large path: LSD radix sort
+// ---------------------------------------------------------------------------------------------
+constexpr int RT = 256;        // threads per CTA
+constexpr int RI = 8;          // keys per thread
+constexpr int RTILE = RT * RI; // keys per tile
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+radix_prepare_kernel(const IdxT* __restrict__ idx, int idx_base, int L, uint32_t* __restrict__ keys,
+                     uint32_t* __restrict__ pos, int64_t cap) {
+    const int k = blockIdx.y;
+    const int step = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += step) {
+        keys[(size_t)k * cap + i] = (uint32_t)((int64_t)idx[(size_t)k * L + i] - idx_base);
+        pos[(size_t)k * cap + i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(RT)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t cap, int L, int shift,
+                  uint32_t* __restrict__ tile_hist, int tiles) {
+    __shared__ uint32_t h[256];
+    const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const uint32_t* kin = keys + (size_t)k * cap;
+    const int base = tile * RTILE;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        int e = base + i * RT + tid;
+        if (e < L) atomicAdd(&h[(kin[e] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    tile_hist[((size_t)k * 256 + tid) * tiles + tile] = h[tid];
+}
+
+// exclusive scan, in place, over the 256*tiles counters of one table laid out [digit][tile]
+__global__ void __launch_bounds__(1024)
+radix_scan_kernel(uint32_t* __restrict__ tile_hist, int tiles) {
+    __shared__ uint32_t warp_tot[32];
+    uint32_t* h = tile_hist + (size_t)blockIdx.x * 256 * tiles;
+    const int n = 256 * tiles;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += h[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += v;
+        }
+        warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[w] + inc - sum;
+    for (int i = lo; i < hi; ++i) {
+        uint32_t v = h[i];
+        h[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(RT)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ pos_in,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap,
+                     int L, int shift, const uint32_t* __restrict__ tile_hist, int tiles) {
+    __shared__ uint32_t wh[RT / 32][256];
+    const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int w = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (RT / 32) * 256; i += RT) (&wh[0][0])[i] = 0;
+    __syncthreads();
+
+    const uint32_t* kin = keys_in + (size_t)k * cap;
+    const uint32_t* pin = pos_in + (size_t)k * cap;
+    const int base = tile * RTILE + w * (32 * RI);
+    uint32_t key[RI], val[RI], rank[RI];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        int e = base + i * 32 + lane;
+        bool valid = e < L;
+        key[i] = valid ? kin[e] : 0xffffffffu;
+        val[i] = valid ? pin[e] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        int e = base + i * 32 + lane;
+        bool valid = e < L;
+        uint32_t dig = valid ? ((key[i] >> shift) & 255u) : (256u + lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, dig);
+        uint32_t lt = peers & lt_mask;
+        uint32_t b = valid ? wh[w][dig] : 0u;
+        __syncwarp();
+        if (valid && lt == 0) wh[w][dig] = b + __popc(peers);
+        __syncwarp();
+        rank[i] = b + __popc(lt);
+    }
+    __syncthreads();
+    {
+        // thread d owns digit d: turn per-warp counts into per-warp global start offsets
+        uint32_t run = tile_hist[((size_t)k * 256 + tid) * tiles + tile];
+#pragma unroll
+        for (int ww = 0; ww < RT / 32; ++ww) {
+            uint32_t c = wh[ww][tid];
+            wh[ww][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    uint32_t* ko = keys_out + (size_t)k * cap;
+    uint32_t* po = pos_out + (size_t)k * cap;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        int e = base + i * 32 + lane;
+        if (e < L) {
+            uint32_t dst = wh[w][(key[i] >> shift) & 255u] + rank[i];
+            ko[dst] = key[i];
+            po[dst] = val[i];
+        }
+    }
+}
+
+static int radix_passes(int64_t max_rows) {
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) < max_rows) ++bits;
+    return (bits + 7) / 8;
+}
+
+template <typename IdxT>
+static int launch_sort_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, cudaStream_t s) {
+    const int64_t L64 = (int64_t)B * P;
+    const int L = (int)L64;
+    const int64_t cap = t->max_lookups;
+    if (L <= kSmemSortMax) {
+        int n = 2;
+        while (n < L) n <<= 1;
+        int threads = n / 2;
+        threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+        sort_small_kernel<IdxT><<<t->ntab, threads, 0, s>>>(idx, idx_base, L, n, t->keys[0], t->pos[0], cap);
+        DLRMB_LAUNCH_CHECK();
+        t->sorted_buf = 0;
+        return DLRMB_OK;
+    }
+    const int tiles = (int)ceil_div64(L, RTILE);
+    DLRMB_REQUIRE(tiles <= t->radix_tiles_cap, "internal: radix tile capacity exceeded");
+    {
+        int64_t bx = ceil_div64(L, 256 * 4);
+        if (bx > t->sm_count * 8) bx = t->sm_count * 8;
+        dim3 grid((unsigned)bx, (unsigned)t->ntab);
+        radix_prepare_kernel<IdxT><<<grid, 256, 0, s>>>(idx, idx_base, L, t->keys[0], t->pos[0], cap);
+        DLRMB_LAUNCH_CHECK();
+    }
+    const int passes = radix_passes(t->max_rows);
+    int cur = 0;
+    dim3 grid((unsigned)tiles, (unsigned)t->ntab);
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        radix_hist_kernel<<<grid, RT, 0, s>>>(t->keys[cur], cap, L, shift, t->tile_hist, tiles);
+        DLRMB_LAUNCH_CHECK();
+        radix_scan_kernel<<<t->ntab, 1024, 0, s>>>(t->tile_hist, tiles);
+        DLRMB_LAUNCH_CHECK();
+        radix_scatter_kernel<<<grid, RT, 0, s>>>(t->keys[cur], t->pos[cur], t->keys[cur ^ 1], t->pos[cur ^ 1],
+                                                 cap, L, shift, t->tile_hist, tiles);
+        DLRMB_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    t->sorted_buf = cur;
+    return DLRMB_OK;
+}
+
+int launch_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                cudaStream_t s) {
+    if (idx_bytes == 4) return launch_sort_t<uint32_t>(t, static_cast<const uint32_t*>(idx), idx_base, B, P, s);
+    return launch_sort_t<int64_t>(t, static_cast<const int64_t*>(idx), idx_base, B, P, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity export: unique ids + segment offsets of one table's sorted stream (single CTA)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+dedup_export_kernel(const uint32_t* __restrict__ keys, int L, int64_t* __restrict__ uniq,
+                    int32_t* __restrict__ seg, int32_t* __restrict__ n_uniq) {
+    __shared__ int warp_cnt[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < L; base += 1024) {
+        int i = base + tid;
+        bool head = i < L && (i == 0 || keys[i] != keys[i - 1]);
+        uint32_t bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        int before = running;
+        for (int ww = 0; ww < w; ++ww) before += warp_cnt[ww];
+        int total = 0;
+        for (int ww = 0; ww < 32; ++ww) total += warp_cnt[ww];
+        if (head) {
+            int o = before + __popc(bal & ((1u << lane) - 1u));
+            uniq[o] = (int64_t)keys[i];
+            seg[o] = i;
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        seg[running] = L;
+        *n_uniq = running;
+    }
+}
+
+int launch_dedup_export(dlrmb_tables* t, int k, cudaStream_t s) {
+    const int L = t->sorted_B * t->sorted_P;
+    dedup_export_kernel<<<1, 1024, 0, s>>>(t->keys[t->sorted_buf] + (size_t)k * t->max_lookups, L,
+                                           t->d_uniq, t->d_seg, t->d_nuniq);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+}  // namespace dlrmb

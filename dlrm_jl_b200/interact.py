@@ -1,0 +1,117 @@
+"""Host-side mirror of DLRM.jl's dot-interaction entry points (src/model/interact.jl).
+
+``DotInteraction`` is the callable stored in ``DLRMModel.interaction`` (src/model/model.jl:119,163);
+its ``torch.autograd.Function`` plays the role of ``ChainRulesCore.rrule(::DotInteraction, X, Y)``
+(src/model/interact.jl:438-447).  Forward and backward are single launches of the sm_100a
+kernels in csrc/interact.cu.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import _lib
+
+POST_INTERACTION_PAD_TO_MUL = 1  # src/model/model.jl:32
+
+
+def cdiv(x: int, y: int) -> int:
+    return 1 + (x - 1) // y
+
+
+def up_to_mul_of(x: int, y: int) -> int:
+    return y * cdiv(x, y)
+
+
+def interaction_width(F: int, d: int, pad_to_mul: int = POST_INTERACTION_PAD_TO_MUL) -> int:
+    """src/model/interact.jl:453-455."""
+    return up_to_mul_of(d + F * (F - 1) // 2, pad_to_mul)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return int(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.DLRMB200Error(_lib.EINVAL, "dot interaction runs on the GPU only (no CPU fallback)")
+
+
+class _DotInteractionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, T: torch.Tensor, pad_to_mul: int):
+        _require_cuda(x, T)
+        B, F, d = T.shape
+        assert T.is_contiguous() and T.dtype == torch.float32
+        xc = x.contiguous() if x is not None else None
+        assert xc is None or xc.shape == (B, d)
+        out = torch.empty((B, interaction_width(F, d, pad_to_mul)), dtype=torch.float32, device=T.device)
+        lib = _lib.load()
+        # fast_vcat (interact.jl:271-281) is fused: x lands in slot 0 of T inside the kernel
+        _lib.check(lib.dlrmb_interaction_fwd(
+            T.device.index or 0, T.data_ptr(), xc.data_ptr() if xc is not None else None,
+            B, F, d, pad_to_mul, out.data_ptr(), _stream(T)))
+        ctx.save_for_backward(T)
+        ctx.pad_to_mul = pad_to_mul
+        ctx.has_x = x is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut: torch.Tensor):
+        (T,) = ctx.saved_tensors
+        B, F, d = T.shape
+        dOut = dOut.contiguous()
+        dT = torch.empty_like(T)
+        dx = torch.empty((B, d), dtype=torch.float32, device=T.device)
+        lib = _lib.load()
+        _lib.check(lib.dlrmb_interaction_bwd(
+            T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
+            dT.data_ptr(), dx.data_ptr(), _stream(T)))
+        # (dx, dy): dy is the whole (d*F) x B matrix, slot 0 included (interact.jl:428-435)
+        return (dx if ctx.has_x else None), dT, None
+
+
+class DotInteraction:
+    """``DotInteraction`` (src/model/interact.jl:369-411).
+
+    ``dot(x, T)``: x [B][d] bottom-MLP output, T [B][F][d] the PreallocationStrategy lookup
+    buffer whose slot 0 is reserved for x.  Returns [B][d + F(F-1)/2 (+pad)].
+    """
+
+    def __init__(self, pad_to_mul: int = POST_INTERACTION_PAD_TO_MUL):
+        self.pad_to_mul = pad_to_mul
+
+    def __call__(self, x: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
+        return _DotInteractionFn.apply(x, T, self.pad_to_mul)
+
+
+def dot_interaction(x: torch.Tensor, ys: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Implementation-2 entry point (src/model/interact.jl:503-513): ``ys`` is a vector of
+    [B][D] matrices (DefaultStrategy).  Same kernels; the concat is one torch.stack."""
+    T = torch.stack([x, *ys], dim=1).contiguous()
+    return _DotInteractionFn.apply(None, T, POST_INTERACTION_PAD_TO_MUL)
+
+
+def interaction_fwd(T: torch.Tensor, x: torch.Tensor = None, pad_to_mul: int = 1) -> torch.Tensor:
+    """Raw forward launch (no autograd)."""
+    with torch.no_grad():
+        return _DotInteractionFn.apply(x, T, pad_to_mul)
+
+
+def interaction_bwd(dOut: torch.Tensor, T: torch.Tensor, pad_to_mul: int = 1):
+    """Raw backward launch: returns (dx, dT) as dot_back does (src/model/interact.jl:424-436)."""
+    _require_cuda(dOut, T)
+    B, F, d = T.shape
+    dT = torch.empty_like(T)
+    dx = torch.empty((B, d), dtype=torch.float32, device=T.device)
+    lib = _lib.load()
+    _lib.check(lib.dlrmb_interaction_bwd(
+        T.device.index or 0, dOut.contiguous().data_ptr(), T.data_ptr(), B, F, d, pad_to_mul,
+        dT.data_ptr(), dx.data_ptr(), _stream(T)))
+    return dx, dT
+
+
+__all__ = ["DotInteraction", "dot_interaction", "interaction_fwd", "interaction_bwd",
+           "interaction_width", "POST_INTERACTION_PAD_TO_MUL"]

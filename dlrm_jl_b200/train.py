@@ -1,0 +1,108 @@
+"""Training-step glue: the embedding branch of `custom_update!` and the step ordering of
+`train!` (src/train/train.jl:189-293), plus `bce_loss` and its rrule (:33-71).
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable, Iterable, List, Optional
+
+import torch
+
+from .embedding import Descent, sparse_updates, update_
+from .model import DLRMModel, callback, donothing
+
+_EPS32 = float(torch.finfo(torch.float32).eps)
+
+
+class _BCELoss(torch.autograd.Function):
+    """bce_loss + its hand-written pullback (src/train/train.jl:33-41 and :45-71):
+    forward clamps the logs at -100, backward uses the eps-regularised quotient."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, y: torch.Tensor):
+        ctx.save_for_backward(x, y)
+        lx = torch.clamp_min(torch.log(x), -100.0)
+        l1x = torch.clamp_min(torch.log(1.0 - x), -100.0)
+        return (-y * lx + (y - 1.0) * l1x).sum() / x.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        d = g / x.numel()
+        c = 1.0 - x + _EPS32
+        dd = x + _EPS32
+        return d * ((1.0 - y) / c - y / dd), None
+
+
+def bce_loss(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    return _BCELoss.apply(x, y)
+
+
+class LossWrapper:
+    """``wrap_loss(loss_fn; kw...)`` (src/train/train.jl:74-92)."""
+
+    def __init__(self, f: Callable, **kw):
+        self.f = f
+        self.kw = kw
+
+    def __call__(self, model: DLRMModel, labels, dense, sparse, training: bool = False):
+        cb = self.kw.get("cb", donothing)
+        out, T = model(dense, sparse, training=training, **self.kw)
+        loss = callback(cb, "loss", self.f, out, labels)
+        return loss, T
+
+
+def wrap_loss(loss_fn: Callable, **kw) -> LossWrapper:
+    return LossWrapper(loss_fn, **kw)
+
+
+def custom_update_(opt: Descent, model: DLRMModel, T: torch.Tensor, telemetry: Callable = donothing,
+                   presorted: bool = False) -> None:
+    """``custom_update!`` (src/train/train.jl:242-293): dense SGD, then the sparse embedding
+    update from the lookup buffer's gradient."""
+    params = [p for p in model.dense_parameters() if p.grad is not None]
+    with torch.no_grad():
+        torch._foreach_add_(params, [p.grad for p in params], alpha=-opt.eta)  # Flux.update!: x .-= eta*grad
+    telemetry("weight_update_done")
+    grads = sparse_updates(T.grad, T.indices, T.slot0, T.idx_base)
+    update_(opt, model.embeddings, grads, presorted=presorted)
+    telemetry("embedding_update_done")
+
+
+def train_step(loss: LossWrapper, model: DLRMModel, opt: Descent, labels, dense, sparse,
+               overlap_sort: bool = True) -> torch.Tensor:
+    """One iteration of the loop body of ``train!`` (src/train/train.jl:215-237).
+    Returns the loss tensor (device); no host synchronisation happens here."""
+    telemetry = loss.kw.get("cb", donothing)
+    telemetry("start")
+    for p in model.dense_parameters():
+        p.grad = None
+    l, T = loss(model, labels, dense, sparse, training=True)
+    if overlap_sort:
+        # the dedup sort needs the indices only: run it beside the backward pass
+        model.embeddings.sort(T.indices, T.idx_base, side_stream=True)
+    l.backward()
+    telemetry("grads_done")
+    custom_update_(opt, model, T, telemetry, presorted=overlap_sort)
+    telemetry("update_done")
+    return l.detach()
+
+
+def train(loss: LossWrapper, model: DLRMModel, data: Iterable, opt: Descent, cb: Callable = lambda: None,
+          maxiters: Optional[int] = None):
+    """``train!(loss, model, data, opt; cb, maxiters)`` (src/train/train.jl:189-240).
+    ``data`` yields (labels, dense, sparse).  Returns dict(iteration_times [ns], losses)."""
+    losses: List[float] = []
+    iteration_times: List[int] = []
+    count = 0
+    for labels, dense, sparse in data:
+        start = time.perf_counter_ns()
+        l = train_step(loss, model, opt, labels, dense, sparse)
+        losses.append(float(l))  # the reference pushes the loss every iteration (:231); this syncs
+        iteration_times.append(time.perf_counter_ns() - start)
+        count += 1
+        if maxiters is not None and count == maxiters:
+            break
+        cb()
+    cb()
+    return {"iteration_times": iteration_times, "losses": losses}

@@ -1,0 +1,139 @@
+/*
+ * dlrm_b200.h -- C ABI of libdlrm_b200.so: DLRM.jl's embedding + dot-interaction hot path
+ * as hand-written sm_100a CUDA kernels with device-resident (HBM) embedding tables.
+ *
+ * Every entry point is what a `ccall((:sym, libdlrm_b200), Int32, ...)` in DLRM.jl would
+ * bind in place of the Julia/EmbeddingTables.jl code cited next to it (paths relative to
+ * the DLRM.jl checkout).  No torch / C++ types cross this boundary: opaque handles, plain
+ * pointers, sizes.  All functions return a dlrmb_status (0 = ok); the message of the last
+ * failure on the calling thread is available from dlrmb_last_error().
+ *
+ * Conventions
+ *   - Arrays are C order.  A Julia `D x N` column-major matrix is the C array [N][D], so
+ *     Julia buffers can be passed unchanged.
+ *   - `idx`: table-major [ntab][B][P] (sample b of table k owns the P consecutive entries at
+ *     (k*B + b)*P); this is DACLoader's `sparse[B x ntab]` matrix (src/data/criteo.jl:320-326)
+ *     for P = 1 and load_inputs' `reshape(vec, :, B)` (src/data/criteo.jl:551-557) for P > 1.
+ *     `idx_bytes` is 4 (UInt32/Int32) or 8 (Int64); `idx_base` is 1 for Julia callers, 0 for
+ *     PyTorch-style callers.  Like the reference's `@inbounds` loops, the kernels do not
+ *     range-check indices; dlrmb_check_indices does, on request.
+ *   - Activations: `T` / `out` of the lookup is the PreallocationStrategy buffer
+ *     [B][slots][D] with the first `slot0` slots reserved for the bottom-MLP output
+ *     (slot0 = 1 in DLRM: src/model/model.jl:161, src/model/interact.jl:264-281).
+ *   - `stream` is a cudaStream_t (NULL = the legacy default stream).  Device-pointer entry
+ *     points are asynchronous on it; `_host` entry points take host buffers, copy in and out
+ *     on the tables' own stream and return after completion.
+ *   - Ownership: the library owns table storage and all workspaces (sized at
+ *     dlrmb_tables_create for `max_lookups` = max B*P per table; no per-call allocation);
+ *     activation buffers belong to the caller.  One host thread per handle at a time.
+ */
+#ifndef DLRM_B200_H
+#define DLRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlrmb_tables dlrmb_tables;
+typedef void* dlrmb_stream;
+
+typedef enum dlrmb_status {
+    DLRMB_OK = 0,
+    DLRMB_EINVAL = 1, /* bad argument (the reference raises AssertionError / BoundsError) */
+    DLRMB_ECUDA = 2,  /* CUDA runtime failure; message carries cudaGetErrorString */
+    DLRMB_ENOMEM = 3, /* device allocation failed */
+    DLRMB_EOOB = 4,   /* dlrmb_check_indices found an index outside [base, rows+base) */
+    DLRMB_ESTATE = 5  /* call order violated (e.g. update_sorted without a sort) */
+} dlrmb_status;
+
+#define DLRMB_ABI_VERSION 1
+
+int32_t dlrmb_abi_version(void);
+const char* dlrmb_last_error(void);
+/* Number of kernel launches issued by this library in this process (bench bookkeeping). */
+int64_t dlrmb_launch_count(void);
+
+/* ---- table storage: replaces SimpleEmbedding{Static{D}}(data) on an `embedding_allocator`
+ * array (src/model/model.jl:185-206, src/data/criteo.jl:413,490) and the CachedArrays-backed
+ * storage of src/cachedarrays.jl with HBM-resident tables. ------------------------------- */
+int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
+                            int64_t max_lookups, dlrmb_tables** out);
+int32_t dlrmb_tables_destroy(dlrmb_tables* t);
+int32_t dlrmb_tables_info(const dlrmb_tables* t, int32_t* ntab, int32_t* D, int64_t* max_lookups,
+                          int64_t* total_rows);
+/* host [rows_k][D] f32 <-> device; `Array(table)` / `table.data` read-back
+ * (src/validation.jl:138) and load_embeddings (src/data/criteo.jl:484-492). */
+int32_t dlrmb_tables_upload(dlrmb_tables* t, int32_t k, const float* host);
+int32_t dlrmb_tables_download(dlrmb_tables* t, int32_t k, float* host);
+/* Device base pointer of table k ([rows_k][D] f32), for zero-copy views. */
+int32_t dlrmb_tables_device_ptr(dlrmb_tables* t, int32_t k, float** dev);
+/* ScaledUniform init, U(-1/sqrt(rows_k), 1/sqrt(rows_k)) (src/model/model.jl:61-65), from a
+ * counter-based generator so the result depends only on (seed, k, row, col). */
+int32_t dlrmb_tables_init_uniform(dlrmb_tables* t, uint64_t seed, dlrmb_stream stream);
+int32_t dlrmb_tables_sync(dlrmb_tables* t);
+
+/* ---- lookup: maplookup(PreallocationStrategy(slot0*D), tables, sparse)
+ * (call site src/model/model.jl:161).  out[b][slot0+k][:] = sum_p table_k[idx[k][b][p]][:],
+ * p ascending.  One launch covers every table. ------------------------------------------- */
+int32_t dlrmb_embedding_fwd(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                            int32_t B, int32_t P, float* out, int32_t slots, int32_t slot0,
+                            dlrmb_stream stream);
+
+/* ---- dot interaction: (dot::DotInteraction)(x, ys) and its rrule
+ * (src/model/interact.jl:394-411, 438-447).  T is [B][F][d] with slot 0 = x.  If `x` is
+ * non-NULL ([B][d]) it is used for slot 0 and also stored into T[b][0] (the fast_vcat of
+ * :271-281, fused).  out is [B][d + F(F-1)/2 + pad], pad = padding to `pad_to_mul`
+ * (POST_INTERACTION_PAD_TO_MUL, src/model/model.jl:32). ---------------------------------- */
+int32_t dlrmb_interaction_fwd(int32_t device, float* T, const float* x, int32_t B, int32_t F,
+                              int32_t d, int32_t pad_to_mul, float* out, dlrmb_stream stream);
+/* dot_back (src/model/interact.jl:424-436): dT [B][F][d] (slot 0 included, as the reference
+ * returns the whole (d*F) x B matrix) and dx [B][d] = dOut[:, :d] + dT[:, 0]. */
+int32_t dlrmb_interaction_bwd(int32_t device, const float* dOut, const float* T, int32_t B,
+                              int32_t F, int32_t d, int32_t pad_to_mul, float* dT, float* dx,
+                              dlrmb_stream stream);
+
+/* ---- sparse SGD: lookup pullback -> SparseEmbeddingUpdate(delta = dT[:, slot0+k, :],
+ * indices) (src/train/train.jl:144) followed by EmbeddingTables.update!(Flux.Descent(lr), ...)
+ * (src/train/train.jl:283-290): table_k[r] -= lr * sum_{(b,p): idx=r} dT[b][slot0+k],
+ * duplicates summed in ascending flat position, one read-modify-write per touched row.
+ *
+ * dlrmb_embedding_sort depends on the indices only (it may run on a side stream while the
+ * forward/backward passes execute); dlrmb_embedding_update_sorted consumes its result.
+ * dlrmb_embedding_bwd_sgd = both, on one stream. ----------------------------------------- */
+int32_t dlrmb_embedding_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                             int32_t B, int32_t P, dlrmb_stream stream);
+int32_t dlrmb_embedding_update_sorted(dlrmb_tables* t, const float* dT, int32_t slots,
+                                      int32_t slot0, float lr, dlrmb_stream stream);
+int32_t dlrmb_embedding_bwd_sgd(dlrmb_tables* t, const void* idx, int32_t idx_bytes,
+                                int32_t idx_base, int32_t B, int32_t P, const float* dT,
+                                int32_t slots, int32_t slot0, float lr, dlrmb_stream stream);
+
+/* Parity/debug export of the last sort for table k (host outputs; the SparseIndexer role,
+ * src/train/train.jl:107-115,276-281): uniq[n_uniq] ascending 0-based row ids,
+ * seg_offsets[n_uniq+1] exclusive prefix of multiplicities, perm[B*P] stable argsort of the
+ * flat [B][P] index list.  Buffers must hold B*P (+1) entries.  Synchronises. */
+int32_t dlrmb_sort_dedup_export(dlrmb_tables* t, int32_t k, int64_t* uniq, int32_t* seg_offsets,
+                                int32_t* perm, int32_t* n_uniq);
+/* Range check of a device or host index batch; DLRMB_EOOB + message on the first offender. */
+int32_t dlrmb_check_indices(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                            int32_t B, int32_t P, int32_t idx_on_host);
+
+/* ---- host-buffer entry points: every pointer is host memory (pageable or pinned); this is
+ * the form a CPU-resident DLRM.jl model calls.  Copies run inside the call. -------------- */
+int32_t dlrmb_embedding_fwd_host(dlrmb_tables* t, const void* idx, int32_t idx_bytes,
+                                 int32_t idx_base, int32_t B, int32_t P, float* out,
+                                 int32_t slots, int32_t slot0);
+int32_t dlrmb_interaction_fwd_host(dlrmb_tables* t, float* T, const float* x, int32_t B, int32_t F,
+                                   int32_t d, int32_t pad_to_mul, float* out);
+int32_t dlrmb_interaction_bwd_host(dlrmb_tables* t, const float* dOut, const float* T, int32_t B,
+                                   int32_t F, int32_t d, int32_t pad_to_mul, float* dT, float* dx);
+int32_t dlrmb_embedding_bwd_sgd_host(dlrmb_tables* t, const void* idx, int32_t idx_bytes,
+                                     int32_t idx_base, int32_t B, int32_t P, const float* dT,
+                                     int32_t slots, int32_t slot0, float lr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLRM_B200_H */

@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol the
+header declares, the ctypes binding covers all of them, and the host-side helpers behave.
+No compute call is made (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dlrm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dlrmb_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from dlrm_jl_b200.csrc import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dlrm_b200.h but not exported"
+
+
+def test_binding_covers_header_exactly(built_lib):
+    from dlrm_jl_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    lib = _lib.load()
+    assert lib.dlrmb_abi_version() == 1
+    assert isinstance(lib.dlrmb_launch_count(), int)
+
+
+def test_argument_validation_needs_no_gpu(built_lib):
+    from dlrm_jl_b200 import _lib
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    rows = (ctypes.c_int64 * 1)(10)
+    rc = lib.dlrmb_tables_create(0, 0, rows, 16, 128, ctypes.byref(out))   # ntab = 0
+    assert rc == _lib.EINVAL and b"ntab" in lib.dlrmb_last_error()
+    rc = lib.dlrmb_tables_create(0, 1, rows, 3000, 128, ctypes.byref(out))  # bad D
+    assert rc == _lib.EINVAL and b"D must be" in lib.dlrmb_last_error()
+    rc = lib.dlrmb_interaction_fwd(0, None, None, 4, 8, 16, 1, None, None)
+    assert rc == _lib.EINVAL
+    with pytest.raises(_lib.DLRMB200Error, match="DLRMB_EINVAL"):
+        _lib.check(rc)
+
+
+def test_product_path_has_no_cpu_fallback(built_lib):
+    from dlrm_jl_b200 import DLRMB200Error
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    from dlrm_jl_b200.interact import interaction_fwd
+    with pytest.raises(DLRMB200Error):
+        EmbeddingTables([10], 16, 8, torch.device("cpu"))
+    with pytest.raises(DLRMB200Error):
+        interaction_fwd(torch.zeros(2, 3, 4))
+    # and nothing in the package imports the oracle
+    pkg = os.path.join(ROOT, "dlrm_jl_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f
+
+
+def test_index_normalisation_and_widths():
+    from dlrm_jl_b200.embedding import _as_index_tensor
+    from dlrm_jl_b200.interact import interaction_width
+    cpu = torch.device("cpu")
+    a = _as_index_tensor([np.arange(4), np.arange(4)], 2, cpu)
+    assert a.shape == (2, 4, 1) and a.dtype == torch.int64
+    b = _as_index_tensor(np.zeros((3, 5, 2), dtype=np.int32), 3, cpu)
+    assert b.shape == (3, 5, 2) and b.dtype == torch.int32
+    c = _as_index_tensor([np.zeros((6, 10), dtype=np.int64)] * 7, 7, cpu)   # multi golden: P = 10
+    assert c.shape == (7, 6, 10)
+    with pytest.raises(ValueError):
+        _as_index_tensor(np.zeros((2, 4), dtype=np.int64), 3, cpu)
+    assert interaction_width(27, 64) == 415 and interaction_width(8, 16) == 44
+    assert interaction_width(27, 128) == 479 and interaction_width(27, 64, 8) == 416
+
+
+def test_model_constants_match_reference():
+    from dlrm_jl_b200.model import KAGGLE_EMBEDDING_SIZES, TERABYTE_EMBEDDING_SIZES
+    assert len(KAGGLE_EMBEDDING_SIZES) == 26 and sum(KAGGLE_EMBEDDING_SIZES) == 33762577
+    assert len(TERABYTE_EMBEDDING_SIZES) == 26
+    assert sum(min(r, 40_000_000) for r in TERABYTE_EMBEDDING_SIZES) == 204184588

@@ -1,0 +1,471 @@
+"""Parity of the sm_100a kernels (through the C ABI) against the CPU oracle and the goldens.
+
+Tolerances (BASELINE.json north_star): bit-exact for index sort / dedup / segment offsets and
+for the lookup (pure copies and ordered fp32 adds); rel 1e-5 (2-norm) for the interaction
+forward/backward; rel 1e-4 for tables after N SGD steps.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.helpers import golden_model, golden_updates, load_golden, load_known_answer
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+FWD_RTOL = 1e-5
+SGD_RTOL = 1e-4
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _tables(arrays, max_lookups):
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    return EmbeddingTables.from_arrays(arrays, max_lookups, 0)
+
+
+def _rand_tables(rng, rows, D):
+    return [rng.standard_normal((r, D)).astype(np.float32) for r in rows]
+
+
+# ------------------------------------------------------------------------------------------------
+# lookup
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["single", "multi"])
+def test_lookup_golden_concatenated_result(name):
+    from dlrm_jl_b200.embedding import PreallocationStrategy, maplookup
+    g = load_golden(name)
+    _bot, _top, tables, _dense, idx, _labels = golden_model(g)
+    t = _tables(tables, idx[0].size)
+    T = maplookup(PreallocationStrategy(16), t, idx).cpu().numpy()
+    ref = O.lookup(tables, idx, slot0=1)
+    assert np.array_equal(T, ref)                                    # bit-exact vs oracle
+    assert np.all(T[:, 0] == 0)                                      # slot 0 reserved for x
+    assert O.rel_err(T[:, 1:], g["concatenated_result"][:, 1:]) < FWD_RTOL   # vs PyTorch golden
+
+
+@pytest.mark.parametrize("D", [4, 10, 16, 48, 64, 128, 256])
+@pytest.mark.parametrize("P", [1, 3, 10])
+def test_lookup_random_bit_exact(D, P):
+    from dlrm_jl_b200.embedding import PreallocationStrategy, maplookup
+    rng = np.random.default_rng(D * 100 + P)
+    rows = [7, 1000, 33, 5000]
+    tables = _rand_tables(rng, rows, D)
+    for B, dtype, base in [(1, np.int64, 0), (3, np.int32, 1), (257, np.int64, 1), (1024, np.int32, 0)]:
+        idx = [rng.integers(0, r, size=(B, P)) for r in rows]
+        t = _tables(tables, B * P)
+        dev_idx = np.stack(idx).astype(dtype) + base
+        T = maplookup(PreallocationStrategy(D), t, dev_idx, idx_base=base).cpu().numpy()
+        assert np.array_equal(T, O.lookup(tables, idx, slot0=1)), (B, dtype, base)
+        t.close()
+
+
+def test_lookup_default_strategy_and_identity_rows():
+    from dlrm_jl_b200.embedding import DefaultStrategy, maplookup
+    rng = np.random.default_rng(5)
+    tables = _rand_tables(rng, [64, 64], 32)
+    idx = [np.arange(64), np.arange(64)[::-1].copy()]
+    t = _tables(tables, 64)
+    ys = maplookup(DefaultStrategy(), t, idx)
+    assert len(ys) == 2
+    assert np.array_equal(ys[0].cpu().numpy(), tables[0])
+    assert np.array_equal(ys[1].cpu().numpy(), tables[1][::-1])
+
+
+def test_lookup_host_entry_point():
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    rng = np.random.default_rng(6)
+    tables = _rand_tables(rng, [100, 50, 9], 64)
+    t = _tables(tables, 40)
+    idx = [rng.integers(0, r, size=(20, 2)) for r in [100, 50, 9]]
+    flat = np.ascontiguousarray(np.stack(idx).astype(np.int64) + 1)   # Julia-style 1-based Int64
+    out = np.zeros((20, 4, 64), dtype=np.float32)
+    out[:, 0] = 7.0
+    _lib.check(_lib.load().dlrmb_embedding_fwd_host(
+        t._h, flat.ctypes.data_as(C.c_void_p), 8, 1, 20, 2, out.ctypes.data_as(C.c_void_p), 4, 1))
+    ref = O.lookup(tables, idx, slot0=1)
+    assert np.array_equal(out[:, 1:], ref[:, 1:])
+    assert np.all(out[:, 0] == 7.0)
+
+
+def test_index_range_check_reports_offender():
+    from dlrm_jl_b200 import DLRMB200Error
+    t = _tables([np.zeros((10, 8), np.float32), np.zeros((5, 8), np.float32)], 16)
+    good = torch.tensor([[0, 9, 3], [4, 0, 1]], dtype=torch.int64, device=_dev()).unsqueeze(-1)
+    t.check_indices(good)
+    bad = good.clone()
+    bad[1, 2, 0] = 5
+    with pytest.raises(DLRMB200Error, match="table 1"):
+        t.check_indices(bad)
+
+
+def test_errors_are_loud():
+    from dlrm_jl_b200 import DLRMB200Error
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    with pytest.raises(DLRMB200Error):
+        EmbeddingTables([10], 2000, 16, 0)               # unsupported D
+    t = EmbeddingTables([10], 8, 16, 0)
+    idx = torch.zeros((1, 32, 1), dtype=torch.int64, device=_dev())
+    out = torch.zeros((32, 1, 8), device=_dev())
+    with pytest.raises(DLRMB200Error, match="max_lookups"):
+        t.lookup(idx, out, 0)
+    with pytest.raises(DLRMB200Error, match="without a preceding"):
+        t.update_sorted(out[:16].contiguous(), 0, 0.1)
+
+
+# ------------------------------------------------------------------------------------------------
+# interaction
+# ------------------------------------------------------------------------------------------------
+SHAPES = [  # (B, F, d)
+    (4, 4, 4),        # known-answer geometry (test/model/model.jl)
+    (128, 8, 16),     # golden geometry
+    (300, 27, 64),    # Kaggle-shaped, ragged batch
+    (64, 27, 128),    # Terabyte-shaped
+    (130, 11, 128),   # reference test: x 128 wide, 10 ys (test/model/interact.jl:166)
+    (33, 21, 256),    # reference test: implementation 2, 256 wide, 20 ys (:244)
+    (10, 6, 10),      # d not a multiple of 4 -> generic path (:196)
+    (5, 1, 16),       # no pairs
+    (7, 2, 8),
+    (1, 100, 128),    # process_slice! test geometry (:149)
+]
+
+
+@pytest.mark.parametrize("B,F,d", SHAPES)
+def test_interaction_forward_vs_oracle(B, F, d):
+    from dlrm_jl_b200.interact import interaction_fwd
+    rng = np.random.default_rng(B * 1000 + F * 10 + d)
+    T = rng.standard_normal((B, F, d)).astype(np.float32)
+    ref = O.interaction_fwd(T)
+    out = interaction_fwd(torch.from_numpy(T).to(_dev())).cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.array_equal(out[:, :d], T[:, 0])
+    assert O.rel_err(out, ref) < FWD_RTOL
+    # x handed separately: slot 0 of T is filled by the kernel (fused fast_vcat)
+    Tz = T.copy()
+    Tz[:, 0] = 0
+    Td = torch.from_numpy(Tz).to(_dev())
+    out2 = interaction_fwd(Td, torch.from_numpy(T[:, 0].copy()).to(_dev())).cpu().numpy()
+    assert np.array_equal(out2, out)
+    assert np.array_equal(Td.cpu().numpy(), T)
+
+
+def test_interaction_forward_integer_exact_and_padding():
+    from dlrm_jl_b200.interact import interaction_fwd
+    rng = np.random.default_rng(11)
+    T = rng.integers(-4, 5, size=(50, 27, 64)).astype(np.float32)     # integer Gram is exact in fp32
+    for pad in (1, 8, 64):
+        ref = O.interaction_fwd(T, pad)
+        out = interaction_fwd(torch.from_numpy(T).to(_dev()), pad_to_mul=pad).cpu().numpy()
+        assert out.shape == ref.shape and out.shape[1] % pad == 0
+        assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("name", ["single", "multi"])
+def test_interaction_forward_golden(name):
+    from dlrm_jl_b200.interact import interaction_fwd
+    g = load_golden(name)
+    out = interaction_fwd(torch.from_numpy(g["concatenated_result"]).to(_dev())).cpu().numpy()
+    assert O.rel_err(out, g["output_interaction"]) < FWD_RTOL
+    assert O.rel_err(out[:, 16:], g["zflat"]) < FWD_RTOL
+
+
+@pytest.mark.parametrize("B,F,d", SHAPES)
+def test_interaction_backward_vs_oracle(B, F, d):
+    from dlrm_jl_b200.interact import interaction_bwd, interaction_width
+    rng = np.random.default_rng(B * 7 + F * 3 + d)
+    T = rng.standard_normal((B, F, d)).astype(np.float32)
+    for pad in (1, 16):
+        w = interaction_width(F, d, pad)
+        g = rng.standard_normal((B, w)).astype(np.float32)
+        dx_ref, dT_ref = O.interaction_bwd(g, T, w - d - F * (F - 1) // 2)
+        dx, dT = interaction_bwd(torch.from_numpy(g).to(_dev()), torch.from_numpy(T).to(_dev()), pad)
+        assert O.rel_err(dT.cpu().numpy(), dT_ref) < FWD_RTOL or F == 1
+        assert O.rel_err(dx.cpu().numpy(), dx_ref) < FWD_RTOL
+        if F == 1:
+            assert np.all(dT.cpu().numpy() == 0)
+
+
+def test_interaction_autograd_matches_reference_pullback_shape():
+    """rrule contract (interact.jl:438-447): returns dx and the whole dT, slot 0 included."""
+    from dlrm_jl_b200.interact import DotInteraction
+    rng = np.random.default_rng(3)
+    B, F, d = 64, 11, 128
+    Tn = rng.standard_normal((B, F, d)).astype(np.float32)
+    x = torch.from_numpy(Tn[:, 0].copy()).to(_dev()).requires_grad_(True)
+    T = torch.from_numpy(Tn).to(_dev()).requires_grad_(True)
+    z = DotInteraction()(x, T)
+    gn = rng.standard_normal(tuple(z.shape)).astype(np.float32)
+    z.backward(torch.from_numpy(gn).to(_dev()))
+    dx_ref, dT_ref = O.interaction_bwd(gn, Tn)
+    assert O.rel_err(x.grad.cpu().numpy(), dx_ref) < FWD_RTOL
+    assert O.rel_err(T.grad.cpu().numpy(), dT_ref) < FWD_RTOL
+
+
+def test_interaction_host_entry_points():
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    rng = np.random.default_rng(8)
+    t = _tables([np.zeros((4, 16), np.float32)], 4)
+    B, F, d = 37, 8, 16
+    T = rng.standard_normal((B, F, d)).astype(np.float32)
+    out = np.empty((B, d + 28), dtype=np.float32)
+    lib = _lib.load()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.dlrmb_interaction_fwd_host(t._h, p(T), None, B, F, d, 1, p(out)))
+    assert O.rel_err(out, O.interaction_fwd(T)) < FWD_RTOL
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    dT = np.empty_like(T)
+    dx = np.empty((B, d), dtype=np.float32)
+    _lib.check(lib.dlrmb_interaction_bwd_host(t._h, p(g), p(T), B, F, d, 1, p(dT), p(dx)))
+    dx_ref, dT_ref = O.interaction_bwd(g, T)
+    assert O.rel_err(dT, dT_ref) < FWD_RTOL and O.rel_err(dx, dx_ref) < FWD_RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# sort / dedup (bit-exact integers)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,rows", [(1, 5), (2, 2), (128, 1000), (1280, 1000), (2048, 3), (2048, 10131227),
+                                    (4096, 50), (4097, 50), (5000, 100000), (70000, 7), (1 << 16, 1 << 20),
+                                    (200000, 40000000)])
+@pytest.mark.parametrize("dtype,base", [(np.int32, 0), (np.int64, 1)])
+def test_sort_dedup_bit_exact(L, rows, dtype, base):
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    rng = np.random.default_rng(L + rows)
+    row_list = [rows, max(2, rows // 3)]
+    t = EmbeddingTables(row_list, 4, L, 0)
+    idx = np.stack([rng.integers(0, r, size=L) for r in row_list])
+    dev = torch.from_numpy((idx + base).astype(dtype)).to(_dev()).reshape(2, L, 1)
+    t.sort(dev, base)
+    for k in range(2):
+        uniq, seg, perm = t.sort_dedup_export(k, L)
+        u_ref, s_ref, p_ref = O.sort_dedup(idx[k])
+        assert np.array_equal(uniq, u_ref)
+        assert np.array_equal(seg, s_ref)
+        assert np.array_equal(perm, p_ref)
+    t.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse SGD update
+# ------------------------------------------------------------------------------------------------
+def _run_update(tables_np, idx, dT, slot0, lr, steps=1):
+    t = _tables(tables_np, idx[0].size)
+    dev_idx = torch.from_numpy(np.stack([i.reshape(i.shape[0], -1) for i in idx])).to(_dev())
+    g = torch.from_numpy(dT).to(_dev())
+    for _ in range(steps):
+        t.bwd_sgd(dev_idx, g, slot0, lr)
+    out = [t.download(k) for k in range(len(tables_np))]
+    t.close()
+    return out
+
+
+@pytest.mark.parametrize("D", [4, 10, 16, 64, 128, 256])
+@pytest.mark.parametrize("B,P,rows", [(128, 1, [1000, 3, 57]), (2048, 1, [3, 10131227 // 1000, 24]),
+                                      (128, 10, [1000, 5, 300]), (3000, 3, [4, 100000, 11]),
+                                      (5, 1, [2, 2, 2])])
+def test_sparse_sgd_vs_oracle(D, B, P, rows):
+    rng = np.random.default_rng(D + B + P)
+    tables = _rand_tables(rng, rows, D)
+    idx = [rng.integers(0, r, size=(B, P)) for r in rows]
+    dT = rng.standard_normal((B, 1 + len(rows), D)).astype(np.float32)
+    got = _run_update(tables, idx, dT, 1, 0.1, steps=3)
+    ref = [tb.copy() for tb in tables]
+    for _ in range(3):
+        for k in range(len(rows)):
+            O.sparse_sgd_update_fast(ref[k], idx[k], np.ascontiguousarray(dT[:, 1 + k]), 0.1)
+    for k in range(len(rows)):
+        assert O.rel_err(got[k], ref[k]) < SGD_RTOL, k
+        assert not np.array_equal(got[k], tables[k]), "update must change the table"
+        untouched = np.setdiff1d(np.arange(rows[k]), np.unique(idx[k]))
+        assert np.array_equal(got[k][untouched], tables[k][untouched]), "untouched rows must be bit-identical"
+
+
+def test_sparse_sgd_is_deterministic_and_matches_ordered_sum():
+    rng = np.random.default_rng(42)
+    rows, D, B = [3, 17, 5000], 64, 4096 + 123
+    tables = _rand_tables(rng, rows, D)
+    # Zipf-like skew: a few very hot rows
+    idx = [np.minimum((rng.pareto(1.05, size=(B, 1)) * 1.0).astype(np.int64), r - 1) for r in rows]
+    dT = rng.standard_normal((B, len(rows), D)).astype(np.float32)
+    a = _run_update(tables, idx, dT, 0, 0.5)
+    b = _run_update(tables, idx, dT, 0, 0.5)
+    for k in range(len(rows)):
+        assert np.array_equal(a[k], b[k]), "run-to-run bitwise reproducibility"
+        ref = tables[k].copy()
+        O.sparse_sgd_update_fast(ref, idx[k], np.ascontiguousarray(dT[:, k]), 0.5)
+        assert O.rel_err(a[k], ref) < SGD_RTOL
+
+
+def test_sparse_sgd_radix_path_hot_rows():
+    """L above the shared-memory sort limit: radix path + runs spanning thousands of tiles."""
+    rng = np.random.default_rng(9)
+    rows, D, B = [2, 100000], 16, 70000
+    tables = _rand_tables(rng, rows, D)
+    idx = [rng.integers(0, r, size=(B, 1)) for r in rows]
+    dT = (rng.standard_normal((B, 2, D)) * 0.01).astype(np.float32)
+    got = _run_update(tables, idx, dT, 0, 1.0)
+    for k in range(2):
+        ref = tables[k].copy()
+        O.sparse_sgd_update_fast(ref, idx[k], np.ascontiguousarray(dT[:, k]), 1.0)
+        assert O.rel_err(got[k], ref) < SGD_RTOL
+        dense = O.uncompress(np.ascontiguousarray(dT[:, k]), idx[k], rows[k]) if rows[k] < 10 else None
+        if dense is not None:
+            assert np.allclose(got[k], tables[k] - dense, rtol=1e-3, atol=1e-3)
+
+
+def test_uncompress_matches_dense_gradient():
+    """test/train/backprop.jl:148-158: uncompress(update) == dense gradient of table[:, ids]."""
+    from dlrm_jl_b200.embedding import sparse_updates, uncompress
+    rng = np.random.default_rng(1234)
+    B, D, nrows = 128, 64, 1000
+    ids = rng.integers(0, nrows, size=(26, B))
+    dT = rng.standard_normal((B, 27, D)).astype(np.float32)
+    ups = sparse_updates(torch.from_numpy(dT).to(_dev()), torch.from_numpy(ids).to(_dev()).unsqueeze(-1), 1)
+    for k in (0, 13, 25):
+        ref = O.uncompress(np.ascontiguousarray(dT[:, 1 + k]), ids[k], nrows)
+        assert O.rel_err(uncompress(ups[k], nrows).cpu().numpy(), ref) < 1e-6
+
+
+def test_update_host_entry_point():
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    rng = np.random.default_rng(10)
+    rows, D, B, P = [40, 7], 32, 50, 2
+    tables = _rand_tables(rng, rows, D)
+    t = _tables(tables, B * P)
+    idx = [rng.integers(0, r, size=(B, P)) for r in rows]
+    flat = np.ascontiguousarray(np.stack(idx).astype(np.int32))
+    dT = rng.standard_normal((B, 3, D)).astype(np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.load().dlrmb_embedding_bwd_sgd_host(t._h, p(flat), 4, 0, B, P, p(dT), 3, 1, 0.25))
+    for k in range(2):
+        ref = tables[k].copy()
+        O.sparse_sgd_update_fast(ref, idx[k], np.ascontiguousarray(dT[:, 1 + k]), 0.25)
+        assert O.rel_err(t.download(k), ref) < SGD_RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end: the reference's validate() on both goldens, and the hand-typed PyTorch case
+# ------------------------------------------------------------------------------------------------
+def _torch_mlp(layers, sigmoid_last):
+    import torch.nn as nn
+    mods = []
+    for i, (W, b) in enumerate(layers):
+        lin = nn.Linear(W.shape[1], W.shape[0], device=_dev())
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(W))
+            lin.bias.copy_(torch.from_numpy(b))
+        mods += [lin, nn.Sigmoid() if (sigmoid_last and i == len(layers) - 1) else nn.ReLU()]
+    return nn.Sequential(*mods)
+
+
+@pytest.mark.parametrize("name", ["single", "multi"])
+def test_validate_golden_one_sgd_step(name):
+    """src/validation.jl:1-44 + test/integration.jl: loss, then one step at lr = 10.0; every
+    embedding table and MLP parameter must match the PyTorch post-step values."""
+    from dlrm_jl_b200.embedding import Descent
+    from dlrm_jl_b200.interact import DotInteraction
+    from dlrm_jl_b200.model import DLRMModel
+    from dlrm_jl_b200.train import bce_loss, train_step, wrap_loss
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden(name)
+    bot, top, tables, dense, idx, labels = golden_model(g)
+    t = _tables(tables, idx[0].size)
+    model = DLRMModel(_torch_mlp(bot, False), t, DotInteraction(), _torch_mlp(top, True))
+    seen = []
+    loss_fn = wrap_loss(bce_loss, cb=seen.append)
+    dense_d = torch.from_numpy(dense).to(_dev())
+    labels_d = torch.from_numpy(labels).to(_dev())
+    with torch.no_grad():
+        out, T = model(dense_d, idx)
+    assert O.rel_err(T.cpu().numpy()[:, 1:], g["concatenated_result"][:, 1:]) < FWD_RTOL
+    assert O.rel_err(out.cpu().numpy(), g["mlp_top"].reshape(-1)) < FWD_RTOL
+    loss = train_step(loss_fn, model, Descent(10.0), labels_d, dense_d, idx)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    ubot, utop, uemb = golden_updates(g)
+    for k in range(7):
+        got = t.download(k)
+        assert O.rel_err(got, uemb[k]) < SGD_RTOL, k
+        assert not O.isapprox(tables[k], got), "update must differ from the original (validation.jl:142)"
+    for lin, (uW, ub) in zip([m for m in list(model.bottom_mlp) + list(model.top_mlp) if hasattr(m, "weight")],
+                             ubot + utop):
+        assert O.rel_err(lin.weight.detach().cpu().numpy(), uW) < SGD_RTOL
+        assert O.rel_err(lin.bias.detach().cpu().numpy(), ub) < SGD_RTOL
+    for sym in ("start", "lookup", "bottom_mlp", "interaction", "top_mlp", "loss", "interaction_back",
+                "grads_done", "weight_update_done", "embedding_update_done", "update_done"):
+        assert sym in seen, sym
+
+
+def test_known_answer_small_pytorch_case():
+    """test/model/model.jl:80-283 (values typed to 5 decimals -> absolute gate)."""
+    from dlrm_jl_b200.embedding import DefaultStrategy, PreallocationStrategy
+    from dlrm_jl_b200.interact import DotInteraction
+    from dlrm_jl_b200.model import DLRMModel
+    ka = load_known_answer()
+    tables = [ka[f"py_embedding{i}_weights"] for i in (1, 2, 3)]
+    t = _tables(tables, 4)
+    bot = [(ka["py_dense1_weights"], ka["py_dense1_bias"])]
+    top = [(ka["py_dense2_weights"], ka["py_dense2_bias"]), (ka["py_dense3_weights"].reshape(1, -1), ka["py_dense3_bias"])]
+    model = DLRMModel(_torch_mlp(bot, False), t, DotInteraction(), _torch_mlp(top, True))
+    dense = torch.from_numpy(ka["py_dense_input"]).to(_dev())
+    idx = [np.asarray(v) for v in ka["py_sparse_input"]]
+    for strategy in (PreallocationStrategy(4), DefaultStrategy()):
+        with torch.no_grad():
+            out, y = model(dense, idx, strategy=strategy)
+        assert np.allclose(out.cpu().numpy(), ka["py_top_mlp_output"], atol=2e-5)
+    with torch.no_grad():
+        out, T = model(dense, idx)
+    for k in range(3):
+        assert np.allclose(T[:, 1 + k].cpu().numpy(), np.asarray(ka["py_embedding_outputs"][k], np.float32), atol=1e-6)
+    z = DotInteraction()(model.bottom_mlp(dense), T)
+    assert np.allclose(z.detach().cpu().numpy(), ka["py_interaction_output"], atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-size runs: size-independent properties (Kaggle-shaped: 26 tables, D 64, B 2048)
+# ------------------------------------------------------------------------------------------------
+def test_kaggle_shaped_properties():
+    from dlrm_jl_b200.embedding import EmbeddingTables, PreallocationStrategy, maplookup
+    from dlrm_jl_b200.model import KAGGLE_EMBEDDING_SIZES as ROWS
+    D, B = 64, 2048
+    t = EmbeddingTables(ROWS, D, B, 0)
+    t.init_uniform(1)
+    rng = np.random.default_rng(20261018)
+    idx_np = np.stack([rng.integers(0, r, size=B) for r in ROWS]).astype(np.int32)
+    idx = torch.from_numpy(idx_np).to(_dev()).unsqueeze(-1)
+    # init bounds: U(-1/sqrt(rows), 1/sqrt(rows))
+    for k in (0, 8, 2):
+        tv = t.table(k)
+        bound = 1.0 / np.sqrt(ROWS[k])
+        assert float(tv.abs().max()) <= bound and float(tv.abs().max()) > 0.5 * bound
+    # lookup == rows of the zero-copy table views, and is idempotent
+    T = maplookup(PreallocationStrategy(D), t, idx)
+    T2 = maplookup(PreallocationStrategy(D), t, idx)
+    assert torch.equal(T, T2)
+    for k in range(26):
+        assert torch.equal(T[:, 1 + k], t.table(k)[idx[k, :, 0].long()])
+    # sort: keys ascending, perm a permutation, keys == idx[perm]
+    t.sort(idx)
+    for k in (2, 8, 25):
+        uniq, seg, perm = t.sort_dedup_export(k, B)
+        keys = idx_np[k][perm]
+        assert np.all(np.diff(keys) >= 0) and np.array_equal(np.sort(perm), np.arange(B))
+        assert np.array_equal(uniq, np.unique(idx_np[k])) and seg[-1] == B
+    # update: checksum of checksums -- the total change of a table equals -lr * sum of its deltas
+    dT = torch.randn((B, 27, D), device=_dev())
+    before = [t.table(k).double().sum(dim=0) for k in range(26)]
+    snap = {k: t.table(k).clone() for k in (0, 5, 8, 19)}
+    t.update_sorted(dT, 1, 0.1)
+    for k in range(26):
+        delta = t.table(k).double().sum(dim=0) - before[k]
+        want = -0.1 * dT[:, 1 + k].double().sum(dim=0)
+        assert torch.allclose(delta, want, rtol=1e-4, atol=1e-4), k
+    # linearity: the opposite step restores the tables to rounding error
+    t.bwd_sgd(idx, dT, 1, -0.1)
+    for k, s in snap.items():
+        assert torch.allclose(t.table(k), s, rtol=0, atol=1e-5), k
+    t.close()

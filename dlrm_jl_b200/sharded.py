@@ -1,0 +1,208 @@
+"""Table-wise sharded embeddings across the GPUs of one box (new functionality: DLRM.jl is
+single-process; BASELINE.json's north_star asks for table-wise model parallelism with the dense
+MLPs and the interaction data-parallel).
+
+One process per GPU.  Every table lives whole on one rank.  Per step:
+
+  forward   each rank sends the index columns of its local batch to the tables' owners
+            (all-to-all, a few hundred KB), owners pool their tables for the GLOBAL batch in one
+            lookup launch, and a second all-to-all delivers to every rank the pooled rows of its
+            local samples, which land in the interaction input T [B_local][1 + ntab][D];
+  backward  the mirror all-to-all returns dT slices to the owners, which run the fused sparse SGD
+            locally over the global batch; dense gradients are summed with one all-reduce.
+
+The routing logic here is pure tensor plumbing over ``torch.distributed`` (NCCL on GPUs, gloo in
+the CPU tests); the compute is injected (`lookup_fn`, `update_fn`) and in the product is always the
+CUDA library.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class TableSharding:
+    """Which rank owns which table, balanced by LOOKUP COUNT first (every table receives
+    B_global * P lookups per step whatever its size), then by bytes: tables are dealt in
+    descending row count, snake order, so the big tables land on different ranks."""
+    rows: List[int]
+    world: int
+    owner: List[int]
+    local: List[List[int]]      # local[r] = global table ids owned by rank r, ascending
+
+    @classmethod
+    def build(cls, rows: Sequence[int], world: int) -> "TableSharding":
+        rows = [int(r) for r in rows]
+        order = sorted(range(len(rows)), key=lambda k: (-rows[k], k))
+        owner = [0] * len(rows)
+        for i, k in enumerate(order):
+            rnd, pos = divmod(i, world)
+            owner[k] = pos if rnd % 2 == 0 else world - 1 - pos
+        local = [[k for k in range(len(rows)) if owner[k] == r] for r in range(world)]
+        return cls(rows, world, owner, local)
+
+    def counts(self) -> List[int]:
+        return [len(l) for l in self.local]
+
+    def bytes_per_rank(self, D: int) -> List[int]:
+        return [sum(self.rows[k] for k in l) * D * 4 for l in self.local]
+
+
+def _a2a(out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits, group) -> None:
+    dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+
+
+def exchange_indices(idx_local: torch.Tensor, sh: TableSharding, rank: int, group=None) -> torch.Tensor:
+    """idx_local [ntab][B_local][P] (this rank's samples, all tables) ->
+    [t_mine][B_global][P] (all samples, this rank's tables; sample order = rank-major)."""
+    ntab, Bl, P = idx_local.shape
+    W = sh.world
+    if W == 1:
+        return idx_local
+    send = torch.cat([idx_local[sh.local[r]] for r in range(W)], dim=0).contiguous()   # grouped by owner
+    t_mine = len(sh.local[rank])
+    recv = torch.empty((W, t_mine, Bl, P), dtype=idx_local.dtype, device=idx_local.device)
+    in_splits = [len(sh.local[r]) * Bl * P for r in range(W)]
+    out_splits = [t_mine * Bl * P] * W
+    _a2a(recv.view(-1), send.view(-1), out_splits, in_splits, group)
+    # [W][t][Bl][P] -> [t][W*Bl][P]
+    return recv.permute(1, 0, 2, 3).reshape(t_mine, W * Bl, P).contiguous()
+
+
+def exchange_pooled(pooled: torch.Tensor, T: torch.Tensor, sh: TableSharding, rank: int, group=None) -> None:
+    """pooled [B_global][t_mine][D] (owner side) -> T[:, 1 + k, :] for every table k, on the rank
+    that owns the samples.  T is [B_local][1 + ntab][D]; slot 0 is left for x."""
+    W = sh.world
+    Bg, t_mine, D = pooled.shape
+    Bl = Bg // W
+    if W == 1:
+        T[:, 1:, :] = pooled
+        return
+    counts = sh.counts()
+    recv = torch.empty((Bl * sum(counts) * D,), dtype=pooled.dtype, device=pooled.device)
+    in_splits = [Bl * t_mine * D] * W
+    out_splits = [Bl * counts[r] * D for r in range(W)]
+    _a2a(recv, pooled.reshape(-1), out_splits, in_splits, group)
+    off = 0
+    for r in range(W):
+        if counts[r] == 0:
+            continue
+        chunk = recv[off:off + Bl * counts[r] * D].view(Bl, counts[r], D)
+        slots = torch.as_tensor([1 + k for k in sh.local[r]], device=T.device)
+        T.index_copy_(1, slots, chunk)
+        off += Bl * counts[r] * D
+
+
+def exchange_grads(dT: torch.Tensor, sh: TableSharding, rank: int, group=None) -> torch.Tensor:
+    """dT [B_local][1 + ntab][D] -> [B_global][t_mine][D] on each owner (mirror of exchange_pooled)."""
+    W = sh.world
+    Bl, S, D = dT.shape
+    if W == 1:
+        return dT[:, 1:, :].contiguous()
+    counts = sh.counts()
+    t_mine = counts[rank]
+    send = torch.cat([dT[:, [1 + k for k in sh.local[r]], :].reshape(-1) for r in range(W)])
+    recv = torch.empty((W * Bl, t_mine, D), dtype=dT.dtype, device=dT.device)
+    in_splits = [Bl * counts[r] * D for r in range(W)]
+    out_splits = [Bl * t_mine * D] * W
+    _a2a(recv.view(-1), send, out_splits, in_splits, group)
+    return recv
+
+
+class _ShardedLookupFn(torch.autograd.Function):
+    """lookup (owner side) + pooled all-to-all forward; gradient all-to-all backward.  The
+    owner-side gradient [B_global][t_mine][D] is parked on ``ctx_obj.owned_grad`` for the sparse
+    update (the tables are not torch parameters, as in the reference where the lookup pullback
+    yields SparseEmbeddingUpdate objects rather than dense gradients)."""
+
+    @staticmethod
+    def forward(ctx, anchor: torch.Tensor, se: "ShardedEmbedding", idx_local: torch.Tensor):
+        ctx.se = se
+        idx_owned = exchange_indices(idx_local, se.sharding, se.rank, se.group)
+        se.idx_owned = idx_owned
+        Bg = idx_owned.shape[1]
+        D = se.D
+        pooled = torch.empty((Bg, len(se.local_ids), D), dtype=torch.float32, device=idx_local.device)
+        if len(se.local_ids):
+            se.lookup_fn(idx_owned, pooled)
+        Bl = idx_local.shape[1]
+        T = torch.zeros((Bl, 1 + se.ntab, D), dtype=torch.float32, device=idx_local.device)
+        exchange_pooled(pooled, T, se.sharding, se.rank, se.group)
+        return T
+
+    @staticmethod
+    def backward(ctx, dT: torch.Tensor):
+        se = ctx.se
+        se.owned_grad = exchange_grads(dT.contiguous(), se.sharding, se.rank, se.group)
+        return None, None, None
+
+
+class ShardedEmbedding:
+    """Table-wise sharded drop-in for ``maplookup`` + ``update!`` at world size W.
+
+    ``lookup_fn(idx_owned [t][Bg][P], out [Bg][t][D])`` and
+    ``update_fn(idx_owned, grad [Bg][t][D], lr)`` do the local compute; `from_tables` wires them to
+    an :class:`~dlrm_jl_b200.embedding.EmbeddingTables` holding this rank's tables.
+    """
+
+    def __init__(self, rows: Sequence[int], D: int, rank: int, world: int, lookup_fn: Callable,
+                 update_fn: Callable, group=None, sort_fn: Optional[Callable] = None):
+        self.sharding = TableSharding.build(rows, world)
+        self.rank, self.world, self.group = rank, world, group
+        self.D = D
+        self.ntab = len(rows)
+        self.local_ids = self.sharding.local[rank]
+        self.lookup_fn, self.update_fn, self.sort_fn = lookup_fn, update_fn, sort_fn
+        self.idx_owned: Optional[torch.Tensor] = None
+        self.owned_grad: Optional[torch.Tensor] = None
+
+    @classmethod
+    def create(cls, rows: Sequence[int], D: int, B_local: int, P: int, rank: int, world: int, device,
+               group=None, seed: int = 51234) -> "ShardedEmbedding":
+        from .embedding import EmbeddingTables
+        sh = TableSharding.build(rows, world)
+        mine = sh.local[rank]
+        tables = EmbeddingTables([rows[k] for k in mine] or [1], D, B_local * world * P, device)
+        tables.init_uniform(seed + 7919 * rank)
+        se = cls(rows, D, rank, world,
+                 lookup_fn=lambda idx, out: tables.lookup(idx, out, 0),
+                 update_fn=lambda idx, g, lr, presorted=False: (
+                     tables.update_sorted(g, 0, lr) if presorted else tables.bwd_sgd(idx, g, 0, lr)),
+                 group=group,
+                 sort_fn=lambda idx: tables.sort(idx, 0, side_stream=True))
+        se.tables = tables
+        return se
+
+    def lookup(self, idx_local: torch.Tensor, anchor: torch.Tensor) -> torch.Tensor:
+        """idx_local [ntab][B_local][P] -> T [B_local][1 + ntab][D] (requires grad through `anchor`,
+        any tensor that requires grad, so autograd calls the gradient exchange)."""
+        return _ShardedLookupFn.apply(anchor, self, idx_local)
+
+    def update(self, lr: float, presorted: bool = False) -> None:
+        if len(self.local_ids) == 0:
+            return
+        if presorted:
+            self.update_fn(self.idx_owned, self.owned_grad, lr, True)
+        else:
+            self.update_fn(self.idx_owned, self.owned_grad, lr)
+
+
+def allreduce_dense_grads(params: Sequence[torch.nn.Parameter], world: int, group=None) -> None:
+    """Sum the data-parallel MLP gradients with ONE all-reduce over a flat bucket (a few MB: sized
+    for launch latency, NVSwitch gives every pair full bandwidth).  The loss is the mean over the
+    local batch, so the global-batch mean needs a 1/world factor."""
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -30,7 +30,7 @@ from typing import List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, _prof
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -148,9 +148,10 @@ class EmbeddingTables:
         ntab, B, P = idx.shape
         slots = out.shape[1]
         assert out.is_contiguous() and out.dtype == torch.float32 and out.shape == (B, slots, self.D)
-        _lib.check(self._lib.dlrmb_embedding_fwd(
-            self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, out.data_ptr(), slots, slot0,
-            _stream_ptr(self.device)))
+        with _prof.range("lookup"):
+            _lib.check(self._lib.dlrmb_embedding_fwd(
+                self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, out.data_ptr(), slots, slot0,
+                _stream_ptr(self.device)))
 
     def sort(self, idx: torch.Tensor, idx_base: int = 0, side_stream: bool = False) -> None:
         """Index sort/dedup for the next update.  With ``side_stream`` it is issued on a second
@@ -162,14 +163,16 @@ class EmbeddingTables:
                 self._sorted_event = torch.cuda.Event()
             self._side_stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._side_stream):
-                _lib.check(self._lib.dlrmb_embedding_sort(
-                    self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, self._side_stream.cuda_stream))
+                with _prof.range("sort"):
+                    _lib.check(self._lib.dlrmb_embedding_sort(
+                        self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, self._side_stream.cuda_stream))
                 idx.record_stream(self._side_stream)
                 self._sorted_event.record(self._side_stream)
             self._pending_side = True
         else:
-            _lib.check(self._lib.dlrmb_embedding_sort(
-                self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, _stream_ptr(self.device)))
+            with _prof.range("sort"):
+                _lib.check(self._lib.dlrmb_embedding_sort(
+                    self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, _stream_ptr(self.device)))
             self._pending_side = False
 
     def update_sorted(self, dT: torch.Tensor, slot0: int, lr: float) -> None:
@@ -178,8 +181,9 @@ class EmbeddingTables:
             self._pending_side = False
         B, slots, D = dT.shape
         assert dT.is_contiguous() and dT.dtype == torch.float32 and D == self.D
-        _lib.check(self._lib.dlrmb_embedding_update_sorted(
-            self._h, dT.data_ptr(), slots, slot0, float(lr), _stream_ptr(self.device)))
+        with _prof.range("update"):
+            _lib.check(self._lib.dlrmb_embedding_update_sorted(
+                self._h, dT.data_ptr(), slots, slot0, float(lr), _stream_ptr(self.device)))
 
     def bwd_sgd(self, idx: torch.Tensor, dT: torch.Tensor, slot0: int, lr: float, idx_base: int = 0) -> None:
         self.sort(idx, idx_base)

@@ -11,7 +11,7 @@ from typing import List, Sequence
 
 import torch
 
-from . import _lib
+from . import _lib, _prof
 
 POST_INTERACTION_PAD_TO_MUL = 1  # src/model/model.jl:32
 
@@ -50,9 +50,10 @@ class _DotInteractionFn(torch.autograd.Function):
         out = torch.empty((B, interaction_width(F, d, pad_to_mul)), dtype=torch.float32, device=T.device)
         lib = _lib.load()
         # fast_vcat (interact.jl:271-281) is fused: x lands in slot 0 of T inside the kernel
-        _lib.check(lib.dlrmb_interaction_fwd(
-            T.device.index or 0, T.data_ptr(), xc.data_ptr() if xc is not None else None,
-            B, F, d, pad_to_mul, out.data_ptr(), _stream(T)))
+        with _prof.range("interaction_fwd"):
+            _lib.check(lib.dlrmb_interaction_fwd(
+                T.device.index or 0, T.data_ptr(), xc.data_ptr() if xc is not None else None,
+                B, F, d, pad_to_mul, out.data_ptr(), _stream(T)))
         ctx.save_for_backward(T)
         ctx.pad_to_mul = pad_to_mul
         ctx.has_x = x is not None
@@ -66,9 +67,10 @@ class _DotInteractionFn(torch.autograd.Function):
         dT = torch.empty_like(T)
         dx = torch.empty((B, d), dtype=torch.float32, device=T.device)
         lib = _lib.load()
-        _lib.check(lib.dlrmb_interaction_bwd(
-            T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
-            dT.data_ptr(), dx.data_ptr(), _stream(T)))
+        with _prof.range("interaction_bwd"):
+            _lib.check(lib.dlrmb_interaction_bwd(
+                T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
+                dT.data_ptr(), dx.data_ptr(), _stream(T)))
         # (dx, dy): dy is the whole (d*F) x B matrix, slot 0 included (interact.jl:428-435)
         return (dx if ctx.has_x else None), dT, None
 

@@ -122,14 +122,21 @@ class _ShardedLookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor: torch.Tensor, se: "ShardedEmbedding", idx_local: torch.Tensor):
         ctx.se = se
+        D = se.D
+        Bl = idx_local.shape[1]
+        if se.world == 1:
+            # no exchange: pool straight into the interaction input (slot 0 is filled with x by
+            # the interaction kernel's fused fast_vcat)
+            se.idx_owned = idx_local
+            T = torch.empty((Bl, 1 + se.ntab, D), dtype=torch.float32, device=idx_local.device)
+            se.lookup_fn(idx_local, T, 1)
+            return T
         idx_owned = exchange_indices(idx_local, se.sharding, se.rank, se.group)
         se.idx_owned = idx_owned
         Bg = idx_owned.shape[1]
-        D = se.D
         pooled = torch.empty((Bg, len(se.local_ids), D), dtype=torch.float32, device=idx_local.device)
         if len(se.local_ids):
-            se.lookup_fn(idx_owned, pooled)
-        Bl = idx_local.shape[1]
+            se.lookup_fn(idx_owned, pooled, 0)
         T = torch.zeros((Bl, 1 + se.ntab, D), dtype=torch.float32, device=idx_local.device)
         exchange_pooled(pooled, T, se.sharding, se.rank, se.group)
         return T
@@ -137,16 +144,20 @@ class _ShardedLookupFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dT: torch.Tensor):
         se = ctx.se
-        se.owned_grad = exchange_grads(dT.contiguous(), se.sharding, se.rank, se.group)
+        if se.world == 1:
+            se.owned_grad = dT.contiguous()      # [B][1 + ntab][D], consumed with slot0 = 1
+        else:
+            se.owned_grad = exchange_grads(dT.contiguous(), se.sharding, se.rank, se.group)
         return None, None, None
 
 
 class ShardedEmbedding:
     """Table-wise sharded drop-in for ``maplookup`` + ``update!`` at world size W.
 
-    ``lookup_fn(idx_owned [t][Bg][P], out [Bg][t][D])`` and
-    ``update_fn(idx_owned, grad [Bg][t][D], lr)`` do the local compute; `from_tables` wires them to
-    an :class:`~dlrm_jl_b200.embedding.EmbeddingTables` holding this rank's tables.
+    ``lookup_fn(idx_owned [t][Bg][P], out [Bg][slot0 + t][D], slot0)`` and
+    ``update_fn(idx_owned, grad [Bg][slot0 + t][D], lr, slot0, presorted)`` do the local compute;
+    :meth:`create` wires them to an :class:`~dlrm_jl_b200.embedding.EmbeddingTables` holding this
+    rank's tables.  ``slot0`` is 1 at world size 1 (the buffers ARE the interaction input) else 0.
     """
 
     def __init__(self, rows: Sequence[int], D: int, rank: int, world: int, lookup_fn: Callable,
@@ -159,6 +170,7 @@ class ShardedEmbedding:
         self.lookup_fn, self.update_fn, self.sort_fn = lookup_fn, update_fn, sort_fn
         self.idx_owned: Optional[torch.Tensor] = None
         self.owned_grad: Optional[torch.Tensor] = None
+        self.slot0 = 1 if world == 1 else 0
 
     @classmethod
     def create(cls, rows: Sequence[int], D: int, B_local: int, P: int, rank: int, world: int, device,
@@ -169,9 +181,9 @@ class ShardedEmbedding:
         tables = EmbeddingTables([rows[k] for k in mine] or [1], D, B_local * world * P, device)
         tables.init_uniform(seed + 7919 * rank)
         se = cls(rows, D, rank, world,
-                 lookup_fn=lambda idx, out: tables.lookup(idx, out, 0),
-                 update_fn=lambda idx, g, lr, presorted=False: (
-                     tables.update_sorted(g, 0, lr) if presorted else tables.bwd_sgd(idx, g, 0, lr)),
+                 lookup_fn=lambda idx, out, slot0: tables.lookup(idx, out, slot0),
+                 update_fn=lambda idx, g, lr, slot0, presorted=False: (
+                     tables.update_sorted(g, slot0, lr) if presorted else tables.bwd_sgd(idx, g, slot0, lr)),
                  group=group,
                  sort_fn=lambda idx: tables.sort(idx, 0, side_stream=True))
         se.tables = tables
@@ -182,13 +194,15 @@ class ShardedEmbedding:
         any tensor that requires grad, so autograd calls the gradient exchange)."""
         return _ShardedLookupFn.apply(anchor, self, idx_local)
 
+    def sort_async(self) -> None:
+        """Start the index sort/dedup for this step's update on the side stream."""
+        if self.sort_fn is not None and len(self.local_ids):
+            self.sort_fn(self.idx_owned)
+
     def update(self, lr: float, presorted: bool = False) -> None:
         if len(self.local_ids) == 0:
             return
-        if presorted:
-            self.update_fn(self.idx_owned, self.owned_grad, lr, True)
-        else:
-            self.update_fn(self.idx_owned, self.owned_grad, lr)
+        self.update_fn(self.idx_owned, self.owned_grad, lr, self.slot0, presorted)
 
 
 def allreduce_dense_grads(params: Sequence[torch.nn.Parameter], world: int, group=None) -> None:

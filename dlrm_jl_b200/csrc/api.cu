@@ -91,6 +91,7 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
     t->ntab = ntab;
     t->D = D;
     t->max_lookups = max_lookups;
+    t->cap = (max_lookups + 3) / 4 * 4;
     t->sm_count = device_sm_count(device);
     t->h_rows = (int64_t*)malloc(sizeof(int64_t) * ntab);
     t->h_offsets = (int64_t*)malloc(sizeof(int64_t) * (ntab + 1));
@@ -136,7 +137,7 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
         free(h);
         TRY_CUDA(e);
     }
-    size_t nl = (size_t)ntab * (size_t)max_lookups;
+    size_t nl = (size_t)ntab * (size_t)t->cap + 8;
     for (int i = 0; i < 2; ++i) {
         TRY_CUDA(cudaMalloc((void**)&t->keys[i], sizeof(uint32_t) * nl));
         TRY_CUDA(cudaMalloc((void**)&t->pos[i], sizeof(uint32_t) * nl));
@@ -148,6 +149,8 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
     TRY_CUDA(cudaMalloc((void**)&t->partial,
                         sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)D));
     TRY_CUDA(cudaMalloc((void**)&t->tile_flags, (size_t)ntab * (size_t)t->partial_tiles_cap));
+    TRY_CUDA(cudaMalloc((void**)&t->head_list, sizeof(uint32_t) * (size_t)ntab * (size_t)t->partial_tiles_cap));
+    TRY_CUDA(cudaMalloc((void**)&t->head_count, sizeof(uint32_t)));
     TRY_CUDA(cudaMalloc((void**)&t->d_seg, sizeof(int32_t) * ((size_t)max_lookups + 1)));
     TRY_CUDA(cudaMalloc((void**)&t->d_uniq, sizeof(int64_t) * (size_t)max_lookups));
     TRY_CUDA(cudaMalloc((void**)&t->d_nuniq, sizeof(int32_t)));
@@ -169,6 +172,8 @@ int32_t dlrmb_tables_destroy(dlrmb_tables* t) {
     cudaFree(t->tile_hist);
     cudaFree(t->partial);
     cudaFree(t->tile_flags);
+    cudaFree(t->head_list);
+    cudaFree(t->head_count);
     cudaFree(t->d_seg);
     cudaFree(t->d_uniq);
     cudaFree(t->d_nuniq);
@@ -338,7 +343,7 @@ int32_t dlrmb_sort_dedup_export(dlrmb_tables* t, int32_t k, int64_t* uniq, int32
     *n_uniq = n;
     DLRMB_CUDA(cudaMemcpyAsync(uniq, t->d_uniq, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, t->own_stream));
     DLRMB_CUDA(cudaMemcpyAsync(seg_offsets, t->d_seg, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, t->own_stream));
-    DLRMB_CUDA(cudaMemcpyAsync(perm, t->pos[t->sorted_buf] + (size_t)k * t->max_lookups, sizeof(uint32_t) * L,
+    DLRMB_CUDA(cudaMemcpyAsync(perm, t->pos[t->sorted_buf] + (size_t)k * t->cap, sizeof(uint32_t) * L,
                                cudaMemcpyDeviceToHost, t->own_stream));
     DLRMB_CUDA(cudaStreamSynchronize(t->own_stream));
     return DLRMB_OK;

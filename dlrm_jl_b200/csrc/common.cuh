@@ -58,6 +58,7 @@ struct dlrmb_tables {
     int D = 0;
     int sm_count = 148;
     int64_t max_lookups = 0;   // max B*P per table
+    int64_t cap = 0;           // max_lookups rounded up to 4: stride of the per-table streams
     int64_t total_rows = 0;
     int64_t max_rows = 0;
     int64_t* h_rows = nullptr;       // host copy
@@ -75,6 +76,8 @@ struct dlrmb_tables {
     float* partial = nullptr;                 // [ntab][tiles][2][D] boundary partial sums
     uint8_t* tile_flags = nullptr;            // [ntab][tiles] boundary flags
     int64_t partial_tiles_cap = 0;
+    uint32_t* head_list = nullptr;            // [ntab * tiles] tiles whose last run continues
+    uint32_t* head_count = nullptr;
     // dedup export scratch
     int32_t* d_seg = nullptr;                 // [max_lookups + 1]
     int64_t* d_uniq = nullptr;                // [max_lookups]

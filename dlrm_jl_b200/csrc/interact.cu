@@ -13,9 +13,10 @@
 // Both are HBM-bound at DLRM shapes (5-12 flop/byte, below the fp32 FMA ridge), so the work
 // stays on the FP32 FMA pipe (TF32 tensor cores would break the 1e-5 tolerance) and the design
 // goal is one read of T and one write of the result per sample:
-//   - a CTA owns NS consecutive samples; their T rows are one contiguous global range, staged
-//     into shared memory with 16-byte cp.async copies (row stride padded by 4 floats so the
-//     128-bit operand reads of different rows spread across the bank groups);
+//   - a CTA owns NS consecutive samples; their T rows are staged into shared memory by TMA 1-D
+//     bulk copies (cp.async.bulk, one per feature row, completion on an mbarrier), row stride
+//     padded by 4 floats so the 128-bit operand reads of different rows spread across the bank
+//     groups;
 //   - forward: each thread owns a TB x TB register block of the Gram lower triangle and walks
 //     k in float4 steps; results are staged in shared memory so that the CTA's output, which
 //     is again one contiguous global range, is written fully coalesced;
@@ -25,12 +26,27 @@
 
 namespace dlrmb {
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 static inline int interaction_width(int F, int d, int pad_to_mul) {
@@ -58,7 +74,20 @@ interaction_fwd_kernel(float* __restrict__ T, const float* __restrict__ x, int B
     const int s0 = blockIdx.x * NS;
     const int ns = min(NS, B - s0);
 
-    // block-pair table: task q -> (bi >= bj)
+    __shared__ unsigned long long bar;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_arrive_expect_tx(&bar, (unsigned)(ns * F * d * sizeof(float)));
+    }
+    __syncthreads();
+    // stage T: one TMA bulk copy per feature row (slot 0 from x when given)
+    for (int r = tid; r < ns * F; r += blockDim.x) {
+        const int s = r / F, f = r - s * F;
+        const float* src = (x != nullptr && f == 0) ? x + (size_t)(s0 + s) * d
+                                                    : T + ((size_t)(s0 + s) * F + f) * d;
+        bulk_g2s(Ts + ((size_t)s * Fp + f) * ldt4, src, (unsigned)(d * sizeof(float)), &bar);
+    }
+    // meanwhile: block-pair table (task q -> bi >= bj) and zeroed padding rows
     for (int q = tid; q < nt; q += blockDim.x) {
         int bi = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
         while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
@@ -66,23 +95,15 @@ interaction_fwd_kernel(float* __restrict__ T, const float* __restrict__ x, int B
         pr[2 * q] = (unsigned char)bi;
         pr[2 * q + 1] = (unsigned char)(q - bi * (bi + 1) / 2);
     }
-    // stage T (slot 0 from x when given), zero the padding rows
-    const int chunks = ns * Fp * d4;
-    for (int i = tid; i < chunks; i += blockDim.x) {
-        int c = i % d4;
-        int r = i / d4;
-        int f = r % Fp;
-        int s = r / Fp;
-        float4* dst = Ts + ((size_t)s * Fp + f) * ldt4 + c;
-        if (f < F) {
-            const float* src = (x != nullptr && f == 0) ? x + (size_t)(s0 + s) * d + 4 * c
-                                                        : T + ((size_t)(s0 + s) * F + f) * d + 4 * c;
-            cp_async16(dst, src);
-        } else {
-            *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Fp > F) {
+        const int padrows = Fp - F;
+        for (int i = tid; i < ns * padrows * d4; i += blockDim.x) {
+            const int c = i % d4, r = i / d4;
+            const int s = r / padrows, f = F + (r - s * padrows);
+            Ts[((size_t)s * Fp + f) * ldt4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    cp_async_wait_all();
+    mbar_wait(&bar, 0);
     __syncthreads();
 
     // x passthrough: out[b][0:d] = T[b][0]; also fast_vcat into T when x came separately
@@ -203,30 +224,32 @@ struct TilePlan {
     size_t smem;
 };
 
-// Pick samples-per-CTA and CTA size so the task count fills whole rounds of the CTA and at
-// least two CTAs fit an SM.
+// Pick samples-per-CTA and CTA size.  These kernels are latency-bound at DLRM batch sizes, so the
+// plan keeps CTAs small (shared memory <= ~40 KB: at least 5 resident CTAs per SM, whose load /
+// compute / store phases then overlap), fills whole rounds of the CTA with tasks, and among
+// equals prefers more samples per CTA (fewer, fuller CTAs).
 static TilePlan plan_tiles(int B, int tasks_per_sample, size_t smem_per_sample, size_t smem_fixed,
                            int sm_count) {
     TilePlan best{1, 128, smem_per_sample + smem_fixed};
     double best_score = -1.0;
-    const size_t budget = 100 * 1024;
-    for (int ns = 1; ns <= 32; ++ns) {
+    const size_t budget = 40 * 1024;
+    for (int ns = 1; ns <= 16; ++ns) {
         size_t smem = ns * smem_per_sample + smem_fixed;
         if (smem > budget && ns > 1) break;
-        for (int threads = 128; threads <= 256; threads += 32) {
+        for (int threads = 96; threads <= 256; threads += 32) {
             int tasks = ns * tasks_per_sample;
             int rounds = (tasks + threads - 1) / threads;
             double eff = (double)tasks / ((double)rounds * threads);
-            // prefer enough CTAs to cover the machine twice, then larger tiles
             int64_t ctas = (B + ns - 1) / ns;
-            double fill = ctas >= 2 * sm_count ? 1.0 : (double)ctas / (2.0 * sm_count);
-            double score = eff * (0.5 + 0.5 * fill) + 0.002 * ns;
+            double fill = ctas >= 4 * (int64_t)sm_count ? 1.0 : (double)ctas / (4.0 * sm_count);
+            double score = eff * (0.6 + 0.4 * fill) - 0.01 * (rounds - 1) + 0.001 * ns;
             if (score > best_score) {
                 best_score = score;
                 best = TilePlan{ns, threads, smem};
             }
         }
     }
+    (void)sm_count;
     return best;
 }
 
@@ -301,32 +324,41 @@ interaction_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__
     const int ns = min(NS, B - s0);
     const int npair = F * (F - 1) / 2;
 
-    // stage T (16-byte async copies) and dOut (contiguous, 4-byte aligned only)
-    for (int i = tid; i < ns * F * d4; i += blockDim.x) {
-        int c = i % d4, r = i / d4;
-        cp_async16(Ts + (size_t)r * ldt4 + c, T + ((size_t)s0 * F + r) * d + 4 * c);
+    __shared__ unsigned long long bar;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_arrive_expect_tx(&bar, (unsigned)(ns * F * d * sizeof(float)));
     }
+    __syncthreads();
+    // stage T: one TMA bulk copy per feature row into the padded-stride tile
+    for (int r = tid; r < ns * F; r += blockDim.x)
+        bulk_g2s(Ts + (size_t)r * ldt4, T + ((size_t)s0 * F + r) * d, (unsigned)(d * sizeof(float)), &bar);
+    // dOut tile: contiguous but only 4-byte aligned (odd row width) -> coalesced scalar loads
     const float* gg = dOut + (size_t)s0 * width;
     for (int i = tid; i < ns * width; i += blockDim.x) Gs[i] = __ldg(gg + i);
-    cp_async_wait_all();
-    __syncthreads();
-
-    // S[j][f] = g[d + pair(j, f)], zero diagonal and zero padding columns
-    float* Sf = reinterpret_cast<float*>(Ss);
-    for (int i = tid; i < ns * F * Fp; i += blockDim.x) {
-        int f = i % Fp;
-        int r = i / Fp;
-        int j = r % F;
-        int s = r / F;
-        float v = 0.f;
-        if (f < F && f != j) {
-            int hi = max(j, f), lo = min(j, f);
-            v = Gs[(size_t)s * width + d + hi * (hi - 1) / 2 + lo];
-        }
-        Sf[i] = v;
+    // pair table m -> (hi, lo), and S zeroed (diagonal and padding columns stay zero)
+    unsigned char* pr = reinterpret_cast<unsigned char*>(Gs + (size_t)NS * width);
+    for (int m = tid; m < npair; m += blockDim.x) {
+        int j = (int)((sqrtf(8.f * m + 1.f) + 1.f) * 0.5f);
+        while (j * (j - 1) / 2 > m) --j;
+        while ((j + 1) * j / 2 <= m) ++j;
+        pr[2 * m] = (unsigned char)j;
+        pr[2 * m + 1] = (unsigned char)(m - j * (j - 1) / 2);
     }
+    for (int i = tid; i < ns * F * nfb; i += blockDim.x) Ss[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    (void)npair;
+    // S[hi][lo] = S[lo][hi] = g[d + m]
+    float* Sf = reinterpret_cast<float*>(Ss);
+    for (int i = tid; i < ns * npair; i += blockDim.x) {
+        const int s = i / npair, m = i - s * npair;
+        const int hi = pr[2 * m], lo = pr[2 * m + 1];
+        const float v = Gs[(size_t)s * width + d + m];
+        float* Sb = Sf + (size_t)s * F * Fp;
+        Sb[hi * Fp + lo] = v;
+        Sb[lo * Fp + hi] = v;
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
 
     const int per_sample = nfb * d4;
     for (int task = tid; task < ns * per_sample; task += blockDim.x) {
@@ -399,7 +431,7 @@ int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int 
     const int d4 = d / 4;
     const int Fp = (F + 3) & ~3;
     size_t per_sample = ((size_t)F * (d4 + 1) * 4 + (size_t)F * Fp + width) * sizeof(float);
-    TilePlan p = plan_tiles(B, (Fp / 4) * d4, per_sample, 16, sm_count);
+    TilePlan p = plan_tiles(B, (Fp / 4) * d4, per_sample, (size_t)F * (F - 1) + 16, sm_count);
     DLRMB_REQUIRE(p.smem <= 200 * 1024, "interaction tile needs %zu bytes of shared memory", p.smem);
     static unsigned long long attr_done = 0;
     int rc = ensure_smem_attr((const void*)interaction_bwd_kernel, 200 * 1024, &attr_done);

@@ -32,7 +32,7 @@ template <> struct Vec<1> {
 template <typename IdxT, int VEC, int U>
 __global__ void __launch_bounds__(256)
 lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
-                     uint32_t B, uint32_t C, float* __restrict__ out, int slots, int slot0) {
+                     uint32_t B, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
     using V = typename Vec<VEC>::type;
     const int k = blockIdx.y;
     const float* __restrict__ tb = desc[k].base;
@@ -51,7 +51,7 @@ lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict_
         for (int u = 0; u < U; ++u) {
             uint32_t tt = t + (uint32_t)u * step;
             ok[u] = tt < n;
-            b[u] = tt / C;
+            b[u] = cshift >= 0 ? (tt >> cshift) : (tt / C);   // C is a power of two for the usual dims
             c[u] = tt - b[u] * C;
             row[u] = ok[u] ? (int64_t)__ldg(ik + b[u]) - idx_base : 0;
         }
@@ -69,7 +69,7 @@ lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict_
 template <typename IdxT, int VEC>
 __global__ void __launch_bounds__(256)
 lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
-                   uint32_t B, uint32_t P, uint32_t C, float* __restrict__ out, int slots, int slot0) {
+                   uint32_t B, uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
     using V = typename Vec<VEC>::type;
     const int k = blockIdx.y;
     const float* __restrict__ tb = desc[k].base;
@@ -81,7 +81,7 @@ lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
     const size_t ostride = (size_t)slots * D;
 
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step) {
-        const uint32_t b = t / C;
+        const uint32_t b = cshift >= 0 ? (t >> cshift) : (t / C);
         const uint32_t c = t - b * C;
         const IdxT* __restrict__ ip = ik + (size_t)b * P;
         V acc = Vec<VEC>::zero();
@@ -120,10 +120,15 @@ static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B
     const int64_t cap = (int64_t)t->sm_count * 32;
     if (bx * t->ntab > cap) bx = cap / t->ntab > 0 ? cap / t->ntab : 1;
     dim3 grid((unsigned)bx, (unsigned)t->ntab);
+    int cshift = -1;
+    if ((C & (C - 1)) == 0) {
+        cshift = 0;
+        while ((1u << cshift) < C) ++cshift;
+    }
     if (P == 1)
-        lookup_gather_kernel<IdxT, VEC, U><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, out, slots, slot0);
+        lookup_gather_kernel<IdxT, VEC, U><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, cshift, out, slots, slot0);
     else
-        lookup_pool_kernel<IdxT, VEC><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, out, slots, slot0);
+        lookup_pool_kernel<IdxT, VEC><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }

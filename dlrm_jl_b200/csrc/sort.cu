@@ -7,8 +7,9 @@
 // position) so the update is deterministic without floating-point atomics.
 //
 // Two paths, chosen per call from L = B*P:
-//   * L <= kSmemSortMax: one CTA per table sorts (row id << 32 | position) composites with a
-//     bitonic network held entirely in shared memory; a single launch covers all tables.
+//   * L <= kSmemSortMax: one CTA per table runs the whole LSD radix sort in shared memory
+//     (8-bit digits, as many passes as that table's row count needs); a single launch covers
+//     all tables.
 //   * larger L: least-significant-digit radix sort, 8-bit digits, tiles of 2048 keys, all tables
 //     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
 //     (digit, tile) -> stable scatter whose in-tile ranks come from warp match_any + per-warp
@@ -21,46 +22,113 @@
 namespace dlrmb {
 
 // ---------------------------------------------------------------------------------------------
-// small path: bitonic sort in shared memory, one CTA per table
+// small path: LSD radix sort held in shared memory, one CTA per table, one launch for all tables
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT>
-__global__ void __launch_bounds__(1024)
-sort_small_kernel(const IdxT* __restrict__ idx, int idx_base, int L, int n /* pow2 >= L */,
+// 256 threads x ITEMS keys.  Element e of the table's flat index list lives in warp w = e / (32 *
+// ITEMS), item i, lane l (e = w*32*ITEMS + i*32 + l), so (warp, item, lane) order is input order
+// and the per-digit ranks below make every pass stable.  Per pass: match_any groups the lanes of a
+// warp by digit, a per-warp digit counter in shared memory turns that into a rank inside the warp's
+// chunk, a 256-wide exclusive scan over the digit totals gives the bucket starts, and the keys are
+// scattered through shared memory.  The number of passes follows the table's own row count
+// (a 24-row table needs one 8-bit pass, a 10M-row table three).
+template <typename IdxT, int ITEMS>
+__global__ void __launch_bounds__(256)
+sort_small_kernel(const IdxT* __restrict__ idx, int idx_base, int L, const TableDesc* __restrict__ desc,
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap) {
-    __shared__ unsigned long long sk[kSmemSortMax];
+    constexpr int N = 256 * ITEMS;
+    __shared__ uint32_t ksm[N];
+    __shared__ uint16_t vsm[N];
+    __shared__ uint32_t wh[8][256];
+    __shared__ uint32_t wsum[8];
     const int k = blockIdx.x;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const IdxT* __restrict__ ik = idx + (size_t)k * L;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        unsigned long long v = ~0ull;
-        if (i < L) {
-            uint32_t key = (uint32_t)((int64_t)ik[i] - idx_base);
-            v = ((unsigned long long)key << 32) | (uint32_t)i;
-        }
-        sk[i] = v;
+    const int64_t rows = desc[k].rows;
+    int bits = 0;
+    while (bits < 32 && (1ll << bits) < rows) ++bits;
+    const int passes = (bits + 7) >> 3;
+    const int base = w * (32 * ITEMS);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    uint32_t key[ITEMS];
+    uint32_t val[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int e = base + i * 32 + lane;
+        key[i] = e < L ? (uint32_t)((int64_t)ik[e] - idx_base) : 0xffffffffu;
+        val[i] = (uint32_t)e;
     }
-    __syncthreads();
-    const int half = n >> 1;
-    for (int kk = 2; kk <= n; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < half; i += blockDim.x) {
-                int lo = 2 * i - (i & (j - 1));
-                int hi = lo + j;
-                bool up = (lo & kk) == 0;
-                unsigned long long a = sk[lo], b = sk[hi];
-                if ((a > b) == up) {
-                    sk[lo] = b;
-                    sk[hi] = a;
-                }
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        for (int i = tid; i < 8 * 256; i += 256) (&wh[0][0])[i] = 0;
+        __syncthreads();
+        uint32_t rank[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t dig = (key[i] >> shift) & 255u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+            const uint32_t lt = peers & lt_mask;
+            const uint32_t b = wh[w][dig];
+            __syncwarp();
+            if (lt == 0) wh[w][dig] = b + __popc(peers);
+            __syncwarp();
+            rank[i] = b + __popc(lt);
+        }
+        __syncthreads();
+        {   // thread d owns digit d: bucket start = exclusive scan of the digit totals
+            uint32_t c[8], total = 0;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) {
+                c[ww] = wh[ww][tid];
+                total += c[ww];
             }
+            uint32_t inc = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) wsum[w] = inc;
             __syncthreads();
+            uint32_t run = inc - total;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww)
+                if (ww < w) run += wsum[ww];
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) {
+                wh[ww][tid] = run;
+                run += c[ww];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t dst = wh[w][(key[i] >> shift) & 255u] + rank[i];
+            ksm[dst] = key[i];
+            vsm[dst] = (uint16_t)val[i];
+        }
+        __syncthreads();
+        if (p + 1 < passes) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int e = base + i * 32 + lane;
+                key[i] = ksm[e];
+                val[i] = vsm[e];
+            }
         }
     }
     uint32_t* ko = keys_out + (size_t)k * cap;
     uint32_t* po = pos_out + (size_t)k * cap;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        unsigned long long v = sk[i];
-        ko[i] = (uint32_t)(v >> 32);
-        po[i] = (uint32_t)v;
+    if (passes == 0) {   // single-row table: already sorted
+        for (int i = tid; i < L; i += 256) {
+            ko[i] = 0u;
+            po[i] = (uint32_t)i;
+        }
+        return;
+    }
+    for (int i = tid; i < L; i += 256) {
+        ko[i] = ksm[i];
+        po[i] = vsm[i];
     }
 }
 
@@ -208,13 +276,14 @@ template <typename IdxT>
 static int launch_sort_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, cudaStream_t s) {
     const int64_t L64 = (int64_t)B * P;
     const int L = (int)L64;
-    const int64_t cap = t->max_lookups;
+    const int64_t cap = t->cap;
     if (L <= kSmemSortMax) {
-        int n = 2;
-        while (n < L) n <<= 1;
-        int threads = n / 2;
-        threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
-        sort_small_kernel<IdxT><<<t->ntab, threads, 0, s>>>(idx, idx_base, L, n, t->keys[0], t->pos[0], cap);
+        if (L <= 1024)
+            sort_small_kernel<IdxT, 4><<<t->ntab, 256, 0, s>>>(idx, idx_base, L, t->d_desc, t->keys[0], t->pos[0], cap);
+        else if (L <= 2048)
+            sort_small_kernel<IdxT, 8><<<t->ntab, 256, 0, s>>>(idx, idx_base, L, t->d_desc, t->keys[0], t->pos[0], cap);
+        else
+            sort_small_kernel<IdxT, 16><<<t->ntab, 256, 0, s>>>(idx, idx_base, L, t->d_desc, t->keys[0], t->pos[0], cap);
         DLRMB_LAUNCH_CHECK();
         t->sorted_buf = 0;
         return DLRMB_OK;
@@ -290,7 +359,7 @@ dedup_export_kernel(const uint32_t* __restrict__ keys, int L, int64_t* __restric
 
 int launch_dedup_export(dlrmb_tables* t, int k, cudaStream_t s) {
     const int L = t->sorted_B * t->sorted_P;
-    dedup_export_kernel<<<1, 1024, 0, s>>>(t->keys[t->sorted_buf] + (size_t)k * t->max_lookups, L,
+    dedup_export_kernel<<<1, 1024, 0, s>>>(t->keys[t->sorted_buf] + (size_t)k * t->cap, L,
                                            t->d_uniq, t->d_seg, t->d_nuniq);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;

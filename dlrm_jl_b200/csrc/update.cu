@@ -13,8 +13,9 @@
 // one tile ends in exactly one read-modify-write of its table row by its own lane group: no
 // atomics, fixed order.  A run that crosses tile boundaries leaves per-tile partial sums in a
 // scratch buffer ("head" for the tile where the run starts, "carry" for the tiles it continues
-// into); a second small kernel adds them in ascending tile order and performs the row's single
-// read-modify-write.  Results are therefore bit-reproducible run to run, and hot rows (Zipf
+// into) and the head tile is appended to a work list; a second small kernel gives every listed
+// run one CTA, whose lane groups add the carried partial sums in a fixed strided order and
+// perform the row's single read-modify-write.  Results are therefore bit-reproducible run to run, and hot rows (Zipf
 // heads, tiny tables) cost a bounded, evenly spread amount of work per lane group.
 //
 // HBM traffic per entry: 8 B of (key, position), one D*4-byte gradient row read, and per
@@ -55,12 +56,18 @@ struct UpdateGeom {
     int total_groups;
 };
 
-template <int VEC, int NCH, int U>
-__global__ void __launch_bounds__(256)
+// Batches are 4 entries: the 4 keys and 4 positions of a batch are one 16-byte load each (the
+// per-table streams are 16-byte aligned and tiles start at multiples of 4), plus one look-ahead
+// key.  The next batch's keys/positions are requested before the current batch's rows, so a batch
+// costs one memory round trip, not two.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1))
 update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
                     const uint32_t* __restrict__ pos, const float* __restrict__ dT, float lr,
-                    float* __restrict__ partial, uint8_t* __restrict__ flags, UpdateGeom gm) {
+                    float* __restrict__ partial, uint8_t* __restrict__ flags,
+                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm) {
     using V = typename UV<VEC>::type;
+    constexpr int U = 4;
     const int lpr = 1 << gm.lpr_log2;
     const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> gm.lpr_log2);
     if (gid >= gm.total_groups) return;
@@ -77,8 +84,11 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
 
     const int e0 = g * gm.tile;
     const int e1 = min(gm.L, e0 + gm.tile);
-    const bool cin = e0 > 0 && __ldg(ks + e0 - 1) == __ldg(ks + e0);
-    const bool cout = e1 < gm.L && __ldg(ks + e1) == __ldg(ks + e1 - 1);
+
+    uint4 kq = __ldg(reinterpret_cast<const uint4*>(ks + e0));
+    uint4 pq = __ldg(reinterpret_cast<const uint4*>(ps + e0));
+    uint32_t kn = (e0 + U < gm.L) ? __ldg(ks + e0 + U) : 0xffffffffu;
+    const uint32_t kprev = (e0 > 0) ? __ldg(ks + e0 - 1) : 0xffffffffu;
 
     bool chunk_ok[NCH];
 #pragma unroll
@@ -87,23 +97,29 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     V acc[NCH];
 #pragma unroll
     for (int m = 0; m < NCH; ++m) acc[m] = UV<VEC>::zero();
+    const bool cin = e0 > 0 && kprev == kq.x;
+    bool cout = false;
     bool first = cin;
     uint8_t fl = cin ? FLAG_CARRY_IN : 0;
     float* pcarry = partial + (((size_t)k * gm.ptiles_cap + g) * 2 + 0) * D;
     float* phead = partial + (((size_t)k * gm.ptiles_cap + g) * 2 + 1) * D;
 
     for (int e = e0; e < e1; e += U) {
-        uint32_t key[U];
+        const uint32_t key[U + 1] = {kq.x, kq.y, kq.z, kq.w, kn};
+        const uint32_t pp[U] = {pq.x, pq.y, pq.z, pq.w};
+        if (e + U < e1) {   // request the next batch's keys / positions now
+            kq = __ldg(reinterpret_cast<const uint4*>(ks + e + U));
+            pq = __ldg(reinterpret_cast<const uint4*>(ps + e + U));
+            kn = (e + 2 * U < gm.L) ? __ldg(ks + e + 2 * U) : 0xffffffffu;
+        }
         bool valid[U], is_end[U];
         V dv[U][NCH], rv[U][NCH];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int ee = e + u;
             valid[u] = ee < e1;
-            key[u] = valid[u] ? __ldg(ks + ee) : 0u;
-            const uint32_t p = valid[u] ? __ldg(ps + ee) : 0u;
-            is_end[u] = valid[u] && ((ee + 1 >= gm.L) || (__ldg(ks + ee + 1) != key[u]));
-            const uint32_t b = (gm.P == 1) ? p : p / (uint32_t)gm.P;
+            is_end[u] = valid[u] && ((ee + 1 >= gm.L) || (key[u + 1] != key[u]));
+            const uint32_t b = (gm.P == 1) ? pp[u] : pp[u] / (uint32_t)gm.P;
             const V* src = reinterpret_cast<const V*>(gbase + (size_t)b * gstride);
 #pragma unroll
             for (int m = 0; m < NCH; ++m)
@@ -116,6 +132,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             for (int m = 0; m < NCH; ++m)
                 if (is_end[u] && chunk_ok[m]) rv[u][m] = row[sl + m * lpr];
         }
+        if (e + U >= e1) cout = (e1 < gm.L) && (e + U == e1) && (key[U] == key[U - 1]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!valid[u]) continue;
@@ -148,48 +165,91 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         for (int m = 0; m < NCH; ++m)
             if (chunk_ok[m]) reinterpret_cast<V*>(dst)[sl + m * lpr] = acc[m];
     }
-    if (sl == 0) flags[(size_t)k * gm.ptiles_cap + g] = fl;
+    if (sl == 0) {
+        flags[(size_t)k * gm.ptiles_cap + g] = fl;
+        if (fl & FLAG_HEAD) head_list[atomicAdd(head_count, 1u)] = (uint32_t)gid;
+    }
 }
 
-// Runs that cross tile boundaries: the lane group of the tile where the run starts adds the
-// carried partial sums in ascending tile order and applies the row update once.
+// Runs that cross tile boundaries.  One CTA per listed head tile: the end of the run is found by
+// probing the tile flags 256 at a time, lane group `sub` adds the carry partials of tiles
+// g+1+sub, g+1+sub+nsub, ... (ascending, four loads in flight), the groups' sums are then added
+// in group order on top of the head partial, and the row is updated once.  The order depends only
+// on the geometry, so the result is bit-reproducible (the work list's order is not, but no
+// arithmetic depends on it).
 template <int VEC, int NCH>
 __global__ void __launch_bounds__(256)
 update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys, float lr,
                     const float* __restrict__ partial, const uint8_t* __restrict__ flags,
+                    const uint32_t* __restrict__ head_list, const uint32_t* __restrict__ head_count,
                     UpdateGeom gm) {
     using V = typename UV<VEC>::type;
+    __shared__ V red[256 * NCH];
+    __shared__ int s_first;
     const int lpr = 1 << gm.lpr_log2;
-    const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> gm.lpr_log2);
-    if (gid >= gm.total_groups) return;
-    const int sl = threadIdx.x & (lpr - 1);
-    const int k = gid / gm.tiles;
-    const int g = gid - k * gm.tiles;
-    const uint8_t* fk = flags + (size_t)k * gm.ptiles_cap;
-    if (!(fk[g] & FLAG_HEAD)) return;
+    const int tid = threadIdx.x;
+    const int sl = tid & (lpr - 1);
+    const int sub = tid >> gm.lpr_log2;
+    const int nsub = 256 >> gm.lpr_log2;
     const size_t D = (size_t)gm.C * VEC;
-    const float* pk = partial + (size_t)k * gm.ptiles_cap * 2 * D;
+    const uint32_t n_heads = *head_count;
 
-    V acc[NCH];
+    for (uint32_t h = blockIdx.x; h < n_heads; h += gridDim.x) {
+        const int gid = (int)head_list[h];
+        const int k = gid / gm.tiles;
+        const int g = gid - k * gm.tiles;
+        const uint8_t* fk = flags + (size_t)k * gm.ptiles_cap;
+        const float* pk = partial + (size_t)k * gm.ptiles_cap * 2 * D;
+        // where the run ends: the first later tile whose carried run stops inside it.  All 256
+        // threads probe one tile flag each per round (the table's last tile always stops it).
+        if (tid == 0) s_first = 0x7fffffff;
+        __syncthreads();
+        for (int base = g + 1;; base += 256) {
+            const int u = base + tid;
+            const uint8_t f = (u < gm.tiles) ? fk[u] : (uint8_t)FLAG_CARRY_ENDS;
+            if (f & FLAG_CARRY_ENDS) atomicMin(&s_first, u);
+            __syncthreads();
+            if (s_first != 0x7fffffff) break;
+        }
+        const int u_last = s_first;
+        V acc[NCH];
 #pragma unroll
-    for (int m = 0; m < NCH; ++m) {
-        acc[m] = UV<VEC>::zero();
-        if (sl + m * lpr < gm.C)
-            acc[m] = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D)[sl + m * lpr];
+        for (int m = 0; m < NCH; ++m) acc[m] = UV<VEC>::zero();
+        for (int u = g + 1 + sub; u <= u_last; u += 4 * nsub) {
+            V v[4][NCH];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int uu = u + q * nsub;
+                const V* src = reinterpret_cast<const V*>(pk + (size_t)uu * 2 * D);
+#pragma unroll
+                for (int m = 0; m < NCH; ++m)
+                    if (uu <= u_last && sl + m * lpr < gm.C) v[q][m] = src[sl + m * lpr];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int m = 0; m < NCH; ++m)
+                    if (u + q * nsub <= u_last && sl + m * lpr < gm.C) acc[m] = UV<VEC>::add(acc[m], v[q][m]);
+        }
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) red[(sub * NCH + m) * lpr + sl] = acc[m];
+        __syncthreads();
+        if (sub == 0) {
+            const int nact = min(nsub, u_last - g);
+            const uint32_t key = keys[(size_t)k * gm.cap + (size_t)(g + 1) * gm.tile - 1];
+            V* row = reinterpret_cast<V*>(desc[k].base + (size_t)key * D);
+            const V* hp = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D);
+#pragma unroll
+            for (int m = 0; m < NCH; ++m) {
+                if (sl + m * lpr < gm.C) {
+                    V total = hp[sl + m * lpr];
+                    for (int j = 0; j < nact; ++j) total = UV<VEC>::add(total, red[(j * NCH + m) * lpr + sl]);
+                    row[sl + m * lpr] = UV<VEC>::sgd(row[sl + m * lpr], total, lr);
+                }
+            }
+        }
+        __syncthreads();
     }
-    for (int u = g + 1; u < gm.tiles; ++u) {
-        const uint8_t f = fk[u];
-#pragma unroll
-        for (int m = 0; m < NCH; ++m)
-            if (sl + m * lpr < gm.C)
-                acc[m] = UV<VEC>::add(acc[m], reinterpret_cast<const V*>(pk + (size_t)u * 2 * D)[sl + m * lpr]);
-        if (f & FLAG_CARRY_ENDS) break;
-    }
-    const uint32_t key = keys[(size_t)k * gm.cap + (size_t)(g + 1) * gm.tile - 1];
-    V* row = reinterpret_cast<V*>(desc[k].base + (size_t)key * D);
-#pragma unroll
-    for (int m = 0; m < NCH; ++m)
-        if (sl + m * lpr < gm.C) row[sl + m * lpr] = UV<VEC>::sgd(row[sl + m * lpr], acc[m], lr);
 }
 
 static int lanes_per_row_log2(int C) {
@@ -235,7 +295,7 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     gm.tiles = (gm.L + gm.tile - 1) / gm.tile;
     gm.slots = slots;
     gm.slot0 = slot0;
-    gm.cap = t->max_lookups;
+    gm.cap = t->cap;
     gm.ptiles_cap = t->partial_tiles_cap;
     DLRMB_REQUIRE(gm.tiles <= gm.ptiles_cap, "internal: update tile capacity exceeded (%d > %lld)",
                   gm.tiles, (long long)gm.ptiles_cap);
@@ -244,12 +304,16 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     gm.total_groups = (int)groups;
     const int groups_per_block = 256 / lpr;
     const unsigned grid = (unsigned)ceil_div64(groups, groups_per_block);
-    constexpr int U = (NCH <= 2) ? 4 : 2;
+    static_assert(sizeof(uint4) == 16, "batch loads are 16 bytes");
     const uint32_t* keys = t->keys[t->sorted_buf];
     const uint32_t* pos = t->pos[t->sorted_buf];
-    update_tiles_kernel<VEC, NCH, U><<<grid, 256, 0, s>>>(t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, gm);
+    DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, sizeof(uint32_t), s));
+    update_tiles_kernel<VEC, NCH><<<grid, 256, 0, s>>>(t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags,
+                                                          t->head_list, t->head_count, gm);
     DLRMB_LAUNCH_CHECK();
-    update_fixup_kernel<VEC, NCH><<<grid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags, gm);
+    unsigned fgrid = (unsigned)(groups < (int64_t)t->sm_count * 8 ? groups : (int64_t)t->sm_count * 8);
+    update_fixup_kernel<VEC, NCH><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,
+                                                        t->head_list, t->head_count, gm);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }

@@ -306,33 +306,81 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- the step as ONE CUDA graph (kernels of this repo, cuBLAS GEMMs, NCCL collectives):
+    # inputs are copied into static device buffers, then the graph is replayed.  Falls back to
+    # eager launches if capture is unavailable; the mode is reported in config.step_launch.
+    s_dense, s_labels, s_idx = (t.clone() for t in devb[0])
+    s_loss = None
+    graph = None
+    mode = "eager"
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    train_step(s_dense, s_labels, s_idx)
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                s_loss = train_step(s_dense, s_labels, s_idx)
+            barrier()
+            mode = "cuda_graph"
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step(dense, labels, idx, non_blocking=False):
+        if graph is None:
+            return train_step(dense.to(dev, non_blocking=non_blocking), labels.to(dev, non_blocking=non_blocking),
+                              idx.to(dev, non_blocking=non_blocking))
+        s_dense.copy_(dense, non_blocking=non_blocking)
+        s_labels.copy_(labels, non_blocking=non_blocking)
+        s_idx.copy_(idx, non_blocking=non_blocking)
+        graph.replay()
+        return s_loss
+
     # ---- value: inputs resident in HBM ----
     for i in range(W):
-        train_step(*devb[i])
+        run_step(*devb[i])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _prof.enable(True)
     n0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(K):
-        train_step(*devb[W + i])
+        run_step(*devb[W + i])
     e1.record()
     barrier()
     launches = launch_count() - n0
-    _prof.enable(False)
+    if graph is not None:   # replays do not pass through the host-side counter: count per captured step
+        n1 = launch_count()
+        train_step(*devb[0])
+        torch.cuda.synchronize()
+        launches = (launch_count() - n1) * K
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel device time of this repo's kernels: the same K steps launched eagerly with
+    # a CUDA-event pair around every library call (events cannot be timed inside a graph) ----
+    _prof.enable(True)
+    for i in range(K):
+        train_step(*devb[W + i])
+    barrier()
+    _prof.enable(False)
     prof = _prof.summary()
 
     # ---- e2e: host inputs in, loss out, every step ----
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     def e2e_step(i):
         a, b, c = host[i]
-        l = train_step(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True), c.to(dev, non_blocking=True))
+        l = run_step(a, b, c, non_blocking=True)
         loss_host.copy_(l.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host[0])
@@ -360,7 +408,7 @@ def run_ours(args):
             "metric": "dlrm_train_samples_per_sec", "value": Bg * K / (ms_total * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(wl, world),
+            "config": dict(bench_config(wl, world), step_launch=mode),
             "e2e": {"value": Bg * K / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / K, "last_loss": last_loss},
             "gpu_launches": launches,
@@ -440,6 +488,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--cpu-rows-cap", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -142,9 +142,10 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
         TRY_CUDA(cudaMalloc((void**)&t->keys[i], sizeof(uint32_t) * nl));
         TRY_CUDA(cudaMalloc((void**)&t->pos[i], sizeof(uint32_t) * nl));
     }
-    t->radix_tiles_cap = ceil_div64(max_lookups, 2048);
+    t->radix_tiles_cap = ceil_div64(max_lookups, 4096);
     TRY_CUDA(cudaMalloc((void**)&t->tile_hist,
                         sizeof(uint32_t) * (size_t)ntab * 256 * (size_t)t->radix_tiles_cap));
+    TRY_CUDA(cudaMalloc((void**)&t->digit_total, sizeof(uint32_t) * (size_t)ntab * 256));
     t->partial_tiles_cap = update_tiles_cap(ntab, D, max_lookups, t->sm_count);
     TRY_CUDA(cudaMalloc((void**)&t->partial,
                         sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)D));
@@ -170,6 +171,7 @@ int32_t dlrmb_tables_destroy(dlrmb_tables* t) {
         cudaFree(t->pos[i]);
     }
     cudaFree(t->tile_hist);
+    cudaFree(t->digit_total);
     cudaFree(t->partial);
     cudaFree(t->tile_flags);
     cudaFree(t->head_list);

@@ -71,6 +71,7 @@ struct dlrmb_tables {
     uint32_t* keys[2] = {nullptr, nullptr};   // 0-based row ids, ping-pong
     uint32_t* pos[2] = {nullptr, nullptr};    // flat position b*P+p, ping-pong
     uint32_t* tile_hist = nullptr;            // radix: [ntab][256][tiles]
+    uint32_t* digit_total = nullptr;          // radix: [ntab][256]
     int sorted_buf = 0;                       // which ping-pong half holds the sorted stream
     int64_t radix_tiles_cap = 0;
     float* partial = nullptr;                 // [ntab][tiles][2][D] boundary partial sums

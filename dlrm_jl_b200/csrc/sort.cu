@@ -10,9 +10,9 @@
 //   * L <= kSmemSortMax: one CTA per table runs the whole LSD radix sort in shared memory
 //     (8-bit digits, as many passes as that table's row count needs); a single launch covers
 //     all tables.
-//   * larger L: least-significant-digit radix sort, 8-bit digits, tiles of 2048 keys, all tables
+//   * larger L: least-significant-digit radix sort, 8-bit digits, tiles of 4096 keys, all tables
 //     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
-//     (digit, tile) -> stable scatter whose in-tile ranks come from warp match_any + per-warp
+//     (digit, tile), one CTA per digit -> stable scatter whose in-tile ranks come from warp match_any + per-warp
 //     digit counters in shared memory.  The sort arrays of a whole batch fit L2 (126 MB), so the
 //     passes run at L2 rather than HBM speed.
 // Output: keys[sorted_buf] (ascending 0-based row ids) and pos[sorted_buf] (the stable
@@ -133,89 +133,96 @@ sort_small_kernel(const IdxT* __restrict__ idx, int idx_base, int L, const Table
 }
 
 // ---------------------------------------------------------------------------------------------
-// large path: LSD radix sort
+// large path: LSD radix sort over global memory, all tables batched through grid.y
 // ---------------------------------------------------------------------------------------------
 constexpr int RT = 256;        // threads per CTA
-constexpr int RI = 8;          // keys per thread
+constexpr int RI = 16;         // keys per thread
 constexpr int RTILE = RT * RI; // keys per tile
 
-template <typename IdxT>
-__global__ void __launch_bounds__(256)
-radix_prepare_kernel(const IdxT* __restrict__ idx, int idx_base, int L, uint32_t* __restrict__ keys,
-                     uint32_t* __restrict__ pos, int64_t cap) {
-    const int k = blockIdx.y;
-    const int step = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += step) {
-        keys[(size_t)k * cap + i] = (uint32_t)((int64_t)idx[(size_t)k * L + i] - idx_base);
-        pos[(size_t)k * cap + i] = (uint32_t)i;
+// exclusive prefix of `v` over the 256 threads of the CTA (thread order); wsum is 8 words of smem
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wsum, uint32_t* total_out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t run = inc - v, tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+        const uint32_t s = wsum[ww];
+        if (ww < w) run += s;
+        tot += s;
+    }
+    if (total_out) *total_out = tot;
+    __syncthreads();
+    return run;
 }
 
+// The first pass reads the caller's index array directly (FIRST): no separate conversion pass.
+template <typename IdxT, bool FIRST>
+__device__ __forceinline__ uint32_t radix_load_key(const IdxT* __restrict__ idx, int idx_base,
+                                                   const uint32_t* __restrict__ keys, int e) {
+    if (FIRST) return (uint32_t)((int64_t)idx[e] - idx_base);
+    return keys[e];
+}
+
+template <typename IdxT, bool FIRST>
 __global__ void __launch_bounds__(RT)
-radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t cap, int L, int shift,
-                  uint32_t* __restrict__ tile_hist, int tiles) {
+radix_hist_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t* __restrict__ keys, int64_t cap,
+                  int L, int shift, uint32_t* __restrict__ tile_hist, int tiles) {
     __shared__ uint32_t h[256];
     const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     h[tid] = 0;
     __syncthreads();
+    const IdxT* ik = idx + (size_t)k * L;
     const uint32_t* kin = keys + (size_t)k * cap;
     const int base = tile * RTILE;
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
         int e = base + i * RT + tid;
-        if (e < L) atomicAdd(&h[(kin[e] >> shift) & 255u], 1u);
+        if (e < L) atomicAdd(&h[(radix_load_key<IdxT, FIRST>(ik, idx_base, kin, e) >> shift) & 255u], 1u);
     }
     __syncthreads();
     tile_hist[((size_t)k * 256 + tid) * tiles + tile] = h[tid];
 }
 
-// exclusive scan, in place, over the 256*tiles counters of one table laid out [digit][tile]
-__global__ void __launch_bounds__(1024)
-radix_scan_kernel(uint32_t* __restrict__ tile_hist, int tiles) {
-    __shared__ uint32_t warp_tot[32];
-    uint32_t* h = tile_hist + (size_t)blockIdx.x * 256 * tiles;
-    const int n = 256 * tiles;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    uint32_t sum = 0;
-    for (int i = lo; i < hi; ++i) sum += h[i];
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
+// One CTA per (digit, table): exclusive scan over that digit's per-tile counts (contiguous, so
+// the loads coalesce), in place, plus the digit's total.
+__global__ void __launch_bounds__(RT)
+radix_scan_kernel(uint32_t* __restrict__ tile_hist, uint32_t* __restrict__ digit_total, int tiles) {
+    __shared__ uint32_t wsum[8];
+    const int d = blockIdx.x, k = blockIdx.y;
+    uint32_t* h = tile_hist + ((size_t)k * 256 + d) * tiles;
+    uint32_t running = 0;
+    for (int c = 0; c < tiles; c += RT) {
+        const int i = c + threadIdx.x;
+        const uint32_t v = i < tiles ? h[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan_256(v, wsum, &tot);
+        if (i < tiles) h[i] = running + ex;
+        running += tot;
     }
-    if (lane == 31) warp_tot[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t t = warp_tot[lane], ti = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, ti, o);
-            if (lane >= o) ti += v;
-        }
-        warp_tot[lane] = ti - t;
-    }
-    __syncthreads();
-    uint32_t run = warp_tot[w] + inc - sum;
-    for (int i = lo; i < hi; ++i) {
-        uint32_t v = h[i];
-        h[i] = run;
-        run += v;
-    }
+    if (threadIdx.x == 0) digit_total[k * 256 + d] = running;
 }
 
+template <typename IdxT, bool FIRST>
 __global__ void __launch_bounds__(RT)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ pos_in,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap,
-                     int L, int shift, const uint32_t* __restrict__ tile_hist, int tiles) {
+radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t* __restrict__ keys_in,
+                     const uint32_t* __restrict__ pos_in, uint32_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ pos_out, int64_t cap, int L, int shift,
+                     const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__ digit_total, int tiles) {
     __shared__ uint32_t wh[RT / 32][256];
+    __shared__ uint32_t wsum[8];
     const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
     for (int i = tid; i < (RT / 32) * 256; i += RT) (&wh[0][0])[i] = 0;
     __syncthreads();
 
+    const IdxT* ik = idx + (size_t)k * L;
     const uint32_t* kin = keys_in + (size_t)k * cap;
     const uint32_t* pin = pos_in + (size_t)k * cap;
     const int base = tile * RTILE + w * (32 * RI);
@@ -223,19 +230,18 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
-        int e = base + i * 32 + lane;
-        bool valid = e < L;
-        key[i] = valid ? kin[e] : 0xffffffffu;
-        val[i] = valid ? pin[e] : 0u;
+        const int e = base + i * 32 + lane;
+        const bool valid = e < L;
+        key[i] = valid ? radix_load_key<IdxT, FIRST>(ik, idx_base, kin, e) : 0xffffffffu;
+        val[i] = FIRST ? (uint32_t)e : (valid ? pin[e] : 0u);
     }
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
-        int e = base + i * 32 + lane;
-        bool valid = e < L;
-        uint32_t dig = valid ? ((key[i] >> shift) & 255u) : (256u + lane);
-        uint32_t peers = __match_any_sync(0xffffffffu, dig);
-        uint32_t lt = peers & lt_mask;
-        uint32_t b = valid ? wh[w][dig] : 0u;
+        const bool valid = (base + i * 32 + lane) < L;
+        const uint32_t dig = valid ? ((key[i] >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, dig);
+        const uint32_t lt = peers & lt_mask;
+        const uint32_t b = valid ? wh[w][dig] : 0u;
         __syncwarp();
         if (valid && lt == 0) wh[w][dig] = b + __popc(peers);
         __syncwarp();
@@ -243,11 +249,13 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     }
     __syncthreads();
     {
-        // thread d owns digit d: turn per-warp counts into per-warp global start offsets
-        uint32_t run = tile_hist[((size_t)k * 256 + tid) * tiles + tile];
+        // thread d owns digit d: bucket start (scan of the digit totals) + this tile's offset
+        // inside the bucket, then the per-warp starts
+        const uint32_t dbase = block_excl_scan_256(digit_total[k * 256 + tid], wsum, nullptr);
+        uint32_t run = dbase + tile_hist[((size_t)k * 256 + tid) * tiles + tile];
 #pragma unroll
         for (int ww = 0; ww < RT / 32; ++ww) {
-            uint32_t c = wh[ww][tid];
+            const uint32_t c = wh[ww][tid];
             wh[ww][tid] = run;
             run += c;
         }
@@ -257,9 +265,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     uint32_t* po = pos_out + (size_t)k * cap;
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
-        int e = base + i * 32 + lane;
-        if (e < L) {
-            uint32_t dst = wh[w][(key[i] >> shift) & 255u] + rank[i];
+        if ((base + i * 32 + lane) < L) {
+            const uint32_t dst = wh[w][(key[i] >> shift) & 255u] + rank[i];
             ko[dst] = key[i];
             po[dst] = val[i];
         }
@@ -290,24 +297,25 @@ static int launch_sort_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, 
     }
     const int tiles = (int)ceil_div64(L, RTILE);
     DLRMB_REQUIRE(tiles <= t->radix_tiles_cap, "internal: radix tile capacity exceeded");
-    {
-        int64_t bx = ceil_div64(L, 256 * 4);
-        if (bx > t->sm_count * 8) bx = t->sm_count * 8;
-        dim3 grid((unsigned)bx, (unsigned)t->ntab);
-        radix_prepare_kernel<IdxT><<<grid, 256, 0, s>>>(idx, idx_base, L, t->keys[0], t->pos[0], cap);
-        DLRMB_LAUNCH_CHECK();
-    }
     const int passes = radix_passes(t->max_rows);
     int cur = 0;
     dim3 grid((unsigned)tiles, (unsigned)t->ntab);
+    dim3 sgrid(256u, (unsigned)t->ntab);
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
-        radix_hist_kernel<<<grid, RT, 0, s>>>(t->keys[cur], cap, L, shift, t->tile_hist, tiles);
+        if (p == 0)
+            radix_hist_kernel<IdxT, true><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], cap, L, shift, t->tile_hist, tiles);
+        else
+            radix_hist_kernel<IdxT, false><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], cap, L, shift, t->tile_hist, tiles);
         DLRMB_LAUNCH_CHECK();
-        radix_scan_kernel<<<t->ntab, 1024, 0, s>>>(t->tile_hist, tiles);
+        radix_scan_kernel<<<sgrid, RT, 0, s>>>(t->tile_hist, t->digit_total, tiles);
         DLRMB_LAUNCH_CHECK();
-        radix_scatter_kernel<<<grid, RT, 0, s>>>(t->keys[cur], t->pos[cur], t->keys[cur ^ 1], t->pos[cur ^ 1],
-                                                 cap, L, shift, t->tile_hist, tiles);
+        if (p == 0)
+            radix_scatter_kernel<IdxT, true><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], t->pos[cur], t->keys[cur ^ 1],
+                                                                t->pos[cur ^ 1], cap, L, shift, t->tile_hist, t->digit_total, tiles);
+        else
+            radix_scatter_kernel<IdxT, false><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], t->pos[cur], t->keys[cur ^ 1],
+                                                                 t->pos[cur ^ 1], cap, L, shift, t->tile_hist, t->digit_total, tiles);
         DLRMB_LAUNCH_CHECK();
         cur ^= 1;
     }

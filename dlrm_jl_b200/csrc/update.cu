@@ -48,7 +48,8 @@ template <> struct UV<1> {
     }
 };
 
-enum : uint8_t { FLAG_CARRY_IN = 1, FLAG_CARRY_ENDS = 2, FLAG_HEAD = 4 };
+enum : uint8_t { FLAG_CARRY_IN = 1, FLAG_CARRY_ENDS = 2, FLAG_HEAD = 4, FLAG_ABSORBED = 8 };
+constexpr int kAbsorbSeg = 64;   // tiles per CTA of the absorb pass
 
 struct UpdateGeom {
     int L, P, tiles, tile, lpr_log2, C, slots, slot0;
@@ -171,6 +172,78 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     }
 }
 
+// Very long runs (hot rows: Zipf heads, tables with a handful of rows) cross hundreds or
+// thousands of tiles, nearly all of them "pass-through" tiles that hold nothing but that one
+// run.  Before the per-run fix-up, every CTA of this pass takes kAbsorbSeg consecutive tiles and
+// folds each stretch of consecutive pass-through tiles into its first tile's carry slot (ascending
+// order), marking the others absorbed.  The fix-up CTA of a run then only adds one partial per
+// stretch, so a run of n tiles costs n / kAbsorbSeg adds on its critical path instead of n.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256)
+update_absorb_kernel(float* __restrict__ partial, uint8_t* __restrict__ flags, UpdateGeom gm) {
+    using V = typename UV<VEC>::type;
+    __shared__ V red[256 * NCH];
+    __shared__ uint8_t f[kAbsorbSeg];
+    __shared__ int n_pass;
+    const int k = blockIdx.y;
+    const int t0 = blockIdx.x * kAbsorbSeg;
+    const int t1 = min(gm.tiles, t0 + kAbsorbSeg);
+    const int tid = threadIdx.x;
+    uint8_t* fk = flags + (size_t)k * gm.ptiles_cap;
+    if (tid == 0) n_pass = 0;
+    __syncthreads();
+    if (tid < kAbsorbSeg) {
+        const uint8_t v = (t0 + tid < t1) ? fk[t0 + tid] : (uint8_t)0xff;
+        f[tid] = v;
+        if (v == FLAG_CARRY_IN) atomicAdd(&n_pass, 1);
+    }
+    __syncthreads();
+    if (n_pass < 2) return;
+
+    const int lpr = 1 << gm.lpr_log2;
+    const int sl = tid & (lpr - 1);
+    const int sub = tid >> gm.lpr_log2;
+    const int nsub = 256 >> gm.lpr_log2;
+    const size_t D = (size_t)gm.C * VEC;
+    float* pk = partial + (size_t)k * gm.ptiles_cap * 2 * D;
+    int t = 0;
+    const int nt = t1 - t0;
+    while (t < nt) {                     // uniform across the CTA: f[] is in shared memory
+        if (f[t] != FLAG_CARRY_IN) { ++t; continue; }
+        int len = 1;
+        while (t + len < nt && f[t + len] == FLAG_CARRY_IN) ++len;
+        if (len >= 2) {
+            V acc[NCH];
+#pragma unroll
+            for (int m = 0; m < NCH; ++m) acc[m] = UV<VEC>::zero();
+            for (int j = sub; j < len; j += nsub) {      // group `sub`: tiles t+sub, t+sub+nsub, ...
+                const V* src = reinterpret_cast<const V*>(pk + (size_t)(t0 + t + j) * 2 * D);
+#pragma unroll
+                for (int m = 0; m < NCH; ++m)
+                    if (sl + m * lpr < gm.C) acc[m] = UV<VEC>::add(acc[m], src[sl + m * lpr]);
+            }
+#pragma unroll
+            for (int m = 0; m < NCH; ++m) red[(sub * NCH + m) * lpr + sl] = acc[m];
+            __syncthreads();
+            if (sub == 0) {
+                const int nact = min(nsub, len);
+                V* dst = reinterpret_cast<V*>(pk + (size_t)(t0 + t) * 2 * D);
+#pragma unroll
+                for (int m = 0; m < NCH; ++m) {
+                    if (sl + m * lpr < gm.C) {
+                        V total = red[m * lpr + sl];
+                        for (int j = 1; j < nact; ++j) total = UV<VEC>::add(total, red[(j * NCH + m) * lpr + sl]);
+                        dst[sl + m * lpr] = total;
+                    }
+                }
+            }
+            if (tid >= 1 && tid < len) fk[t0 + t + tid] = (uint8_t)(FLAG_CARRY_IN | FLAG_ABSORBED);
+            __syncthreads();
+        }
+        t += len;
+    }
+}
+
 // Runs that cross tile boundaries.  One CTA per listed head tile: the end of the run is found by
 // probing the tile flags 256 at a time, lane group `sub` adds the carry partials of tiles
 // g+1+sub, g+1+sub+nsub, ... (ascending, four loads in flight), the groups' sums are then added
@@ -217,19 +290,21 @@ update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         for (int m = 0; m < NCH; ++m) acc[m] = UV<VEC>::zero();
         for (int u = g + 1 + sub; u <= u_last; u += 4 * nsub) {
             V v[4][NCH];
+            bool take[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int uu = u + q * nsub;
                 const V* src = reinterpret_cast<const V*>(pk + (size_t)uu * 2 * D);
+                take[q] = uu <= u_last && !(fk[uu] & FLAG_ABSORBED);
 #pragma unroll
                 for (int m = 0; m < NCH; ++m)
-                    if (uu <= u_last && sl + m * lpr < gm.C) v[q][m] = src[sl + m * lpr];
+                    if (take[q] && sl + m * lpr < gm.C) v[q][m] = src[sl + m * lpr];
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int m = 0; m < NCH; ++m)
-                    if (u + q * nsub <= u_last && sl + m * lpr < gm.C) acc[m] = UV<VEC>::add(acc[m], v[q][m]);
+                    if (take[q] && sl + m * lpr < gm.C) acc[m] = UV<VEC>::add(acc[m], v[q][m]);
         }
 #pragma unroll
         for (int m = 0; m < NCH; ++m) red[(sub * NCH + m) * lpr + sl] = acc[m];
@@ -311,6 +386,11 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     update_tiles_kernel<VEC, NCH><<<grid, 256, 0, s>>>(t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags,
                                                           t->head_list, t->head_count, gm);
     DLRMB_LAUNCH_CHECK();
+    if (false && gm.tiles >= 2 * kAbsorbSeg) {   // TODO(absorb v2)
+        dim3 agrid((unsigned)ceil_div64(gm.tiles, kAbsorbSeg), (unsigned)t->ntab);
+        update_absorb_kernel<VEC, NCH><<<agrid, 256, 0, s>>>(t->partial, t->tile_flags, gm);
+        DLRMB_LAUNCH_CHECK();
+    }
     unsigned fgrid = (unsigned)(groups < (int64_t)t->sm_count * 8 ? groups : (int64_t)t->sm_count * 8);
     update_fixup_kernel<VEC, NCH><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,
                                                         t->head_list, t->head_count, gm);

@@ -166,7 +166,8 @@ class EmbeddingTables:
                 with _prof.range("sort"):
                     _lib.check(self._lib.dlrmb_embedding_sort(
                         self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, self._side_stream.cuda_stream))
-                idx.record_stream(self._side_stream)
+                if not torch.cuda.is_current_stream_capturing():
+                    idx.record_stream(self._side_stream)
                 self._sorted_event.record(self._side_stream)
             self._pending_side = True
         else:

@@ -33,6 +33,27 @@ class TableSharding:
     world: int
     owner: List[int]
     local: List[List[int]]      # local[r] = global table ids owned by rank r, ascending
+    _slot_cache: Optional[dict] = None
+
+    def slot_index(self, r: int, device) -> torch.Tensor:
+        """Device tensor of the interaction slots (1 + table id) of rank r's tables (cached: no
+        host-to-device copy inside the step, which also keeps the step CUDA-graph capturable)."""
+        if self._slot_cache is None:
+            self._slot_cache = {}
+        key = (r, str(device))
+        if key not in self._slot_cache:
+            self._slot_cache[key] = torch.tensor([1 + k for k in self.local[r]], dtype=torch.int64, device=device)
+        return self._slot_cache[key]
+
+    def owner_order(self, device) -> torch.Tensor:
+        """Table ids grouped by owner rank (the send order of the index all-to-all), cached."""
+        if self._slot_cache is None:
+            self._slot_cache = {}
+        key = ("order", str(device))
+        if key not in self._slot_cache:
+            order = [k for r in range(self.world) for k in self.local[r]]
+            self._slot_cache[key] = torch.tensor(order, dtype=torch.int64, device=device)
+        return self._slot_cache[key]
 
     @classmethod
     def build(cls, rows: Sequence[int], world: int) -> "TableSharding":
@@ -63,7 +84,7 @@ def exchange_indices(idx_local: torch.Tensor, sh: TableSharding, rank: int, grou
     W = sh.world
     if W == 1:
         return idx_local
-    send = torch.cat([idx_local[sh.local[r]] for r in range(W)], dim=0).contiguous()   # grouped by owner
+    send = idx_local.index_select(0, sh.owner_order(idx_local.device))                 # grouped by owner
     t_mine = len(sh.local[rank])
     recv = torch.empty((W, t_mine, Bl, P), dtype=idx_local.dtype, device=idx_local.device)
     in_splits = [len(sh.local[r]) * Bl * P for r in range(W)]
@@ -92,8 +113,7 @@ def exchange_pooled(pooled: torch.Tensor, T: torch.Tensor, sh: TableSharding, ra
         if counts[r] == 0:
             continue
         chunk = recv[off:off + Bl * counts[r] * D].view(Bl, counts[r], D)
-        slots = torch.as_tensor([1 + k for k in sh.local[r]], device=T.device)
-        T.index_copy_(1, slots, chunk)
+        T.index_copy_(1, sh.slot_index(r, T.device), chunk)
         off += Bl * counts[r] * D
 
 
@@ -105,7 +125,7 @@ def exchange_grads(dT: torch.Tensor, sh: TableSharding, rank: int, group=None) -
         return dT[:, 1:, :].contiguous()
     counts = sh.counts()
     t_mine = counts[rank]
-    send = torch.cat([dT[:, [1 + k for k in sh.local[r]], :].reshape(-1) for r in range(W)])
+    send = torch.cat([dT.index_select(1, sh.slot_index(r, dT.device)).reshape(-1) for r in range(W)])
     recv = torch.empty((W * Bl, t_mine, D), dtype=dT.dtype, device=dT.device)
     in_splits = [Bl * counts[r] * D for r in range(W)]
     out_splits = [Bl * t_mine * D] * W

@@ -238,7 +238,7 @@ def run_ours(args):
     from dlrm_jl_b200 import _prof, launch_count
     from dlrm_jl_b200.interact import DotInteraction
     from dlrm_jl_b200.model import create_mlp
-    from dlrm_jl_b200.sharded import ShardedEmbedding, allreduce_dense_grads
+    from dlrm_jl_b200.sharded import FlatGrads, ShardedEmbedding
     from dlrm_jl_b200.train import bce_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -268,20 +268,31 @@ def run_ours(args):
     dot = DotInteraction()
     anchor = torch.zeros(1, device=dev, requires_grad=True)
 
+    flat = FlatGrads(params, world)
+    mlp_stream = torch.cuda.Stream()
+
     def train_step(dense, labels, idx):
-        for p in params:
-            p.grad = None
+        main = torch.cuda.current_stream()
+        flat.zero()
+        # bottom MLP on a second stream: it is independent of the embedding exchange until the
+        # interaction, so its GEMMs hide the index / pooled-embedding all-to-alls (and, because
+        # autograd replays backward ops on their forward stream, its backward hides the gradient
+        # all-to-all and the sparse update)
+        mlp_stream.wait_stream(main)
+        with torch.cuda.stream(mlp_stream):
+            x = bottom(dense)
         T = se.lookup(idx, anchor)
         se.sort_async()
-        x = bottom(dense)
+        main.wait_stream(mlp_stream)
         z = dot(x, T)
         out = top(z).reshape(-1)
         loss = bce_loss(out, labels)
         loss.backward()
-        allreduce_dense_grads(params, world)
+        main.wait_stream(mlp_stream)
+        flat.allreduce()
         with torch.no_grad():
-            torch._foreach_add_(params, [p.grad for p in params], alpha=-LR)
-        se.update(LR, presorted=True)
+            torch._foreach_add_(params, flat.views, alpha=-LR * flat.scale)
+        se.update(LR * flat.scale, presorted=True)
         return loss.detach()
 
     # synthetic batches: host-pinned copies (e2e) and device copies (value)
@@ -420,9 +431,13 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
+    # Leave without tearing NCCL down: destroying a communicator that captured CUDA graphs still
+    # reference can block for minutes.  Everything measured is already printed and flushed.
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def hot_path_report(wl, world, rank, se, prof, ms_step, batches):

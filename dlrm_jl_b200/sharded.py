@@ -157,7 +157,8 @@ class _ShardedLookupFn(torch.autograd.Function):
         pooled = torch.empty((Bg, len(se.local_ids), D), dtype=torch.float32, device=idx_local.device)
         if len(se.local_ids):
             se.lookup_fn(idx_owned, pooled, 0)
-        T = torch.zeros((Bl, 1 + se.ntab, D), dtype=torch.float32, device=idx_local.device)
+        # slot 0 needs no clearing: the interaction kernel writes x there (fused fast_vcat)
+        T = torch.empty((Bl, 1 + se.ntab, D), dtype=torch.float32, device=idx_local.device)
         exchange_pooled(pooled, T, se.sharding, se.rank, se.group)
         return T
 
@@ -223,6 +224,34 @@ class ShardedEmbedding:
         if len(self.local_ids) == 0:
             return
         self.update_fn(self.idx_owned, self.owned_grad, lr, self.slot0, presorted)
+
+
+class FlatGrads:
+    """Dense (MLP) gradients as views of ONE flat buffer, so the data-parallel reduction is a
+    single in-place all-reduce with no pack/unpack copies (NVSwitch: bucket sized for launch
+    latency, not link count).  `zero()` before backward, `allreduce()` after; the 1/world mean
+    factor is left to the caller's learning rate (`scale`)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], world: int, group=None):
+        self.params = list(params)
+        self.world, self.group = world, group
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=self.params[0].dtype, device=self.params[0].device)
+        off = 0
+        self.views = []
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.scale = 1.0 / world
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def allreduce(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
 
 
 def allreduce_dense_grads(params: Sequence[torch.nn.Parameter], world: int, group=None) -> None:

@@ -48,7 +48,7 @@ struct TableDesc {
 // consecutive entries of the per-table sorted (row id, position) stream.
 constexpr int kUpdateTile = 16;
 // Largest per-table lookup count the single-CTA shared-memory sort handles (sort.cu).
-constexpr int kSmemSortMax = 4096;
+constexpr int kSmemSortMax = 16384;
 
 }  // namespace dlrmb
 

@@ -229,7 +229,7 @@ def test_interaction_host_entry_points():
 # sort / dedup (bit-exact integers)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L,rows", [(1, 5), (2, 2), (128, 1000), (1280, 1000), (2048, 3), (2048, 10131227),
-                                    (4096, 50), (4097, 50), (5000, 100000), (70000, 7), (1 << 16, 1 << 20),
+                                    (4096, 50), (4097, 50), (5000, 100000), (8192, 3), (12000, 40000000), (16384, 1000), (16385, 1000), (70000, 7), (1 << 16, 1 << 20),
                                     (200000, 40000000)])
 @pytest.mark.parametrize("dtype,base", [(np.int32, 0), (np.int64, 1)])
 def test_sort_dedup_bit_exact(L, rows, dtype, base):

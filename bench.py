@@ -239,7 +239,7 @@ def run_ours(args):
     from dlrm_jl_b200.interact import DotInteraction
     from dlrm_jl_b200.model import create_mlp
     from dlrm_jl_b200.sharded import FlatGrads, ShardedEmbedding
-    from dlrm_jl_b200.train import bce_loss
+    from dlrm_jl_b200.train import SigmoidBCELoss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -263,8 +263,38 @@ def run_ours(args):
     gen = torch.Generator().manual_seed(51234)
     bottom = create_mlp(wl["bottom"], 0, dev, gen)
     top = create_mlp(wl["top"], len(wl["top"]), dev, gen)
+    top_logits = torch.nn.Sequential(*list(top)[:-1])   # the final sigmoid is fused into the loss kernel
+    sigmoid_bce = SigmoidBCELoss(dev)
     params = list(bottom.parameters()) + list(top.parameters())
     se = ShardedEmbedding.create(wl["rows"], D, B, wl["P"], rank, world, dev)
+    exchange = "none (single GPU)"
+    exchange_check = None
+    if world > 1:
+        exchange = "nccl all-to-all"
+        if args.exchange == "p2p":
+            ok, why = 1.0, ""
+            try:
+                # reference result through the NCCL path, then the fused path on the same indices
+                chk = torch.from_numpy(synth_batch(wl, 999, rank)[2]).to(dev)
+                with torch.no_grad():
+                    t_nccl = se.lookup(chk, torch.zeros(1, device=dev)).clone()
+                se.enable_peer_exchange(B)
+                with torch.no_grad():
+                    t_p2p = se.lookup(chk, torch.zeros(1, device=dev))
+                if not torch.equal(t_nccl[:, 1:], t_p2p[:, 1:]):
+                    ok, why = 0.0, "fused exchange result differs from the NCCL path"
+            except Exception as exc:  # noqa: BLE001
+                ok, why = 0.0, f"{type(exc).__name__}: {exc}"
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank takes the same decision
+            if float(flag.item()) == 1.0:
+                exchange = "fused lookup + NVLink peer stores (forward), nccl all-to-all (backward)"
+                exchange_check = "fused peer-store lookup == NCCL all-to-all path, bit for bit, on every rank"
+            else:
+                se.peer = None
+                exchange_check = f"fell back to NCCL ({why or 'another rank failed'})"
+                if rank == 0:
+                    print(f"[bench] peer exchange disabled: {exchange_check}", file=sys.stderr)
     dot = DotInteraction()
     anchor = torch.zeros(1, device=dev, requires_grad=True)
 
@@ -285,8 +315,7 @@ def run_ours(args):
         se.sort_async()
         main.wait_stream(mlp_stream)
         z = dot(x, T)
-        out = top(z).reshape(-1)
-        loss = bce_loss(out, labels)
+        loss = sigmoid_bce(top_logits(z), labels)
         loss.backward()
         main.wait_stream(mlp_stream)
         flat.allreduce()
@@ -340,7 +369,9 @@ def run_ours(args):
             mode = "cuda_graph"
         except Exception as exc:  # noqa: BLE001
             if rank == 0:
+                import traceback
                 print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eager", file=sys.stderr)
+                traceback.print_exc()
             graph = None
             torch.cuda.synchronize()
 
@@ -380,8 +411,11 @@ def run_ours(args):
 
     # ---- per-kernel device time of this repo's kernels: the same K steps launched eagerly with
     # a CUDA-event pair around every library call (events cannot be timed inside a graph) ----
+    # Each step is queued behind a ~2 ms device-side spin so the host runs ahead of the GPU: the
+    # event pairs then bracket back-to-back kernels instead of host launch gaps.
     _prof.enable(True)
     for i in range(K):
+        torch.cuda._sleep(4_000_000)
         train_step(*devb[W + i])
     barrier()
     _prof.enable(False)
@@ -419,7 +453,7 @@ def run_ours(args):
             "metric": "dlrm_train_samples_per_sec", "value": Bg * K / (ms_total * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(bench_config(wl, world), step_launch=mode),
+            "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check),
             "e2e": {"value": Bg * K / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / K, "last_loss": last_loss},
             "gpu_launches": launches,
@@ -486,8 +520,18 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, batches):
                             "frac_hbm": (lookup_bytes + update_bytes) / (emb_ms * 1e-3) / 1e9 / hbm_peak,
                             "includes": "lookup + index sort + scatter-add/SGD kernels"}
     if dom:
+        traffic, traffic_src = None, None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", f"r01_ncu_traffic_{wl['name']}.json")) as fh:
+                tj = json.load(fh)
+            if world == 1 and dom in tj["kernels"]:
+                traffic = tj["kernels"][dom]["dram_bytes_read"] + tj["kernels"][dom]["dram_bytes_write"]
+                traffic_src = f"profiles/r01_ncu_traffic_{wl['name']}.json ({tj['report']})"
+        except Exception:
+            pass
         out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": hbm_peak,
-                           "unit": "GB/s", "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": None,
+                           "unit": "GB/s", "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": traffic,
+                           "traffic_source": traffic_src,
                            "peak_source": peak_src,
                            "note": "achieved = algorithmic bytes per launch / CUDA-event duration inside the timed region"}
     return out
@@ -503,6 +547,8 @@ def main():
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--cpu-rows-cap", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -46,6 +46,15 @@ SIGNATURES = {
     "dlrmb_embedding_bwd_sgd": (_i32, [_vp, *_idx_args, _vp, _i32, _i32, _f32, _vp]),
     "dlrmb_sort_dedup_export": (_i32, [_vp, _i32, _vp, _vp, _vp, C.POINTER(_i32)]),
     "dlrmb_check_indices": (_i32, [_vp, *_idx_args, _i32]),
+    "dlrmb_bce_sigmoid_fwd_bwd": (_i32, [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "dlrmb_xbuf_create": (_i32, [_i32, _i64, C.POINTER(_vp)]),
+    "dlrmb_xbuf_destroy": (_i32, [_vp]),
+    "dlrmb_xbuf_ptr": (_i32, [_vp, C.POINTER(_vp)]),
+    "dlrmb_xbuf_ipc_handle": (_i32, [_vp, _vp]),
+    "dlrmb_xbuf_open": (_i32, [_i32, _vp, C.POINTER(_vp)]),
+    "dlrmb_xbuf_close": (_i32, [_i32, _vp]),
+    "dlrmb_tables_set_slot_map": (_i32, [_vp, C.POINTER(_i32)]),
+    "dlrmb_embedding_fwd_p2p": (_i32, [_vp, *_idx_args, C.POINTER(_vp), _i32, _i32, _i32, _vp]),
     "dlrmb_embedding_fwd_host": (_i32, [_vp, *_idx_args, _vp, _i32, _i32]),
     "dlrmb_interaction_fwd_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "dlrmb_interaction_bwd_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -166,6 +166,7 @@ int32_t dlrmb_tables_destroy(dlrmb_tables* t) {
     if (t->own_stream) cudaStreamSynchronize(t->own_stream);
     cudaFree(t->slab);
     cudaFree(t->d_desc);
+    cudaFree(t->d_slotmap);
     for (int i = 0; i < 2; ++i) {
         cudaFree(t->keys[i]);
         cudaFree(t->pos[i]);
@@ -375,6 +376,16 @@ int32_t dlrmb_check_indices(dlrmb_tables* t, const void* idx, int32_t idx_bytes,
         return DLRMB_EOOB;
     }
     return DLRMB_OK;
+}
+
+int32_t dlrmb_bce_sigmoid_fwd_bwd(int32_t device, const float* logits, const float* labels, int32_t B,
+                                  float* prob, float* dlogits, float* loss, float* scratch,
+                                  dlrmb_stream stream) {
+    DLRMB_REQUIRE(B > 0, "B must be positive (got %d)", B);
+    DLRMB_REQUIRE(logits && labels && dlogits && loss && scratch, "null buffer");
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    return launch_bce_sigmoid(logits, labels, B, prob, dlogits, loss, scratch, (cudaStream_t)stream);
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------

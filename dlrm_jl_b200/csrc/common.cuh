@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include <atomic>
 
@@ -65,6 +68,7 @@ struct dlrmb_tables {
     int64_t* h_offsets = nullptr;    // element offsets of each table inside `slab`
     float* slab = nullptr;           // all tables, one allocation
     dlrmb::TableDesc* d_desc = nullptr;
+    int32_t* d_slotmap = nullptr;    // sharded use: interaction slot of each local table
     cudaStream_t own_stream = nullptr;
 
     // sort / update workspace (all [ntab][max_lookups] unless noted)
@@ -113,6 +117,8 @@ int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s);
 int launch_check_indices(dlrmb_tables* t, const void* d_idx, int idx_bytes, int idx_base, int B,
                          int P, cudaStream_t s, long long* bad_table, long long* bad_pos,
                          long long* bad_val);
+int launch_bce_sigmoid(const float* z, const float* y, int B, float* prob, float* dz, float* loss,
+                       float* scratch, cudaStream_t s);
 int device_sm_count(int device);
 int64_t update_tiles_cap(int ntab, int D, int64_t max_lookups, int sm_count);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)

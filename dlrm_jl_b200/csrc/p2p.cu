@@ -1,0 +1,220 @@
+// Fused lookup + exchange for table-wise sharded embeddings: the owner of a table pools its rows
+// for the GLOBAL batch and stores every pooled row straight into the interaction input buffer of
+// the rank that owns the sample, through NVLink peer mappings (cudaIpc).  This replaces
+// "lookup -> staging buffer -> NCCL all-to-all -> unpack" (dlrm_jl_b200/sharded.py) by one kernel:
+// the transfer is the kernel's own store stream, posted row by row (whole 128-byte lines), so it
+// overlaps the gathers that are still in flight.
+//
+// New functionality (DLRM.jl is single-process); BASELINE.json north_star / SURVEY.md section 8(e).
+#include "common.cuh"
+
+struct dlrmb_xbuf {
+    int device;
+    void* ptr;
+    size_t bytes;
+};
+
+namespace dlrmb {
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+    float* p[kMaxPeers];
+};
+
+// Same mapping as lookup_gather_kernel (one thread per 16-byte chunk, 4 independent index -> row
+// chains), but sample b lives on rank b / B_local and table k lands in slot slotmap[k].
+template <typename IdxT, int VEC, int U>
+__global__ void __launch_bounds__(256)
+lookup_p2p_kernel(const TableDesc* __restrict__ desc, const int32_t* __restrict__ slotmap,
+                  const IdxT* __restrict__ idx, int idx_base, uint32_t Bg, uint32_t B_local, uint32_t P,
+                  uint32_t C, PeerPtrs peers, int slots) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    const int k = blockIdx.y;
+    const float* __restrict__ tb = desc[k].base;
+    const IdxT* __restrict__ ik = idx + (size_t)k * Bg * P;
+    const uint32_t n = Bg * C;
+    const uint32_t step = gridDim.x * blockDim.x;
+    const size_t D = (size_t)C * VEC;
+    const size_t slot_off = (size_t)slotmap[k] * D;
+    const size_t ostride = (size_t)slots * D;
+
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step * U) {
+        uint32_t b[U], c[U];
+        bool ok[U];
+        V acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t tt = t + (uint32_t)u * step;
+            ok[u] = tt < n;
+            b[u] = tt / C;
+            c[u] = tt - b[u] * C;
+        }
+        if (P == 1) {
+            int64_t row[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) row[u] = ok[u] ? (int64_t)__ldg(ik + b[u]) - idx_base : 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) acc[u] = __ldg(reinterpret_cast<const V*>(tb + (size_t)row[u] * D) + c[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const IdxT* ip = ik + (size_t)b[u] * P;
+                V a = __ldg(reinterpret_cast<const V*>(tb + (size_t)((int64_t)__ldg(ip) - idx_base) * D) + c[u]);
+                for (uint32_t p = 1; p < P; ++p) {
+                    V v = __ldg(reinterpret_cast<const V*>(tb + (size_t)((int64_t)__ldg(ip + p) - idx_base) * D) + c[u]);
+                    if constexpr (VEC == 4) {
+                        a = make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
+                    } else {
+                        a = __fadd_rn(a, v);
+                    }
+                }
+                acc[u] = a;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const uint32_t h = b[u] / B_local;
+            const uint32_t bl = b[u] - h * B_local;
+            float* dst = peers.p[h] + (size_t)bl * ostride + slot_off;
+            reinterpret_cast<V*>(dst)[c[u]] = acc[u];
+        }
+    }
+}
+
+template <typename IdxT, int VEC>
+static int launch_p2p_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int Bg, int P, const PeerPtrs& peers,
+                        int B_local, int slots, cudaStream_t s) {
+    const uint32_t C = t->D / VEC;
+    const int64_t n = (int64_t)Bg * C;
+    DLRMB_REQUIRE(n < (1ll << 30), "B * D too large for one lookup launch (%lld chunks)", (long long)n);
+    constexpr int U = 4;
+    int64_t bx = ceil_div64(n, 256 * U);
+    const int64_t cap = (int64_t)t->sm_count * 32;
+    if (bx * t->ntab > cap) bx = cap / t->ntab > 0 ? cap / t->ntab : 1;
+    dim3 grid((unsigned)bx, (unsigned)t->ntab);
+    lookup_p2p_kernel<IdxT, VEC, U><<<grid, 256, 0, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
+                                                         peers, slots);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+}  // namespace dlrmb
+
+using namespace dlrmb;
+
+extern "C" {
+
+int32_t dlrmb_xbuf_create(int32_t device, int64_t bytes, dlrmb_xbuf** out) {
+    DLRMB_REQUIRE(out != nullptr && bytes > 0, "bad xbuf arguments");
+    *out = nullptr;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    DLRMB_CUDA(cudaSetDevice(device));
+    void* p = nullptr;
+    DLRMB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    DLRMB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    dlrmb_xbuf* x = new dlrmb_xbuf{device, p, (size_t)bytes};
+    *out = x;
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_xbuf_destroy(dlrmb_xbuf* x) {
+    if (!x) return DLRMB_OK;
+    cudaFree(x->ptr);
+    delete x;
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_xbuf_ptr(dlrmb_xbuf* x, void** dev) {
+    DLRMB_REQUIRE(x && dev, "null argument");
+    *dev = x->ptr;
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_xbuf_ipc_handle(dlrmb_xbuf* x, uint8_t* handle64) {
+    DLRMB_REQUIRE(x && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    DLRMB_CUDA(cudaIpcGetMemHandle(&h, x->ptr));
+    memcpy(handle64, &h, 64);
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_xbuf_open(int32_t device, const uint8_t* handle64, void** peer_ptr) {
+    DLRMB_REQUIRE(handle64 && peer_ptr, "null argument");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    DLRMB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    DLRMB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    *peer_ptr = p;
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_xbuf_close(int32_t device, void* peer_ptr) {
+    if (!peer_ptr) return DLRMB_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    DLRMB_CUDA(cudaSetDevice(device));
+    DLRMB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_tables_set_slot_map(dlrmb_tables* t, const int32_t* slots) {
+    DLRMB_REQUIRE(t && slots, "null argument");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    DLRMB_CUDA(cudaSetDevice(t->device));
+    if (!t->d_slotmap) DLRMB_CUDA(cudaMalloc((void**)&t->d_slotmap, sizeof(int32_t) * t->ntab));
+    DLRMB_CUDA(cudaMemcpy(t->d_slotmap, slots, sizeof(int32_t) * t->ntab, cudaMemcpyHostToDevice));
+    if (prev >= 0 && prev != t->device) cudaSetDevice(prev);
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
+                                int32_t B_local, int32_t slots, dlrmb_stream stream) {
+    DLRMB_REQUIRE(t != nullptr && idx != nullptr && peer_T != nullptr, "null argument");
+    DLRMB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, "idx_bytes must be 4 or 8 (got %d)", idx_bytes);
+    DLRMB_REQUIRE(world >= 1 && world <= kMaxPeers, "world must be in 1..%d (got %d)", kMaxPeers, world);
+    DLRMB_REQUIRE(B_local > 0 && B_global == B_local * world, "B_global (%d) must equal B_local (%d) * world (%d)",
+                  B_global, B_local, world);
+    DLRMB_REQUIRE((int64_t)B_global * P <= t->max_lookups, "B*P = %lld exceeds max_lookups = %lld",
+                  (long long)B_global * P, (long long)t->max_lookups);
+    if (!t->d_slotmap) {
+        set_error("dlrmb_embedding_fwd_p2p needs dlrmb_tables_set_slot_map first");
+        return DLRMB_ESTATE;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    DLRMB_CUDA(cudaSetDevice(t->device));
+    PeerPtrs peers;
+    bool aligned = (t->D % 4 == 0);
+    for (int r = 0; r < kMaxPeers; ++r) {
+        peers.p[r] = r < world ? peer_T[r] : nullptr;
+        if (r < world) {
+            DLRMB_REQUIRE(peer_T[r] != nullptr, "peer_T[%d] is null", r);
+            aligned = aligned && ((reinterpret_cast<uintptr_t>(peer_T[r]) & 15) == 0);
+        }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (idx_bytes == 4)
+        rc = aligned ? launch_p2p_t<uint32_t, 4>(t, (const uint32_t*)idx, idx_base, B_global, P, peers, B_local, slots, s)
+                     : launch_p2p_t<uint32_t, 1>(t, (const uint32_t*)idx, idx_base, B_global, P, peers, B_local, slots, s);
+    else
+        rc = aligned ? launch_p2p_t<int64_t, 4>(t, (const int64_t*)idx, idx_base, B_global, P, peers, B_local, slots, s)
+                     : launch_p2p_t<int64_t, 1>(t, (const int64_t*)idx, idx_base, B_global, P, peers, B_local, slots, s);
+    if (prev >= 0 && prev != t->device) cudaSetDevice(prev);
+    return rc;
+}
+
+}  // extern "C"

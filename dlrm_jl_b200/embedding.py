@@ -153,6 +153,22 @@ class EmbeddingTables:
                 self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, out.data_ptr(), slots, slot0,
                 _stream_ptr(self.device)))
 
+    def set_slot_map(self, slots: Sequence[int]) -> None:
+        """Sharded use: interaction slot (1 + global table id) of each local table."""
+        arr = (C.c_int32 * self.ntab)(*[int(v) for v in slots])
+        _lib.check(self._lib.dlrmb_tables_set_slot_map(self._h, arr))
+
+    def lookup_p2p(self, idx: torch.Tensor, peer_ptrs: Sequence[int], B_local: int, slots: int, idx_base: int = 0) -> None:
+        """Pool this rank's tables for the global batch and store every pooled row directly into
+        the owning rank's interaction buffer (NVLink peer stores): lookup + forward exchange fused."""
+        ntab, Bg, P = idx.shape
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_ptrs])
+        with _prof.range("lookup"):
+            _lib.check(self._lib.dlrmb_embedding_fwd_p2p(
+                self._h, idx.data_ptr(), idx.element_size(), idx_base, Bg, P, arr, world, B_local, slots,
+                _stream_ptr(self.device)))
+
     def sort(self, idx: torch.Tensor, idx_base: int = 0, side_stream: bool = False) -> None:
         """Index sort/dedup for the next update.  With ``side_stream`` it is issued on a second
         stream (it depends on the indices only) so it overlaps the forward/backward pass."""

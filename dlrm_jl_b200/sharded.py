@@ -133,6 +133,53 @@ def exchange_grads(dT: torch.Tensor, sh: TableSharding, rank: int, group=None) -
     return recv
 
 
+class PeerExchange:
+    """The interaction input buffer T [B_local][1 + ntab][D] of every rank, allocated by the
+    library and mapped into every other rank's address space through CUDA IPC, so the owner of a
+    table can store pooled rows straight into the buffer of the rank that owns the sample
+    (`EmbeddingTables.lookup_p2p`).  `barrier` is the stream-ordered collective that orders the
+    peer stores against the consumers (a one-element NCCL all-reduce by default)."""
+
+    def __init__(self, B_local: int, ntab: int, D: int, rank: int, world: int, device, group=None,
+                 barrier: Optional[Callable] = None):
+        import ctypes as C
+
+        from . import _lib
+        from .embedding import _DevicePtrView
+        self.lib = _lib.load()
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device(device)
+        self.shape = (B_local, 1 + ntab, D)
+        nbytes = B_local * (1 + ntab) * D * 4
+        h = C.c_void_p()
+        _lib.check(self.lib.dlrmb_xbuf_create(self.device.index or 0, nbytes, C.byref(h)))
+        self._xbuf = h
+        p = C.c_void_p()
+        _lib.check(self.lib.dlrmb_xbuf_ptr(h, C.byref(p)))
+        handle = (C.c_uint8 * 64)()
+        _lib.check(self.lib.dlrmb_xbuf_ipc_handle(h, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peer_ptrs = []
+        for r in range(world):
+            if r == rank:
+                self.peer_ptrs.append(p.value)
+                continue
+            buf = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+            q = C.c_void_p()
+            _lib.check(self.lib.dlrmb_xbuf_open(self.device.index or 0, buf, C.byref(q)))
+            self.peer_ptrs.append(q.value)
+        self.T = torch.as_tensor(_DevicePtrView(p.value, self.shape, self), device=self.device)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._barrier = barrier
+
+    def barrier(self) -> None:
+        if self._barrier is not None:
+            self._barrier()
+        else:
+            dist.all_reduce(self._flag, group=self.group)
+
+
 class _ShardedLookupFn(torch.autograd.Function):
     """lookup (owner side) + pooled all-to-all forward; gradient all-to-all backward.  The
     owner-side gradient [B_global][t_mine][D] is parked on ``ctx_obj.owned_grad`` for the sparse
@@ -154,6 +201,15 @@ class _ShardedLookupFn(torch.autograd.Function):
         idx_owned = exchange_indices(idx_local, se.sharding, se.rank, se.group)
         se.idx_owned = idx_owned
         Bg = idx_owned.shape[1]
+        if se.peer is not None:
+            # fused path: pooled rows go straight into the owners' T over NVLink; the barrier
+            # orders every rank's stores before anyone reads its own T
+            if len(se.local_ids):
+                se.tables.lookup_p2p(idx_owned, se.peer.peer_ptrs, Bl, 1 + se.ntab)
+            se.peer.barrier()
+            # a fresh alias every step: the persistent buffer tensor itself must never pick up
+            # autograd history (a stale grad_fn from an earlier step would chain the graphs)
+            return se.peer.T.detach()
         pooled = torch.empty((Bg, len(se.local_ids), D), dtype=torch.float32, device=idx_local.device)
         if len(se.local_ids):
             se.lookup_fn(idx_owned, pooled, 0)
@@ -192,6 +248,17 @@ class ShardedEmbedding:
         self.idx_owned: Optional[torch.Tensor] = None
         self.owned_grad: Optional[torch.Tensor] = None
         self.slot0 = 1 if world == 1 else 0
+        self.peer: Optional[PeerExchange] = None
+
+    def enable_peer_exchange(self, B_local: int, barrier: Optional[Callable] = None) -> None:
+        """Switch the forward exchange to the fused lookup + NVLink peer-store kernel.  Safe with
+        one buffer per rank when every step also runs the backward exchange (a collective all
+        ranks reach only after they have finished reading T)."""
+        if self.world == 1:
+            return
+        self.tables.set_slot_map([1 + k for k in self.local_ids] or [1])
+        self.peer = PeerExchange(B_local, self.ntab, self.D, self.rank, self.world, self.tables.device,
+                                 self.group, barrier)
 
     @classmethod
     def create(cls, rows: Sequence[int], D: int, B_local: int, P: int, rank: int, world: int, device,

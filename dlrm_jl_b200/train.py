@@ -38,6 +38,43 @@ def bce_loss(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return _BCELoss.apply(x, y)
 
 
+class _SigmoidBCE(torch.autograd.Function):
+    """Final sigmoid + bce_loss + its pullback as ONE kernel launch (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, logits: torch.Tensor, labels: torch.Tensor, scratch: torch.Tensor):
+        from . import _lib, _prof
+        z = logits.reshape(-1).contiguous()
+        y = labels.reshape(-1).contiguous()
+        if not z.is_cuda:
+            raise _lib.DLRMB200Error(_lib.EINVAL, "sigmoid_bce_loss runs on the GPU only (no CPU fallback)")
+        dz = torch.empty_like(z)
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        with _prof.range("bce"):
+            _lib.check(_lib.load().dlrmb_bce_sigmoid_fwd_bwd(
+                z.device.index or 0, z.data_ptr(), y.data_ptr(), z.numel(), None, dz.data_ptr(), loss.data_ptr(),
+                scratch.data_ptr(), int(torch.cuda.current_stream(z.device).cuda_stream)))
+        ctx.save_for_backward(dz)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return (dz * g).reshape(ctx.shape), None, None
+
+
+class SigmoidBCELoss:
+    """Callable replacing `sigmoid` (last top-MLP layer) + `bce_loss`: takes the top MLP's
+    pre-sigmoid logits.  Owns the 65-float scratch the kernel's ordered block reduction needs."""
+
+    def __init__(self, device):
+        self.scratch = torch.zeros(80, dtype=torch.float32, device=device)
+
+    def __call__(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        return _SigmoidBCE.apply(logits, labels, self.scratch)
+
+
 class LossWrapper:
     """``wrap_loss(loss_fn; kw...)`` (src/train/train.jl:74-92)."""
 

@@ -120,6 +120,35 @@ int32_t dlrmb_sort_dedup_export(dlrmb_tables* t, int32_t k, int64_t* uniq, int32
 int32_t dlrmb_check_indices(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
                             int32_t B, int32_t P, int32_t idx_on_host);
 
+/* ---- loss: the top MLP's final sigmoid (src/model/model.jl:87-90) fused with bce_loss and its
+ * pullback (src/train/train.jl:33-41, 45-71).  logits/labels [B] device f32.  Writes the mean loss
+ * (one float), d(loss)/d(logit) [B] (sensitivity 1 folded in) and, if `prob` is non-NULL, the
+ * sigmoid outputs [B].  `scratch` is a caller-provided, zero-initialised device buffer of at least
+ * 65 floats that must not be shared between concurrent calls. ---- */
+int32_t dlrmb_bce_sigmoid_fwd_bwd(int32_t device, const float* logits, const float* labels, int32_t B,
+                                  float* prob, float* dlogits, float* loss, float* scratch,
+                                  dlrmb_stream stream);
+
+/* ---- multi-GPU, table-wise sharded embeddings (new functionality: DLRM.jl is single-process).
+ * Exchange buffers are library-owned device allocations that other ranks (one process per GPU)
+ * map through CUDA IPC; dlrmb_embedding_fwd_p2p pools this rank's tables for the GLOBAL batch
+ * (B_global = B_local * world, sample b belongs to rank b / B_local) and stores each pooled row
+ * directly into peer_T[owner of the sample][b_local][slot_map[k]][:] over NVLink -- the lookup and
+ * the forward all-to-all in one kernel.  peer_T is a host array of `world` device pointers (this
+ * rank's own buffer at index `rank`).  The caller orders the launch against the peers' use of the
+ * buffers (a stream-ordered collective after it, see dlrm_jl_b200/sharded.py). ---------------- */
+typedef struct dlrmb_xbuf dlrmb_xbuf;
+int32_t dlrmb_xbuf_create(int32_t device, int64_t bytes, dlrmb_xbuf** out);
+int32_t dlrmb_xbuf_destroy(dlrmb_xbuf* x);
+int32_t dlrmb_xbuf_ptr(dlrmb_xbuf* x, void** dev);
+int32_t dlrmb_xbuf_ipc_handle(dlrmb_xbuf* x, uint8_t* handle64);
+int32_t dlrmb_xbuf_open(int32_t device, const uint8_t* handle64, void** peer_ptr);
+int32_t dlrmb_xbuf_close(int32_t device, void* peer_ptr);
+int32_t dlrmb_tables_set_slot_map(dlrmb_tables* t, const int32_t* slots);
+int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
+                                int32_t B_local, int32_t slots, dlrmb_stream stream);
+
 /* ---- host-buffer entry points: every pointer is host memory (pageable or pinned); this is
  * the form a CPU-resident DLRM.jl model calls.  Copies run inside the call. -------------- */
 int32_t dlrmb_embedding_fwd_host(dlrmb_tables* t, const void* idx, int32_t idx_bytes,

@@ -255,6 +255,15 @@ def bce_loss_back(x: np.ndarray, y: np.ndarray, delta: float = 1.0) -> np.ndarra
     return (dl * ((F32(1) - y) / c - y / dd)).astype(F32)
 
 
+def sigmoid_bce(logits: np.ndarray, y: np.ndarray):
+    """Last top-MLP activation (sigmoid, src/model/model.jl:87-90) + bce_loss + its pullback
+    chained through the sigmoid: returns (loss, dloss/dlogits)."""
+    z = logits.astype(F32).reshape(-1)
+    x = (F32(1) / (F32(1) + np.exp(-z))).astype(F32)
+    dx = bce_loss_back(x, y)
+    return bce_loss(x, y), (dx * x * (F32(1) - x)).astype(F32)
+
+
 def mlp_forward(layers: List[Tuple[np.ndarray, np.ndarray]], x: np.ndarray, sigmoid_last: bool):
     """Dense chain, weights PyTorch-oriented [out][in] (src/data/criteo.jl:494-534): relu on
     every layer; for the top MLP the last layer is sigmoid instead."""

@@ -349,6 +349,37 @@ def test_update_host_entry_point():
 
 
 # ------------------------------------------------------------------------------------------------
+# fused sigmoid + BCE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 4, 128, 2048, 100003])
+def test_sigmoid_bce_fused_vs_oracle(B):
+    from dlrm_jl_b200.train import SigmoidBCELoss
+    rng = np.random.default_rng(B)
+    z = (rng.standard_normal(B) * 3).astype(np.float32)
+    z[: min(B, 2)] = [40.0, -40.0][: min(B, 2)]                     # saturated: exercises the -100 clamp
+    y = rng.random(B).astype(np.float32)                            # soft labels, as in the goldens
+    loss_ref, dz_ref = O.sigmoid_bce(z, y)
+    fn = SigmoidBCELoss(_dev())
+    zt = torch.from_numpy(z).to(_dev()).requires_grad_(True)
+    for _ in range(2):                                              # second call: the block counter reset itself
+        zt.grad = None
+        loss = fn(zt.reshape(-1, 1), torch.from_numpy(y).to(_dev()))
+        loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-6 * max(1.0, abs(float(loss_ref)))
+    assert O.rel_err(zt.grad.cpu().numpy().reshape(-1), dz_ref) < FWD_RTOL
+
+
+@pytest.mark.parametrize("name", ["single", "multi"])
+def test_sigmoid_bce_fused_golden_loss(name):
+    from dlrm_jl_b200.train import SigmoidBCELoss
+    g = load_golden(name)
+    p = g["mlp_top"].reshape(-1).astype(np.float64)
+    logits = np.log(p / (1.0 - p)).astype(np.float32)               # invert the stored sigmoid outputs
+    loss = SigmoidBCELoss(_dev())(torch.from_numpy(logits).to(_dev()), torch.from_numpy(g["labels"].reshape(-1)).to(_dev()))
+    assert abs(float(loss) - float(g["loss"])) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------
 # end to end: the reference's validate() on both goldens, and the hand-typed PyTorch case
 # ------------------------------------------------------------------------------------------------
 def _torch_mlp(layers, sigmoid_last):

@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--full", action="store_true", help="with --sweep: all of P in {1,4,16,64} and Zipf in {0,1.05,1.2}")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     results = []
@@ -169,10 +170,10 @@ def main():
             for D in (16, 32, 64, 128, 256):
                 if rows * D * 4 > 120e9:
                     continue
-                for P in (1, 4, 16, 64):
+                for P in ((1, 4, 16, 64) if a.full else (1, 16)):
                     B = (1 << 20) // P
-                    for alpha in (0.0, 1.05):
-                        r = run_case([rows], D, B, P, alpha, 4, not a.no_graph, 5, interaction=False,
+                    for alpha in ((0.0, 1.05, 1.2) if a.full else (0.0, 1.05)):
+                        r = run_case([rows], D, B, P, alpha, 3, not a.no_graph, 3, interaction=False,
                                      label=f"sweep rows={rows} D={D} P={P} zipf={alpha}")
                         results.append(r)
                         print(json.dumps(r), flush=True)

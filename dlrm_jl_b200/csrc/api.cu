@@ -144,8 +144,8 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
     }
     t->radix_tiles_cap = ceil_div64(max_lookups, 4096);
     TRY_CUDA(cudaMalloc((void**)&t->tile_hist,
-                        sizeof(uint32_t) * (size_t)ntab * 256 * (size_t)t->radix_tiles_cap));
-    TRY_CUDA(cudaMalloc((void**)&t->digit_total, sizeof(uint32_t) * (size_t)ntab * 256));
+                        sizeof(uint32_t) * (size_t)ntab * 512 * (size_t)t->radix_tiles_cap));
+    TRY_CUDA(cudaMalloc((void**)&t->digit_total, sizeof(uint32_t) * (size_t)ntab * 512));
     t->partial_tiles_cap = update_tiles_cap(ntab, D, max_lookups, t->sm_count);
     TRY_CUDA(cudaMalloc((void**)&t->partial,
                         sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)D));

@@ -10,7 +10,7 @@
 //   * L <= kSmemSortMax: one CTA per table runs the whole LSD radix sort in shared memory
 //     (8-bit digits, as many passes as that table's row count needs); a single launch covers
 //     all tables.
-//   * larger L: least-significant-digit radix sort, 8-bit digits, tiles of 4096 keys, all tables
+//   * larger L: least-significant-digit radix sort, digits of up to 9 bits, tiles of 4096 keys, all tables
 //     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
 //     (digit, tile), one CTA per digit -> stable scatter whose in-tile ranks come from warp match_any + per-warp
 //     digit counters in shared memory.  The sort arrays of a whole batch fit L2 (126 MB), so the
@@ -182,24 +182,33 @@ __device__ __forceinline__ uint32_t radix_load_key(const IdxT* __restrict__ idx,
     return keys[e];
 }
 
+// Digits are up to 9 bits wide (NB = 512 bins max): the pass count is ceil(bits / 9) and the bits
+// are spread evenly over the passes, so 1e8 rows (27 bits) take 3 passes and 1e5 rows (17 bits) 2.
+constexpr int NB = 512;
+
 template <typename IdxT, bool FIRST>
 __global__ void __launch_bounds__(RT)
 radix_hist_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t* __restrict__ keys, int64_t cap,
-                  int L, int shift, uint32_t* __restrict__ tile_hist, int tiles) {
-    __shared__ uint32_t h[256];
+                  int L, int shift, uint32_t mask, uint32_t* __restrict__ tile_hist, int tiles) {
+    __shared__ uint32_t h[NB];
     const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     h[tid] = 0;
+    h[tid + RT] = 0;
     __syncthreads();
     const IdxT* ik = idx + (size_t)k * L;
     const uint32_t* kin = keys + (size_t)k * cap;
     const int base = tile * RTILE;
+    uint32_t kk[RI];
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
-        int e = base + i * RT + tid;
-        if (e < L) atomicAdd(&h[(radix_load_key<IdxT, FIRST>(ik, idx_base, kin, e) >> shift) & 255u], 1u);
+        const int e = base + i * RT + tid;
+        kk[i] = e < L ? radix_load_key<IdxT, FIRST>(ik, idx_base, kin, e) : 0u;
     }
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+        if (base + i * RT + tid < L) atomicAdd(&h[(kk[i] >> shift) & mask], 1u);
     __syncthreads();
-    tile_hist[((size_t)k * 256 + tid) * tiles + tile] = h[tid];
+    for (uint32_t d = tid; d <= mask; d += RT) tile_hist[((size_t)k * NB + d) * tiles + tile] = h[d];
 }
 
 // One CTA per (digit, table): exclusive scan over that digit's per-tile counts (contiguous, so
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(RT)
 radix_scan_kernel(uint32_t* __restrict__ tile_hist, uint32_t* __restrict__ digit_total, int tiles) {
     __shared__ uint32_t wsum[8];
     const int d = blockIdx.x, k = blockIdx.y;
-    uint32_t* h = tile_hist + ((size_t)k * 256 + d) * tiles;
+    uint32_t* h = tile_hist + ((size_t)k * NB + d) * tiles;
     uint32_t running = 0;
     for (int c = 0; c < tiles; c += RT) {
         const int i = c + threadIdx.x;
@@ -218,20 +227,20 @@ radix_scan_kernel(uint32_t* __restrict__ tile_hist, uint32_t* __restrict__ digit
         if (i < tiles) h[i] = running + ex;
         running += tot;
     }
-    if (threadIdx.x == 0) digit_total[k * 256 + d] = running;
+    if (threadIdx.x == 0) digit_total[k * NB + d] = running;
 }
 
 template <typename IdxT, bool FIRST>
 __global__ void __launch_bounds__(RT)
 radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t* __restrict__ keys_in,
                      const uint32_t* __restrict__ pos_in, uint32_t* __restrict__ keys_out,
-                     uint32_t* __restrict__ pos_out, int64_t cap, int L, int shift,
+                     uint32_t* __restrict__ pos_out, int64_t cap, int L, int shift, uint32_t mask,
                      const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__ digit_total, int tiles) {
-    __shared__ uint32_t wh[RT / 32][256];
+    __shared__ uint32_t wh[RT / 32][NB];
     __shared__ uint32_t wsum[8];
     const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < (RT / 32) * 256; i += RT) (&wh[0][0])[i] = 0;
+    for (int i = tid; i < (RT / 32) * NB; i += RT) (&wh[0][0])[i] = 0;
     __syncthreads();
 
     const IdxT* ik = idx + (size_t)k * L;
@@ -250,7 +259,7 @@ radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t*
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
         const bool valid = (base + i * 32 + lane) < L;
-        const uint32_t dig = valid ? ((key[i] >> shift) & 255u) : (256u + lane);
+        const uint32_t dig = valid ? ((key[i] >> shift) & mask) : (NB + lane);
         const uint32_t peers = __match_any_sync(0xffffffffu, dig);
         const uint32_t lt = peers & lt_mask;
         const uint32_t b = valid ? wh[w][dig] : 0u;
@@ -261,15 +270,29 @@ radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t*
     }
     __syncthreads();
     {
-        // thread d owns digit d: bucket start (scan of the digit totals) + this tile's offset
-        // inside the bucket, then the per-warp starts
-        const uint32_t dbase = block_excl_scan_256(digit_total[k * 256 + tid], wsum, nullptr);
-        uint32_t run = dbase + tile_hist[((size_t)k * 256 + tid) * tiles + tile];
+        // thread t owns digits 2t and 2t+1: bucket start (scan of the digit totals) + this tile's
+        // offset inside the bucket, then the per-warp starts
+        const uint32_t d0 = 2 * tid, d1 = 2 * tid + 1;
+        const uint32_t t0 = d0 <= mask ? digit_total[k * NB + d0] : 0u;
+        const uint32_t t1 = d1 <= mask ? digit_total[k * NB + d1] : 0u;
+        const uint32_t ex = block_excl_scan_256(t0 + t1, wsum, nullptr);
+        if (d0 <= mask) {
+            uint32_t run = ex + tile_hist[((size_t)k * NB + d0) * tiles + tile];
 #pragma unroll
-        for (int ww = 0; ww < RT / 32; ++ww) {
-            const uint32_t c = wh[ww][tid];
-            wh[ww][tid] = run;
-            run += c;
+            for (int ww = 0; ww < RT / 32; ++ww) {
+                const uint32_t c = wh[ww][d0];
+                wh[ww][d0] = run;
+                run += c;
+            }
+        }
+        if (d1 <= mask) {
+            uint32_t run = ex + t0 + tile_hist[((size_t)k * NB + d1) * tiles + tile];
+#pragma unroll
+            for (int ww = 0; ww < RT / 32; ++ww) {
+                const uint32_t c = wh[ww][d1];
+                wh[ww][d1] = run;
+                run += c;
+            }
         }
     }
     __syncthreads();
@@ -278,17 +301,17 @@ radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t*
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
         if ((base + i * 32 + lane) < L) {
-            const uint32_t dst = wh[w][(key[i] >> shift) & 255u] + rank[i];
+            const uint32_t dst = wh[w][(key[i] >> shift) & mask] + rank[i];
             ko[dst] = key[i];
             po[dst] = val[i];
         }
     }
 }
 
-static int radix_passes(int64_t max_rows) {
+static int key_bits(int64_t max_rows) {
     int bits = 1;
     while (bits < 32 && (1ll << bits) < max_rows) ++bits;
-    return (bits + 7) / 8;
+    return bits;
 }
 
 template <typename IdxT>
@@ -309,27 +332,32 @@ static int launch_sort_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, 
     }
     const int tiles = (int)ceil_div64(L, RTILE);
     DLRMB_REQUIRE(tiles <= t->radix_tiles_cap, "internal: radix tile capacity exceeded");
-    const int passes = radix_passes(t->max_rows);
+    const int bits = key_bits(t->max_rows);
+    const int passes = (bits + 8) / 9;
+    const int per_pass = (bits + passes - 1) / passes;     // <= 9
     int cur = 0;
     dim3 grid((unsigned)tiles, (unsigned)t->ntab);
-    dim3 sgrid(256u, (unsigned)t->ntab);
+    int shift = 0;
     for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
+        const int nb = (bits - shift) < per_pass ? (bits - shift) : per_pass;
+        const uint32_t mask = (1u << nb) - 1u;
+        dim3 sgrid(mask + 1u, (unsigned)t->ntab);
         if (p == 0)
-            radix_hist_kernel<IdxT, true><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], cap, L, shift, t->tile_hist, tiles);
+            radix_hist_kernel<IdxT, true><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], cap, L, shift, mask, t->tile_hist, tiles);
         else
-            radix_hist_kernel<IdxT, false><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], cap, L, shift, t->tile_hist, tiles);
+            radix_hist_kernel<IdxT, false><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], cap, L, shift, mask, t->tile_hist, tiles);
         DLRMB_LAUNCH_CHECK();
         radix_scan_kernel<<<sgrid, RT, 0, s>>>(t->tile_hist, t->digit_total, tiles);
         DLRMB_LAUNCH_CHECK();
         if (p == 0)
             radix_scatter_kernel<IdxT, true><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], t->pos[cur], t->keys[cur ^ 1],
-                                                                t->pos[cur ^ 1], cap, L, shift, t->tile_hist, t->digit_total, tiles);
+                                                                t->pos[cur ^ 1], cap, L, shift, mask, t->tile_hist, t->digit_total, tiles);
         else
             radix_scatter_kernel<IdxT, false><<<grid, RT, 0, s>>>(idx, idx_base, t->keys[cur], t->pos[cur], t->keys[cur ^ 1],
-                                                                 t->pos[cur ^ 1], cap, L, shift, t->tile_hist, t->digit_total, tiles);
+                                                                 t->pos[cur ^ 1], cap, L, shift, mask, t->tile_hist, t->digit_total, tiles);
         DLRMB_LAUNCH_CHECK();
         cur ^= 1;
+        shift += nb;
     }
     t->sorted_buf = cur;
     return DLRMB_OK;

@@ -10,7 +10,7 @@
 //   * L <= kSmemSortMax: one CTA per table runs the whole LSD radix sort in shared memory
 //     (8-bit digits, as many passes as that table's row count needs); a single launch covers
 //     all tables.
-//   * larger L: least-significant-digit radix sort, digits of up to 9 bits, tiles of 4096 keys, all tables
+//   * larger L: least-significant-digit radix sort, digits of up to 9 bits, tiles of 1024 keys, all tables
 //     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
 //     (digit, tile), one CTA per digit -> stable scatter whose in-tile ranks come from warp match_any + per-warp
 //     digit counters in shared memory.  The sort arrays of a whole batch fit L2 (126 MB), so the
@@ -148,7 +148,7 @@ static int launch_sort_small(dlrmb_tables* t, const IdxT* idx, int idx_base, int
 // large path: LSD radix sort over global memory, all tables batched through grid.y
 // ---------------------------------------------------------------------------------------------
 constexpr int RT = 256;        // threads per CTA
-constexpr int RI = 16;         // keys per thread
+constexpr int RI = 4;          // keys per thread (small tiles: many CTAs, the passes are latency-bound)
 constexpr int RTILE = RT * RI; // keys per tile
 
 // exclusive prefix of `v` over the 256 threads of the CTA (thread order); wsum is 8 words of smem

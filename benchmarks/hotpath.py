@@ -99,7 +99,7 @@ def time_graph(fn, nb: int, use_graph: bool, iters: int) -> float:
     return 1e3 * a.elapsed_time(b) / (iters * nb)
 
 
-def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label=""):
+def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label="", only=None):
     dev = torch.device("cuda", 0)
     peak, peak_src = hbm_peak()
     ntab = len(rows)
@@ -120,6 +120,16 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
     def rec(name, us, nbytes):
         res[name] = {"us": us, "algorithmic_bytes": int(nbytes), "gbs": nbytes / us / 1e3, "frac_hbm": nbytes / us / 1e3 / peak}
 
+    if only and only.startswith("interaction"):
+        w = interaction_width(F, D)
+        t.lookup(idx[0], T, 1)
+        g = torch.randn((B, w), device=dev)
+        if only == "interaction_fwd":
+            rec("interaction_fwd", time_graph(lambda i: interaction_fwd(T), nb, use_graph, iters), B * (F * D + w) * 4)
+        else:
+            rec("interaction_bwd", time_graph(lambda i: interaction_bwd(g, T), nb, use_graph, iters), B * (w + 2 * F * D + D) * 4)
+        t.close()
+        return res
     us = time_graph(lambda i: t.lookup(idx[i], T, 1), nb, use_graph, iters)
     lookup_bytes = ntab * (L * D * 4 + B * D * 4 + L * 4)
     rec("lookup", us, lookup_bytes)
@@ -163,6 +173,9 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--full", action="store_true", help="with --sweep: all of P in {1,4,16,64} and Zipf in {0,1.05,1.2}")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="time just this kernel (e.g. interaction_fwd)")
+    ap.add_argument("--small-tables", action="store_true",
+                    help="cap every table at 1000 rows (the interaction kernels do not depend on table size; keeps ncu replays cheap)")
     a = ap.parse_args()
     results = []
     if a.sweep:
@@ -186,7 +199,9 @@ def main():
             rows, D = a.rows or [1_000_000], a.D
         if a.workload and a.D != 64:
             D = a.D
-        r = run_case(rows, D, a.B, a.P, a.zipf, a.nb, not a.no_graph, a.iters, label=a.workload or "custom")
+        if a.small_tables:
+            rows = [min(r, 1000) for r in rows]
+        r = run_case(rows, D, a.B, a.P, a.zipf, a.nb, not a.no_graph, a.iters, label=a.workload or "custom", only=a.only)
         results.append(r)
         print(json.dumps(r), flush=True)
     if a.out:

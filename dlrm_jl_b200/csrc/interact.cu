@@ -17,11 +17,15 @@
 //     bulk copies (cp.async.bulk, one per feature row, completion on an mbarrier), row stride
 //     padded by 4 floats so the 128-bit operand reads of different rows spread across the bank
 //     groups;
-//   - forward: each thread owns a TB x TB register block of the Gram lower triangle and walks
-//     k in float4 steps; results are staged in shared memory so that the CTA's output, which
-//     is again one contiguous global range, is written fully coalesced;
+//   - forward: each thread owns a TB x TB register block of the Gram lower triangle (TB = 3 by
+//     default; 6 and 9, and a k-split across adjacent lanes combined with warp shuffles, are
+//     compiled in but measured slower at DLRM shapes) and walks k in float4 steps; results are
+//     staged in shared memory so that the CTA's output, which is again one contiguous global
+//     range, is written fully coalesced;
 //   - backward: each thread owns 4 features x one float4 of k, reads one float4 of T and one
 //     float4 of S per j (16 FMAs per two 128-bit shared loads) and writes dT as float4.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dlrmb {
@@ -60,7 +64,7 @@ static inline int interaction_width(int F, int d, int pad_to_mul) {
 template <int TB>
 __global__ void __launch_bounds__(256)
 interaction_fwd_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int F, int d,
-                       int width, float* __restrict__ out, int NS, int nblk) {
+                       int width, float* __restrict__ out, int NS, int nblk, int ks_log2) {
     extern __shared__ float4 smem4[];
     const int d4 = d >> 2;
     const int ldt4 = d4 + 1;              // row stride in float4 (4 floats of padding)
@@ -121,45 +125,64 @@ interaction_fwd_kernel(float* __restrict__ T, const float* __restrict__ x, int B
         Os[(size_t)s * width + d + npair + c] = 0.f;
     }
 
-    // Gram blocks
-    for (int task = tid; task < ns * nt; task += blockDim.x) {
-        const int s = task / nt;
-        const int q = task - s * nt;
+    // Gram blocks.  A task is (sample, block pair, k-slice): KS = 2^ks_log2 adjacent lanes can split
+    // the k range of one TB x TB block and combine their partial dot products with warp shuffles
+    // (KS = 1 by default).
+    const int KS = 1 << ks_log2;
+    const int tps = nt * KS;              // tasks per sample
+    const int kper = d4 >> ks_log2;       // float4 k-steps per task
+    const int total_tasks = ns * tps;
+    for (int base_task = 0; base_task < total_tasks; base_task += blockDim.x) {
+        const int task = base_task + tid;
+        const bool live = task < total_tasks;
+        const int s = live ? task / tps : 0;
+        const int rem = live ? task - s * tps : 0;
+        const int q = rem >> ks_log2;
+        const int ks = rem & (KS - 1);
         const int bi = pr[2 * q], bj = pr[2 * q + 1];
-        const float4* A = Ts + ((size_t)s * Fp + bi * TB) * ldt4;
-        const float4* Bm = Ts + ((size_t)s * Fp + bj * TB) * ldt4;
+        const float4* A = Ts + ((size_t)s * Fp + bi * TB) * ldt4 + ks * kper;
+        const float4* Bm = Ts + ((size_t)s * Fp + bj * TB) * ldt4 + ks * kper;
         float acc[TB][TB];
 #pragma unroll
         for (int r = 0; r < TB; ++r)
 #pragma unroll
             for (int c = 0; c < TB; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < d4; ++k) {
-            float4 a[TB], b[TB];
+        if (live) {
+            for (int k = 0; k < kper; ++k) {
+                float4 a[TB];
 #pragma unroll
-            for (int r = 0; r < TB; ++r) a[r] = A[r * ldt4 + k];
+                for (int r = 0; r < TB; ++r) a[r] = A[r * ldt4 + k];
 #pragma unroll
-            for (int c = 0; c < TB; ++c) b[c] = Bm[c * ldt4 + k];
+                for (int c = 0; c < TB; ++c) {
+                    const float4 b = Bm[c * ldt4 + k];
+#pragma unroll
+                    for (int r = 0; r < TB; ++r) {
+                        float v = acc[r][c];
+                        v = fmaf(a[r].x, b.x, v);
+                        v = fmaf(a[r].y, b.y, v);
+                        v = fmaf(a[r].z, b.z, v);
+                        v = fmaf(a[r].w, b.w, v);
+                        acc[r][c] = v;
+                    }
+                }
+            }
+        }
+        for (int o = 1; o < KS; o <<= 1) {   // uniform across the warp
+#pragma unroll
+            for (int r = 0; r < TB; ++r)
+#pragma unroll
+                for (int c = 0; c < TB; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
+        }
+        if (live && ks == 0) {
+            float* o = Os + (size_t)s * width + d;
 #pragma unroll
             for (int r = 0; r < TB; ++r)
 #pragma unroll
                 for (int c = 0; c < TB; ++c) {
-                    float v = acc[r][c];
-                    v = fmaf(a[r].x, b[c].x, v);
-                    v = fmaf(a[r].y, b[c].y, v);
-                    v = fmaf(a[r].z, b[c].z, v);
-                    v = fmaf(a[r].w, b[c].w, v);
-                    acc[r][c] = v;
+                    int j = bi * TB + r, i = bj * TB + c;
+                    if (i < j && j < F) o[j * (j - 1) / 2 + i] = acc[r][c];
                 }
         }
-        float* o = Os + (size_t)s * width + d;
-#pragma unroll
-        for (int r = 0; r < TB; ++r)
-#pragma unroll
-            for (int c = 0; c < TB; ++c) {
-                int j = bi * TB + r, i = bj * TB + c;
-                if (i < j && j < F) o[j * (j - 1) / 2 + i] = acc[r][c];
-            }
     }
     __syncthreads();
 
@@ -259,15 +282,22 @@ static int launch_fwd_tb(float* T, const float* x, int B, int F, int d, int widt
     const int nblk = (F + TB - 1) / TB;
     const int nt = nblk * (nblk + 1) / 2;
     const int Fp = nblk * TB;
-    size_t per_sample = ((size_t)Fp * (d / 4 + 1) * 4 + width) * sizeof(float);
+    const int d4 = d / 4;
+    // k-split (KS = 2^ks_log2 lanes per block): off by default, see launch_interaction_fwd
+    int ks_log2 = 0;
+    if (const char* e = getenv("DLRMB_FWD_KS")) {   // tuning aid
+        int v = atoi(e);
+        if (v >= 0 && v <= 3 && d4 % (1 << v) == 0) ks_log2 = v;
+    }
+    size_t per_sample = ((size_t)Fp * (d4 + 1) * 4 + width) * sizeof(float);
     size_t fixed = (size_t)nt * 2 + 16;
-    TilePlan p = plan_tiles(B, nt, per_sample, fixed, sm_count);
+    TilePlan p = plan_tiles(B, nt << ks_log2, per_sample, fixed, sm_count);
     DLRMB_REQUIRE(p.smem <= 200 * 1024, "interaction tile needs %zu bytes of shared memory", p.smem);
     static unsigned long long attr_done = 0;
     int rc = ensure_smem_attr((const void*)interaction_fwd_kernel<TB>, 200 * 1024, &attr_done);
     if (rc) return rc;
     int grid = (B + p.ns - 1) / p.ns;
-    interaction_fwd_kernel<TB><<<grid, p.threads, p.smem, s>>>(T, x, B, F, d, width, out, p.ns, nblk);
+    interaction_fwd_kernel<TB><<<grid, p.threads, p.smem, s>>>(T, x, B, F, d, width, out, p.ns, nblk, ks_log2);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }
@@ -291,17 +321,18 @@ int launch_interaction_fwd(float* T, const float* x, int B, int F, int d, int pa
         }
         return DLRMB_OK;
     }
-    // register-block edge: the one that wastes the fewest FMAs on padding / diagonal blocks
-    auto cost = [&](int tb) {
-        int nb = (F + tb - 1) / tb;
-        return (double)(nb * (nb + 1) / 2) * tb * (tb + 1.5);
-    };
-    int tb = 2;
-    if (cost(3) < cost(tb)) tb = 3;
-    if (cost(4) < cost(tb)) tb = 4;
-    if (tb == 2) return launch_fwd_tb<2>(T, x, B, F, d, width, out, sm_count, s);
+    // Register-block edge TB and k-split KS.  Measured on B200 (benchmarks/tune_interaction_fwd.py,
+    // F = 27, B = 2048): TB = 3 with no k-split is the fastest plan at d = 64 and d = 128 (18.2 us vs
+    // 21.4 us for TB = 6 and 20.3-29.8 us for TB = 9; every k-split variant loses to its shuffle
+    // reduction), so it is the default; the larger blocks stay selectable for tuning.
+    int tb = 3;
+    if (const char* e = getenv("DLRMB_FWD_TB")) {   // tuning aid
+        int v = atoi(e);
+        if (v == 3 || v == 6 || v == 9) tb = v;
+    }
     if (tb == 3) return launch_fwd_tb<3>(T, x, B, F, d, width, out, sm_count, s);
-    return launch_fwd_tb<4>(T, x, B, F, d, width, out, sm_count, s);
+    if (tb == 6) return launch_fwd_tb<6>(T, x, B, F, d, width, out, sm_count, s);
+    return launch_fwd_tb<9>(T, x, B, F, d, width, out, sm_count, s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -500,3 +500,19 @@ def test_kaggle_shaped_properties():
     for k, s in snap.items():
         assert torch.allclose(t.table(k), s, rtol=0, atol=1e-5), k
     t.close()
+
+
+@pytest.mark.parametrize("name", ["single", "multi"])
+def test_validate_entry_point_and_table_checkpoint(name, tmp_path):
+    """dlrm_jl_b200.validation.validate == the reference's DLRM.validate(path, strategy)
+    (test/integration.jl:39), fed from the committed golden; plus the table export round trip."""
+    import os
+    from dlrm_jl_b200.validation import load_hdf5, load_tables, save_tables, validate
+    path = os.path.join(os.path.dirname(__file__), "golden", f"pytorch_reference_{name}.npz")
+    assert validate(path) is True
+    model = load_hdf5(path)
+    ck = str(tmp_path / "tables.npz")
+    save_tables(model.embeddings, ck)
+    again = load_tables(ck, 16)
+    for k in range(7):
+        assert np.array_equal(again.download(k), model.embeddings.download(k))

@@ -274,24 +274,40 @@ def run_ours(args):
         if args.exchange == "p2p":
             ok, why = 1.0, ""
             try:
-                # reference result through the NCCL path, then the fused path on the same indices
+                # reference results through the NCCL path, then the fused paths on the same inputs
                 chk = torch.from_numpy(synth_batch(wl, 999, rank)[2]).to(dev)
-                with torch.no_grad():
-                    t_nccl = se.lookup(chk, torch.zeros(1, device=dev)).clone()
+                gen_c = torch.Generator(device="cpu").manual_seed(7 + rank)
+                xc = torch.randn((B, D), generator=gen_c).to(dev).requires_grad_(True)
+                gz = torch.randn((B, D + F * (F - 1) // 2), generator=gen_c).to(dev)
+                probe = DotInteraction()
+                a0 = torch.zeros(1, device=dev, requires_grad=True)
+                t_nccl = se.lookup(chk, a0)
+                probe(xc, t_nccl).backward(gz)
+                t_ref, g_ref, dx_ref = t_nccl.detach().clone(), se.owned_grad.clone(), xc.grad.clone()
+                xc.grad = None
                 se.enable_peer_exchange(B)
-                with torch.no_grad():
-                    t_p2p = se.lookup(chk, torch.zeros(1, device=dev))
-                if not torch.equal(t_nccl[:, 1:], t_p2p[:, 1:]):
-                    ok, why = 0.0, "fused exchange result differs from the NCCL path"
+                se.enable_fused_backward(B)
+                t_p2p = se.lookup_fused(chk)
+                if not torch.equal(t_ref[:, 1:], t_p2p[:, 1:]):
+                    ok, why = 0.0, "fused forward exchange differs from the NCCL path"
+                probe(xc, t_p2p, scatter=se.scatter_plan).backward(gz)
+                se.finish_backward()
+                t_mine = len(se.local_ids)
+                if t_mine and not torch.equal(g_ref, se.owned_grad[:, :t_mine]):
+                    ok, why = 0.0, "fused backward exchange differs from the NCCL path"
+                if not torch.equal(dx_ref, xc.grad):
+                    ok, why = 0.0, "dx differs between the fused and the NCCL path"
             except Exception as exc:  # noqa: BLE001
                 ok, why = 0.0, f"{type(exc).__name__}: {exc}"
             flag = torch.tensor([ok], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank takes the same decision
             if float(flag.item()) == 1.0:
-                exchange = "fused lookup + NVLink peer stores (forward), nccl all-to-all (backward)"
-                exchange_check = "fused peer-store lookup == NCCL all-to-all path, bit for bit, on every rank"
+                exchange = ("fused over NVLink peer stores: lookup -> peers' interaction inputs (forward), "
+                            "interaction backward -> owners' gradient buffers (backward)")
+                exchange_check = "pooled rows, owner-side gradients and dx == NCCL all-to-all path, bit for bit, on every rank"
             else:
                 se.peer = None
+                se.scatter_plan = None
                 exchange_check = f"fell back to NCCL ({why or 'another rank failed'})"
                 if rank == 0:
                     print(f"[bench] peer exchange disabled: {exchange_check}", file=sys.stderr)
@@ -311,13 +327,16 @@ def run_ours(args):
         mlp_stream.wait_stream(main)
         with torch.cuda.stream(mlp_stream):
             x = bottom(dense)
-        T = se.lookup(idx, anchor)
+        fused = se.scatter_plan is not None
+        T = se.lookup_fused(idx) if fused else se.lookup(idx, anchor)
         se.sort_async()
         main.wait_stream(mlp_stream)
-        z = dot(x, T)
+        z = dot(x, T, scatter=se.scatter_plan) if fused else dot(x, T)
         loss = sigmoid_bce(top_logits(z), labels)
         loss.backward()
         main.wait_stream(mlp_stream)
+        if fused:
+            se.finish_backward()
         flat.allreduce()
         with torch.no_grad():
             torch._foreach_add_(params, flat.views, alpha=-LR * flat.scale)

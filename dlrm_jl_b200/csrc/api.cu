@@ -292,6 +292,19 @@ int32_t dlrmb_interaction_bwd(int32_t device, const float* dOut, const float* T,
     return launch_interaction_bwd(dOut, T, B, F, d, pad_to_mul, dT, dx, device_sm_count(device), (cudaStream_t)stream);
 }
 
+int32_t dlrmb_interaction_bwd_scatter(int32_t device, const float* dOut, const float* T, int32_t B,
+                                      int32_t F, int32_t d, int32_t pad_to_mul,
+                                      const dlrmb_slot_dest* dests, int64_t sample_offset, float* dx,
+                                      dlrmb_stream stream) {
+    int rc = check_interaction_args(B, F, d, pad_to_mul);
+    if (rc) return rc;
+    DLRMB_REQUIRE(dOut && T && dests && dx, "null buffer");
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    return launch_interaction_bwd_ex(dOut, T, B, F, d, pad_to_mul, const_cast<float*>(T) /* unused */, dx, dests,
+                                     (long long)sample_offset, device_sm_count(device), (cudaStream_t)stream);
+}
+
 int32_t dlrmb_embedding_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
                              int32_t B, int32_t P, dlrmb_stream stream) {
     GUARD(t);

@@ -338,9 +338,21 @@ int launch_interaction_fwd(float* T, const float* x, int B, int F, int d, int pa
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
+// SCATTER: instead of dT[b][f][:], the gradient row of feature slot f >= 1 is stored at
+// dests[f].base + (sample_offset + b) * dests[f].sample_stride + dests[f].offset -- the gradient
+// buffer of the rank that owns that table, mapped over NVLink (table-wise sharded embeddings: the
+// interaction backward and the gradient all-to-all in one kernel).  Slot 0 (x) only feeds dx.
+struct SlotDest {
+    float* base;
+    long long sample_stride;   // floats between consecutive samples in the destination
+    long long offset;          // floats: position of this table inside a destination sample
+};
+
+template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 interaction_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int F,
-                       int d, int width, float* __restrict__ dT, float* __restrict__ dx, int NS) {
+                       int d, int width, float* __restrict__ dT, float* __restrict__ dx, int NS,
+                       const SlotDest* __restrict__ dests, long long sample_offset) {
     extern __shared__ float4 smem4[];
     const int d4 = d >> 2;
     const int ldt4 = d4 + 1;
@@ -410,11 +422,24 @@ interaction_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__
             a3.x = fmaf(sv.w, t.x, a3.x); a3.y = fmaf(sv.w, t.y, a3.y); a3.z = fmaf(sv.w, t.z, a3.z); a3.w = fmaf(sv.w, t.w, a3.w);
         }
         const int f0 = fb * 4;
-        float4* o = reinterpret_cast<float4*>(dT + ((size_t)(s0 + s) * F + f0) * d) + k;
-        o[0] = a0;
-        if (f0 + 1 < F) o[d4] = a1;
-        if (f0 + 2 < F) o[2 * d4] = a2;
-        if (f0 + 3 < F) o[3 * d4] = a3;
+        if (SCATTER) {
+            const float4 av[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int f = f0 + q;
+                if (f >= 1 && f < F) {
+                    const SlotDest dd = dests[f];
+                    float* row = dd.base + (sample_offset + s0 + s) * dd.sample_stride + dd.offset;
+                    reinterpret_cast<float4*>(row)[k] = av[q];
+                }
+            }
+        } else {
+            float4* o = reinterpret_cast<float4*>(dT + ((size_t)(s0 + s) * F + f0) * d) + k;
+            o[0] = a0;
+            if (f0 + 1 < F) o[d4] = a1;
+            if (f0 + 2 < F) o[2 * d4] = a2;
+            if (f0 + 3 < F) o[3 * d4] = a3;
+        }
         if (fb == 0) {
             const float* g = Gs + (size_t)s * width + 4 * k;
             float4 r = make_float4(__fadd_rn(g[0], a0.x), __fadd_rn(g[1], a0.y), __fadd_rn(g[2], a0.z), __fadd_rn(g[3], a0.w));
@@ -446,12 +471,26 @@ interaction_bwd_generic_kernel(const float* __restrict__ dOut, const float* __re
     }
 }
 
+int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
+                              float* dT, float* dx, const void* dests, long long sample_offset,
+                              int sm_count, cudaStream_t s);
+
 int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
                            float* dT, float* dx, int sm_count, cudaStream_t s) {
+    return launch_interaction_bwd_ex(dOut, T, B, F, d, pad_to_mul, dT, dx, nullptr, 0, sm_count, s);
+}
+
+int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
+                              float* dT, float* dx, const void* dests, long long sample_offset,
+                              int sm_count, cudaStream_t s) {
     const int width = interaction_width(F, d, pad_to_mul);
     const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(T) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(dT) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+    if (dests != nullptr && !aligned) {
+        set_error("the scattered interaction backward needs d % 4 == 0 and 16-byte aligned buffers");
+        return DLRMB_EINVAL;
+    }
     if (!aligned) {
         int64_t blocks = ceil_div64((int64_t)B * F * d, 256);
         if (blocks > sm_count * 16) blocks = sm_count * 16;
@@ -465,10 +504,16 @@ int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int 
     TilePlan p = plan_tiles(B, (Fp / 4) * d4, per_sample, (size_t)F * (F - 1) + 16, sm_count);
     DLRMB_REQUIRE(p.smem <= 200 * 1024, "interaction tile needs %zu bytes of shared memory", p.smem);
     static unsigned long long attr_done = 0;
-    int rc = ensure_smem_attr((const void*)interaction_bwd_kernel, 200 * 1024, &attr_done);
+    static unsigned long long attr_done2 = 0;
+    int rc = dests ? ensure_smem_attr((const void*)interaction_bwd_kernel<true>, 200 * 1024, &attr_done2)
+                   : ensure_smem_attr((const void*)interaction_bwd_kernel<false>, 200 * 1024, &attr_done);
     if (rc) return rc;
     int grid = (B + p.ns - 1) / p.ns;
-    interaction_bwd_kernel<<<grid, p.threads, p.smem, s>>>(dOut, T, B, F, d, width, dT, dx, p.ns);
+    if (dests)
+        interaction_bwd_kernel<true><<<grid, p.threads, p.smem, s>>>(dOut, T, B, F, d, width, dT, dx, p.ns,
+                                                                      static_cast<const SlotDest*>(dests), sample_offset);
+    else
+        interaction_bwd_kernel<false><<<grid, p.threads, p.smem, s>>>(dOut, T, B, F, d, width, dT, dx, p.ns, nullptr, 0);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }

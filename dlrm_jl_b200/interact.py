@@ -75,6 +75,52 @@ class _DotInteractionFn(torch.autograd.Function):
         return (dx if ctx.has_x else None), dT, None
 
 
+class ScatterPlan:
+    """Where the interaction backward stores the gradient row of every feature slot when the
+    embedding tables are sharded: `dests` is a device int64 tensor [F][3] laid out as the C struct
+    dlrmb_slot_dest {base pointer, floats per destination sample, float offset of the table}."""
+
+    def __init__(self, dests: torch.Tensor, sample_offset: int):
+        assert dests.dtype == torch.int64 and dests.dim() == 2 and dests.shape[1] == 3 and dests.is_contiguous()
+        self.dests = dests
+        self.sample_offset = int(sample_offset)
+
+
+class _DotInteractionScatterFn(torch.autograd.Function):
+    """Forward as _DotInteractionFn; backward = interaction pullback fused with the gradient
+    exchange (dlrmb_interaction_bwd_scatter): dT rows go straight to the table owners' buffers, only
+    dx comes back through autograd.  T must not require grad."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, T: torch.Tensor, pad_to_mul: int, plan: ScatterPlan):
+        _require_cuda(x, T)
+        B, F, d = T.shape
+        assert T.is_contiguous() and T.dtype == torch.float32 and plan.dests.shape[0] == F
+        xc = x.contiguous()
+        out = torch.empty((B, interaction_width(F, d, pad_to_mul)), dtype=torch.float32, device=T.device)
+        lib = _lib.load()
+        with _prof.range("interaction_fwd"):
+            _lib.check(lib.dlrmb_interaction_fwd(
+                T.device.index or 0, T.data_ptr(), xc.data_ptr(), B, F, d, pad_to_mul, out.data_ptr(), _stream(T)))
+        ctx.T = T
+        ctx.pad_to_mul = pad_to_mul
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut: torch.Tensor):
+        T, plan = ctx.T, ctx.plan
+        B, F, d = T.shape
+        dOut = dOut.contiguous()
+        dx = torch.empty((B, d), dtype=torch.float32, device=T.device)
+        lib = _lib.load()
+        with _prof.range("interaction_bwd"):
+            _lib.check(lib.dlrmb_interaction_bwd_scatter(
+                T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
+                plan.dests.data_ptr(), plan.sample_offset, dx.data_ptr(), _stream(T)))
+        return dx, None, None, None
+
+
 class DotInteraction:
     """``DotInteraction`` (src/model/interact.jl:369-411).
 
@@ -85,7 +131,9 @@ class DotInteraction:
     def __init__(self, pad_to_mul: int = POST_INTERACTION_PAD_TO_MUL):
         self.pad_to_mul = pad_to_mul
 
-    def __call__(self, x: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, T: torch.Tensor, scatter: "ScatterPlan" = None) -> torch.Tensor:
+        if scatter is not None:
+            return _DotInteractionScatterFn.apply(x, T, self.pad_to_mul, scatter)
         return _DotInteractionFn.apply(x, T, self.pad_to_mul)
 
 

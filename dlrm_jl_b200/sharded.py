@@ -172,6 +172,49 @@ class PeerExchange:
         self.T = torch.as_tensor(_DevicePtrView(p.value, self.shape, self), device=self.device)
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._barrier = barrier
+        self.G = None
+        self.peer_G_ptrs = None
+        self._gbuf = None
+
+    def _share(self, nbytes: int):
+        """Allocate an exchange buffer and map every rank's copy: returns (own ptr, [ptr per rank])."""
+        import ctypes as C
+
+        from . import _lib
+        h = C.c_void_p()
+        _lib.check(self.lib.dlrmb_xbuf_create(self.device.index or 0, max(256, nbytes), C.byref(h)))
+        p = C.c_void_p()
+        _lib.check(self.lib.dlrmb_xbuf_ptr(h, C.byref(p)))
+        handle = (C.c_uint8 * 64)()
+        _lib.check(self.lib.dlrmb_xbuf_ipc_handle(h, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(p.value)
+                continue
+            q = C.c_void_p()
+            _lib.check(self.lib.dlrmb_xbuf_open(self.device.index or 0, (C.c_uint8 * 64).from_buffer_copy(handles[r]), C.byref(q)))
+            ptrs.append(q.value)
+        return h, p.value, ptrs
+
+    def enable_gradient_exchange(self, sharding: "TableSharding", B_local: int, D: int):
+        """Gradient buffer G [B_global][tables of this rank][D] on every rank, mapped everywhere, and
+        the per-slot destination table the scattered interaction backward reads."""
+        from .embedding import _DevicePtrView
+        from .interact import ScatterPlan
+        counts = sharding.counts()
+        t_mine = counts[self.rank]
+        Bg = B_local * self.world
+        self._gbuf, own, self.peer_G_ptrs = self._share(Bg * max(1, t_mine) * D * 4)
+        self.G = torch.as_tensor(_DevicePtrView(own, (Bg, max(1, t_mine), D), self), device=self.device)
+        rows = [[0, 0, 0]]                                    # slot 0 (x) has no destination
+        for k in range(len(sharding.rows)):
+            o = sharding.owner[k]
+            rows.append([self.peer_G_ptrs[o], counts[o] * D, sharding.local[o].index(k) * D])
+        dests = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        return ScatterPlan(dests, self.rank * B_local)
 
     def barrier(self) -> None:
         if self._barrier is not None:
@@ -249,6 +292,30 @@ class ShardedEmbedding:
         self.owned_grad: Optional[torch.Tensor] = None
         self.slot0 = 1 if world == 1 else 0
         self.peer: Optional[PeerExchange] = None
+        self.scatter_plan = None
+
+    def enable_fused_backward(self, B_local: int) -> None:
+        """Also fuse the backward exchange: the interaction backward stores dT rows into the owners'
+        gradient buffers (pass `self.scatter_plan` to DotInteraction), `finish_backward()` orders the
+        stores before the sparse update.  Needs enable_peer_exchange first."""
+        assert self.peer is not None
+        self.scatter_plan = self.peer.enable_gradient_exchange(self.sharding, B_local, self.D)
+
+    def lookup_fused(self, idx_local: torch.Tensor) -> torch.Tensor:
+        """Forward of the fully fused path: no autograd node (the gradient never comes back through
+        T; it is scattered to the owners by the interaction backward)."""
+        with torch.no_grad():
+            idx_owned = exchange_indices(idx_local, self.sharding, self.rank, self.group)
+            self.idx_owned = idx_owned
+            if len(self.local_ids):
+                self.tables.lookup_p2p(idx_owned, self.peer.peer_ptrs, idx_local.shape[1], 1 + self.ntab)
+            self.peer.barrier()
+            return self.peer.T.detach()
+
+    def finish_backward(self) -> None:
+        """After loss.backward() on the fused path: every rank's gradient rows have landed."""
+        self.peer.barrier()
+        self.owned_grad = self.peer.G
 
     def enable_peer_exchange(self, B_local: int, barrier: Optional[Callable] = None) -> None:
         """Switch the forward exchange to the fused lookup + NVLink peer-store kernel.  Safe with

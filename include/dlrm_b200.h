@@ -149,6 +149,22 @@ int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_by
                                 int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
                                 int32_t B_local, int32_t slots, dlrmb_stream stream);
 
+/* Interaction backward fused with the gradient exchange: as dlrmb_interaction_bwd, but the gradient
+ * row of feature slot f >= 1 of local sample b is stored at
+ *   dests[f].base + (sample_offset + b) * dests[f].sample_stride + dests[f].offset   (floats)
+ * i.e. straight into the gradient buffer [B_global][tables of that rank][D] of the rank that owns
+ * table f-1 (a dlrmb_xbuf mapped over NVLink); slot 0 only contributes to dx.  `dests` is a DEVICE
+ * array of F entries (entry 0 unused). */
+typedef struct dlrmb_slot_dest {
+    float* base;
+    int64_t sample_stride;
+    int64_t offset;
+} dlrmb_slot_dest;
+int32_t dlrmb_interaction_bwd_scatter(int32_t device, const float* dOut, const float* T, int32_t B,
+                                      int32_t F, int32_t d, int32_t pad_to_mul,
+                                      const dlrmb_slot_dest* dests, int64_t sample_offset, float* dx,
+                                      dlrmb_stream stream);
+
 /* ---- host-buffer entry points: every pointer is host memory (pageable or pinned); this is
  * the form a CPU-resident DLRM.jl model calls.  Copies run inside the call. -------------- */
 int32_t dlrmb_embedding_fwd_host(dlrmb_tables* t, const void* idx, int32_t idx_bytes,

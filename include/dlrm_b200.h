@@ -129,6 +129,14 @@ int32_t dlrmb_bce_sigmoid_fwd_bwd(int32_t device, const float* logits, const flo
                                   float* prob, float* dlogits, float* loss, float* scratch,
                                   dlrmb_stream stream);
 
+/* ---- batch marshalling: `load!(labels, dense, sparse, records)` (src/data/criteo.jl:284-310) on
+ * the device.  `records` is a DEVICE copy of B packed DACRecord structs (160 bytes each: Int32
+ * label, 13 Float32, 26 UInt32; src/data/criteo.jl:91-95).  Outputs: labels [B] as Float32,
+ * dense [B][13], sparse [26][B] (table-major, the layout dlrmb_embedding_fwd takes).
+ *  ------------------------------------------------------------- */
+int32_t dlrmb_dac_unpack(int32_t device, const void* records, int32_t B, float* labels, float* dense,
+                         uint32_t* sparse, dlrmb_stream stream);
+
 /* ---- multi-GPU, table-wise sharded embeddings (new functionality: DLRM.jl is single-process).
  * Exchange buffers are library-owned device allocations that other ranks (one process per GPU)
  * map through CUDA IPC; dlrmb_embedding_fwd_p2p pools this rank's tables for the GLOBAL batch

@@ -341,3 +341,16 @@ def rel_err(a: np.ndarray, b: np.ndarray) -> float:
     b = np.asarray(b, dtype=np.float64).ravel()
     nb = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a - b))
+
+
+# --------------------------------------------------------------------------------------
+# Batch marshalling
+# --------------------------------------------------------------------------------------
+def dac_unpack(records: np.ndarray):
+    """`load!(labels, dense, sparse, records)`, src/data/criteo.jl:284-310: per record copy the
+    label, the 13 continuous values into dense[13 x B] (C [B][13]) and the 26 categorical values
+    into sparse[B x 26] (C [26][B])."""
+    labels = records["label"].astype(F32)
+    dense = np.ascontiguousarray(records["continuous"], dtype=F32)
+    sparse = np.ascontiguousarray(records["categorical"].T)
+    return labels, dense, sparse

@@ -516,3 +516,24 @@ def test_validate_entry_point_and_table_checkpoint(name, tmp_path):
     again = load_tables(ck, 16)
     for k in range(7):
         assert np.array_equal(again.download(k), model.embeddings.download(k))
+
+
+def test_dac_loader_device_unpack_bit_exact():
+    """DACLoader + dlrmb_dac_unpack vs the reference's load! (src/data/criteo.jl:284-310)."""
+    from dlrm_jl_b200.loader import DAC_DTYPE, DACLoader
+    rng = np.random.default_rng(77)
+    n, B = 1000, 192                               # 5 whole batches, the ragged tail is dropped
+    data = np.zeros(n, dtype=DAC_DTYPE)
+    data["label"] = rng.integers(0, 2, size=n)
+    data["continuous"] = rng.standard_normal((n, 13)).astype(np.float32)
+    data["categorical"] = rng.integers(0, 2**32 - 1, size=(n, 26), dtype=np.uint64).astype(np.uint32)
+    loader = DACLoader(data, B, 0)
+    assert len(loader) == n // B
+    seen = 0
+    for i, (labels, dense, sparse) in enumerate(loader):
+        l_ref, d_ref, s_ref = O.dac_unpack(data[i * B:(i + 1) * B])
+        assert np.array_equal(labels.cpu().numpy(), l_ref)
+        assert np.array_equal(dense.cpu().numpy(), d_ref)
+        assert np.array_equal(sparse.cpu().numpy().view(np.uint32)[:, :, 0], s_ref)
+        seen += 1
+    assert seen == n // B

@@ -142,7 +142,7 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
         TRY_CUDA(cudaMalloc((void**)&t->keys[i], sizeof(uint32_t) * nl));
         TRY_CUDA(cudaMalloc((void**)&t->pos[i], sizeof(uint32_t) * nl));
     }
-    t->radix_tiles_cap = ceil_div64(max_lookups, 1024);
+    t->radix_tiles_cap = ceil_div64(max_lookups, 4096);
     TRY_CUDA(cudaMalloc((void**)&t->tile_hist,
                         sizeof(uint32_t) * (size_t)ntab * 512 * (size_t)t->radix_tiles_cap));
     TRY_CUDA(cudaMalloc((void**)&t->digit_total, sizeof(uint32_t) * (size_t)ntab * 512));

@@ -10,10 +10,11 @@
 //   * L <= kSmemSortMax: one CTA per table runs the whole LSD radix sort in shared memory
 //     (8-bit digits, as many passes as that table's row count needs); a single launch covers
 //     all tables.
-//   * larger L: least-significant-digit radix sort, digits of up to 9 bits, tiles of 1024 keys, all tables
+//   * larger L: least-significant-digit radix sort, digits of up to 9 bits, tiles of 4096 keys, all tables
 //     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
 //     (digit, tile), one CTA per digit -> stable scatter whose in-tile ranks come from warp match_any + per-warp
-//     digit counters in shared memory.  The sort arrays of a whole batch fit L2 (126 MB), so the
+//     digit counters in shared memory and whose keys are reordered in shared memory first, so each
+//     digit's keys leave the CTA as one contiguous run.  The sort arrays of a whole batch fit L2 (126 MB), so the
 //     passes run at L2 rather than HBM speed.
 // Output: keys[sorted_buf] (ascending 0-based row ids) and pos[sorted_buf] (the stable
 // permutation), both [ntab][max_lookups].
@@ -148,7 +149,7 @@ static int launch_sort_small(dlrmb_tables* t, const IdxT* idx, int idx_base, int
 // large path: LSD radix sort over global memory, all tables batched through grid.y
 // ---------------------------------------------------------------------------------------------
 constexpr int RT = 256;        // threads per CTA
-constexpr int RI = 4;          // keys per thread (small tiles: many CTAs, the passes are latency-bound)
+constexpr int RI = 16;         // keys per thread
 constexpr int RTILE = RT * RI; // keys per tile
 
 // exclusive prefix of `v` over the 256 threads of the CTA (thread order); wsum is 8 words of smem
@@ -230,23 +231,32 @@ radix_scan_kernel(uint32_t* __restrict__ tile_hist, uint32_t* __restrict__ digit
     if (threadIdx.x == 0) digit_total[k * NB + d] = running;
 }
 
+// Scatter with a shared-memory reorder: the tile's keys are first placed in digit order in shared
+// memory, then written out in that order, so the keys of one digit leave as one contiguous run
+// (coalesced) instead of one 4-byte store per key.
 template <typename IdxT, bool FIRST>
 __global__ void __launch_bounds__(RT)
 radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t* __restrict__ keys_in,
                      const uint32_t* __restrict__ pos_in, uint32_t* __restrict__ keys_out,
                      uint32_t* __restrict__ pos_out, int64_t cap, int L, int shift, uint32_t mask,
                      const uint32_t* __restrict__ tile_hist, const uint32_t* __restrict__ digit_total, int tiles) {
-    __shared__ uint32_t wh[RT / 32][NB];
+    __shared__ uint16_t wc[RT / 32][NB];      // per-warp digit counts, then exclusive prefix over warps
+    __shared__ uint32_t lstart[NB];           // first slot of each digit inside the sorted tile
+    __shared__ uint32_t gdst[NB];             // global position of slot 0 of each digit, minus lstart
+    __shared__ uint32_t skeys[RTILE];
+    __shared__ uint32_t svals[RTILE];
     __shared__ uint32_t wsum[8];
     const int k = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int w = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < (RT / 32) * NB; i += RT) (&wh[0][0])[i] = 0;
+    for (int i = tid; i < (RT / 32) * NB; i += RT) (&wc[0][0])[i] = 0;
     __syncthreads();
 
     const IdxT* ik = idx + (size_t)k * L;
     const uint32_t* kin = keys_in + (size_t)k * cap;
     const uint32_t* pin = pos_in + (size_t)k * cap;
-    const int base = tile * RTILE + w * (32 * RI);
+    const int tile_base = tile * RTILE;
+    const int base = tile_base + w * (32 * RI);
+    const int n_valid = min(RTILE, L - tile_base);
     uint32_t key[RI], val[RI], rank[RI];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -262,49 +272,64 @@ radix_scatter_kernel(const IdxT* __restrict__ idx, int idx_base, const uint32_t*
         const uint32_t dig = valid ? ((key[i] >> shift) & mask) : (NB + lane);
         const uint32_t peers = __match_any_sync(0xffffffffu, dig);
         const uint32_t lt = peers & lt_mask;
-        const uint32_t b = valid ? wh[w][dig] : 0u;
+        const uint32_t b = valid ? wc[w][dig] : 0u;
         __syncwarp();
-        if (valid && lt == 0) wh[w][dig] = b + __popc(peers);
+        if (valid && lt == 0) wc[w][dig] = (uint16_t)(b + __popc(peers));
         __syncwarp();
         rank[i] = b + __popc(lt);
     }
     __syncthreads();
     {
-        // thread t owns digits 2t and 2t+1: bucket start (scan of the digit totals) + this tile's
-        // offset inside the bucket, then the per-warp starts
+        // thread t owns digits 2t and 2t+1
         const uint32_t d0 = 2 * tid, d1 = 2 * tid + 1;
-        const uint32_t t0 = d0 <= mask ? digit_total[k * NB + d0] : 0u;
-        const uint32_t t1 = d1 <= mask ? digit_total[k * NB + d1] : 0u;
-        const uint32_t ex = block_excl_scan_256(t0 + t1, wsum, nullptr);
+        uint32_t c0 = 0, c1 = 0;
         if (d0 <= mask) {
-            uint32_t run = ex + tile_hist[((size_t)k * NB + d0) * tiles + tile];
 #pragma unroll
             for (int ww = 0; ww < RT / 32; ++ww) {
-                const uint32_t c = wh[ww][d0];
-                wh[ww][d0] = run;
-                run += c;
+                const uint32_t c = wc[ww][d0];
+                wc[ww][d0] = (uint16_t)c0;
+                c0 += c;
             }
         }
         if (d1 <= mask) {
-            uint32_t run = ex + t0 + tile_hist[((size_t)k * NB + d1) * tiles + tile];
 #pragma unroll
             for (int ww = 0; ww < RT / 32; ++ww) {
-                const uint32_t c = wh[ww][d1];
-                wh[ww][d1] = run;
-                run += c;
+                const uint32_t c = wc[ww][d1];
+                wc[ww][d1] = (uint16_t)c1;
+                c1 += c;
             }
+        }
+        const uint32_t lex = block_excl_scan_256(c0 + c1, wsum, nullptr);       // slots inside the tile
+        const uint32_t t0 = d0 <= mask ? digit_total[k * NB + d0] : 0u;
+        const uint32_t t1 = d1 <= mask ? digit_total[k * NB + d1] : 0u;
+        const uint32_t gex = block_excl_scan_256(t0 + t1, wsum, nullptr);       // buckets in the stream
+        if (d0 <= mask) {
+            lstart[d0] = lex;
+            gdst[d0] = gex + tile_hist[((size_t)k * NB + d0) * tiles + tile] - lex;
+        }
+        if (d1 <= mask) {
+            lstart[d1] = lex + c0;
+            gdst[d1] = gex + t0 + tile_hist[((size_t)k * NB + d1) * tiles + tile] - (lex + c0);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        if ((base + i * 32 + lane) < L) {
+            const uint32_t dig = (key[i] >> shift) & mask;
+            const uint32_t slot = lstart[dig] + wc[w][dig] + rank[i];
+            skeys[slot] = key[i];
+            svals[slot] = val[i];
         }
     }
     __syncthreads();
     uint32_t* ko = keys_out + (size_t)k * cap;
     uint32_t* po = pos_out + (size_t)k * cap;
-#pragma unroll
-    for (int i = 0; i < RI; ++i) {
-        if ((base + i * 32 + lane) < L) {
-            const uint32_t dst = wh[w][(key[i] >> shift) & mask] + rank[i];
-            ko[dst] = key[i];
-            po[dst] = val[i];
-        }
+    for (int j = tid; j < n_valid; j += RT) {
+        const uint32_t kk = skeys[j];
+        const uint32_t dst = gdst[(kk >> shift) & mask] + (uint32_t)j;
+        ko[dst] = kk;
+        po[dst] = svals[j];
     }
 }
 

@@ -99,12 +99,13 @@ def time_graph(fn, nb: int, use_graph: bool, iters: int) -> float:
     return 1e3 * a.elapsed_time(b) / (iters * nb)
 
 
-def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label="", only=None):
+def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label="", only=None, dtype="f32"):
     dev = torch.device("cuda", 0)
     peak, peak_src = hbm_peak()
     ntab = len(rows)
     L = B * P
-    t = EmbeddingTables(rows, D, L, dev)
+    eb = 4 if dtype == "f32" else 2
+    t = EmbeddingTables(rows, D, L, dev, dtype=torch.float32 if dtype == "f32" else torch.bfloat16)
     t.init_uniform(1)
     rng = np.random.default_rng(1234)
     idx_np = [make_indices(rng, rows, B, P, alpha) for _ in range(nb)]
@@ -114,7 +115,7 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
     T = torch.empty((B, F, D), device=dev)
     dT = torch.randn((B, F, D), device=dev) * 0.01
     res = {"label": label, "tables": ntab, "rows_total": int(sum(rows)), "rows_max": int(max(rows)), "D": D, "B": B,
-           "P": P, "zipf": alpha, "lookups_per_launch": ntab * L, "distinct_rows_per_launch": uniq,
+           "P": P, "zipf": alpha, "table_dtype": dtype, "lookups_per_launch": ntab * L, "distinct_rows_per_launch": uniq,
            "hbm_peak_gbs": peak, "peak_source": peak_src}
 
     def rec(name, us, nbytes):
@@ -131,7 +132,7 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
         t.close()
         return res
     us = time_graph(lambda i: t.lookup(idx[i], T, 1), nb, use_graph, iters)
-    lookup_bytes = ntab * (L * D * 4 + B * D * 4 + L * 4)
+    lookup_bytes = ntab * (L * D * eb + B * D * 4 + L * 4)
     rec("lookup", us, lookup_bytes)
     us_sort = time_graph(lambda i: t.sort(idx[i]), nb, use_graph, iters)
     res["sort"] = {"us": us_sort}
@@ -140,7 +141,7 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
         t.sort(idx[i])
         t.update_sorted(dT, 1, 0.01)
     us_both = time_graph(upd, nb, use_graph, iters)
-    update_bytes = ntab * (B * D * 4 + L * 4) + 2 * uniq * D * 4
+    update_bytes = ntab * (B * D * 4 + L * 4) + 2 * uniq * D * eb
     rec("sort_plus_update", us_both, update_bytes)
     rec("update_only", max(us_both - us_sort, 1e-3), update_bytes)
     rec("embedding_lookup_plus_update", res["lookup"]["us"] + us_both, lookup_bytes + update_bytes)
@@ -173,6 +174,7 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--full", action="store_true", help="with --sweep: all of P in {1,4,16,64} and Zipf in {0,1.05,1.2}")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="table storage type")
     ap.add_argument("--only", default=None, help="time just this kernel (e.g. interaction_fwd)")
     ap.add_argument("--small-tables", action="store_true",
                     help="cap every table at 1000 rows (the interaction kernels do not depend on table size; keeps ncu replays cheap)")
@@ -201,7 +203,7 @@ def main():
             D = a.D
         if a.small_tables:
             rows = [min(r, 1000) for r in rows]
-        r = run_case(rows, D, a.B, a.P, a.zipf, a.nb, not a.no_graph, a.iters, label=a.workload or "custom", only=a.only)
+        r = run_case(rows, D, a.B, a.P, a.zipf, a.nb, not a.no_graph, a.iters, label=a.workload or "custom", only=a.only, dtype=a.dtype)
         results.append(r)
         print(json.dumps(r), flush=True)
     if a.out:

@@ -31,6 +31,8 @@ SIGNATURES = {
     "dlrmb_last_error": (C.c_char_p, []),
     "dlrmb_launch_count": (_i64, []),
     "dlrmb_tables_create": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, C.POINTER(_vp)]),
+    "dlrmb_tables_create_ex": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, _i32, C.POINTER(_vp)]),
+    "dlrmb_tables_elem_bytes": (_i32, [_vp]),
     "dlrmb_tables_destroy": (_i32, [_vp]),
     "dlrmb_tables_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
     "dlrmb_tables_upload": (_i32, [_vp, _i32, _vp]),

@@ -75,8 +75,14 @@ int64_t dlrmb_launch_count(void) { return g_launches.load(); }
 
 int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
                             int64_t max_lookups, dlrmb_tables** out) {
+    return dlrmb_tables_create_ex(device, ntab, rows, D, max_lookups, 4, out);
+}
+
+int32_t dlrmb_tables_create_ex(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
+                               int64_t max_lookups, int32_t elem_bytes, dlrmb_tables** out) {
     DLRMB_REQUIRE(out != nullptr, "out is null");
     *out = nullptr;
+    DLRMB_REQUIRE(elem_bytes == 4 || elem_bytes == 2, "elem_bytes must be 4 (f32) or 2 (bf16), got %d", elem_bytes);
     DLRMB_REQUIRE(ntab > 0 && ntab <= 65535, "ntab must be in 1..65535 (got %d)", ntab);
     DLRMB_REQUIRE(rows != nullptr, "rows is null");
     DLRMB_REQUIRE(D > 0 && ((D % 4 == 0 && D <= 1024) || D <= 256),
@@ -90,6 +96,7 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
     t->device = device;
     t->ntab = ntab;
     t->D = D;
+    t->elem_bytes = elem_bytes;
     t->max_lookups = max_lookups;
     t->cap = (max_lookups + 3) / 4 * 4;
     t->sm_count = device_sm_count(device);
@@ -105,7 +112,7 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
         t->h_rows[k] = rows[k];
         t->h_offsets[k] = off;
         int64_t elems = rows[k] * (int64_t)D;
-        off += (elems + 63) / 64 * 64;  // keep every table 256-byte aligned
+        off += (elems + 127) / 128 * 128;  // keep every table 256-byte aligned (f32 and bf16)
         t->total_rows += rows[k];
         if (rows[k] > t->max_rows) t->max_rows = rows[k];
     }
@@ -125,12 +132,12 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
     } while (0)
 
     TRY_CUDA(cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking));
-    TRY_CUDA(cudaMalloc((void**)&t->slab, sizeof(float) * (size_t)off));
+    TRY_CUDA(cudaMalloc((void**)&t->slab, (size_t)elem_bytes * (size_t)off));
     TRY_CUDA(cudaMalloc((void**)&t->d_desc, sizeof(TableDesc) * ntab));
     {
         TableDesc* h = (TableDesc*)malloc(sizeof(TableDesc) * ntab);
         for (int k = 0; k < ntab; ++k) {
-            h[k].base = t->slab + t->h_offsets[k];
+            h[k].base = reinterpret_cast<float*>(reinterpret_cast<char*>(t->slab) + (size_t)t->h_offsets[k] * elem_bytes);
             h[k].rows = t->h_rows[k];
         }
         cudaError_t e = cudaMemcpy(t->d_desc, h, sizeof(TableDesc) * ntab, cudaMemcpyHostToDevice);
@@ -192,6 +199,8 @@ int32_t dlrmb_tables_destroy(dlrmb_tables* t) {
     return DLRMB_OK;
 }
 
+int32_t dlrmb_tables_elem_bytes(const dlrmb_tables* t) { return t ? t->elem_bytes : 0; }
+
 int32_t dlrmb_tables_info(const dlrmb_tables* t, int32_t* ntab, int32_t* D, int64_t* max_lookups,
                           int64_t* total_rows) {
     DLRMB_REQUIRE(t != nullptr, "null tables handle");
@@ -202,12 +211,24 @@ int32_t dlrmb_tables_info(const dlrmb_tables* t, int32_t* ntab, int32_t* D, int6
     return DLRMB_OK;
 }
 
+static inline char* table_ptr(dlrmb_tables* t, int k) {
+    return reinterpret_cast<char*>(t->slab) + (size_t)t->h_offsets[k] * t->elem_bytes;
+}
+
 int32_t dlrmb_tables_upload(dlrmb_tables* t, int32_t k, const float* host) {
     GUARD(t);
     DLRMB_REQUIRE(k >= 0 && k < t->ntab, "table index %d outside 0..%d", k, t->ntab - 1);
     DLRMB_REQUIRE(host != nullptr, "host buffer is null");
     size_t bytes = sizeof(float) * (size_t)t->h_rows[k] * (size_t)t->D;
-    DLRMB_CUDA(cudaMemcpyAsync(t->slab + t->h_offsets[k], host, bytes, cudaMemcpyHostToDevice, t->own_stream));
+    if (t->elem_bytes == 4) {
+        DLRMB_CUDA(cudaMemcpyAsync(table_ptr(t, k), host, bytes, cudaMemcpyHostToDevice, t->own_stream));
+    } else {   // bf16 storage: stage the f32 rows on the device, round to nearest even there
+        int rc = grow((void**)&t->stage_a, &t->stage_a_bytes, bytes);
+        if (rc) return rc;
+        DLRMB_CUDA(cudaMemcpyAsync(t->stage_a, host, bytes, cudaMemcpyHostToDevice, t->own_stream));
+        rc = launch_convert_rows(t, k, t->stage_a, true, t->own_stream);
+        if (rc) return rc;
+    }
     DLRMB_CUDA(cudaStreamSynchronize(t->own_stream));
     return DLRMB_OK;
 }
@@ -219,7 +240,15 @@ int32_t dlrmb_tables_download(dlrmb_tables* t, int32_t k, float* host) {
     size_t bytes = sizeof(float) * (size_t)t->h_rows[k] * (size_t)t->D;
     // the caller's compute streams may still be updating the table: drain the device first
     DLRMB_CUDA(cudaDeviceSynchronize());
-    DLRMB_CUDA(cudaMemcpyAsync(host, t->slab + t->h_offsets[k], bytes, cudaMemcpyDeviceToHost, t->own_stream));
+    if (t->elem_bytes == 4) {
+        DLRMB_CUDA(cudaMemcpyAsync(host, table_ptr(t, k), bytes, cudaMemcpyDeviceToHost, t->own_stream));
+    } else {
+        int rc = grow((void**)&t->stage_a, &t->stage_a_bytes, bytes);
+        if (rc) return rc;
+        rc = launch_convert_rows(t, k, t->stage_a, false, t->own_stream);
+        if (rc) return rc;
+        DLRMB_CUDA(cudaMemcpyAsync(host, t->stage_a, bytes, cudaMemcpyDeviceToHost, t->own_stream));
+    }
     DLRMB_CUDA(cudaStreamSynchronize(t->own_stream));
     return DLRMB_OK;
 }
@@ -227,7 +256,7 @@ int32_t dlrmb_tables_download(dlrmb_tables* t, int32_t k, float* host) {
 int32_t dlrmb_tables_device_ptr(dlrmb_tables* t, int32_t k, float** dev) {
     DLRMB_REQUIRE(t != nullptr && dev != nullptr, "null argument");
     DLRMB_REQUIRE(k >= 0 && k < t->ntab, "table index %d outside 0..%d", k, t->ntab - 1);
-    *dev = t->slab + t->h_offsets[k];
+    *dev = reinterpret_cast<float*>(table_ptr(t, k));
     return DLRMB_OK;
 }
 

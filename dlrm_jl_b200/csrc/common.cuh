@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libdlrm_b200.so.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -43,8 +44,44 @@ extern std::atomic<long long> g_launches;
 
 // ---- table storage -----------------------------------------------------------------------
 struct TableDesc {
-    float* base;   // [rows][D] f32 in HBM, 256-byte aligned
+    float* base;   // [rows][D] in HBM, 256-byte aligned; f32, or bf16 when the tables store bf16
     int64_t rows;
+};
+
+// Row storage access.  Tables are f32 (the reference default) or bf16 (its `embedding_eltype`
+// option, DLRM.jl src/model/model.jl:187 and the BF16 load/store hooks of src/cachedarrays.jl:5-19):
+// all arithmetic stays fp32, only the stored rows are rounded (to nearest even).
+template <typename RowT> struct RowIO;
+template <> struct RowIO<float> {
+    static __device__ __forceinline__ const float* row(const float* base, size_t r, size_t D) { return base + r * D; }
+    static __device__ __forceinline__ float* row(float* base, size_t r, size_t D) { return base + r * D; }
+    static __device__ __forceinline__ float4 load4(const float* row, int c) { return reinterpret_cast<const float4*>(row)[c]; }
+    static __device__ __forceinline__ float4 ldg4(const float* row, int c) { return __ldg(reinterpret_cast<const float4*>(row) + c); }
+    static __device__ __forceinline__ void store4(float* row, int c, float4 v) { reinterpret_cast<float4*>(row)[c] = v; }
+    static __device__ __forceinline__ float load1(const float* row, int c) { return row[c]; }
+    static __device__ __forceinline__ float ldg1(const float* row, int c) { return __ldg(row + c); }
+    static __device__ __forceinline__ void store1(float* row, int c, float v) { row[c] = v; }
+};
+template <> struct RowIO<__nv_bfloat16> {
+    using B = __nv_bfloat16;
+    static __device__ __forceinline__ const B* row(const float* base, size_t r, size_t D) { return reinterpret_cast<const B*>(base) + r * D; }
+    static __device__ __forceinline__ B* row(float* base, size_t r, size_t D) { return reinterpret_cast<B*>(base) + r * D; }
+    static __device__ __forceinline__ float4 unpack(uint2 q) {
+        return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                           __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+    }
+    static __device__ __forceinline__ float4 load4(const B* row, int c) { return unpack(reinterpret_cast<const uint2*>(row)[c]); }
+    static __device__ __forceinline__ float4 ldg4(const B* row, int c) { return unpack(__ldg(reinterpret_cast<const uint2*>(row) + c)); }
+    static __device__ __forceinline__ void store4(B* row, int c, float4 v) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 q;
+        q.x = *reinterpret_cast<unsigned int*>(&lo);
+        q.y = *reinterpret_cast<unsigned int*>(&hi);
+        reinterpret_cast<uint2*>(row)[c] = q;
+    }
+    static __device__ __forceinline__ float load1(const B* row, int c) { return __bfloat162float(row[c]); }
+    static __device__ __forceinline__ float ldg1(const B* row, int c) { return __bfloat162float(row[c]); }
+    static __device__ __forceinline__ void store1(B* row, int c, float v) { row[c] = __float2bfloat16_rn(v); }
 };
 
 // Geometry of the sorted-stream reduction (update.cu): every lane group walks TILE
@@ -59,6 +96,7 @@ struct dlrmb_tables {
     int device = 0;
     int ntab = 0;
     int D = 0;
+    int elem_bytes = 4;        // 4 = f32 rows, 2 = bf16 rows
     int sm_count = 148;
     int64_t max_lookups = 0;   // max B*P per table
     int64_t cap = 0;           // max_lookups rounded up to 4: stride of the per-table streams
@@ -66,7 +104,7 @@ struct dlrmb_tables {
     int64_t max_rows = 0;
     int64_t* h_rows = nullptr;       // host copy
     int64_t* h_offsets = nullptr;    // element offsets of each table inside `slab`
-    float* slab = nullptr;           // all tables, one allocation
+    float* slab = nullptr;           // all tables, one allocation (f32 or bf16 elements)
     dlrmb::TableDesc* d_desc = nullptr;
     int32_t* d_slotmap = nullptr;    // sharded use: interaction slot of each local table
     cudaStream_t own_stream = nullptr;
@@ -117,6 +155,7 @@ int launch_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, i
 int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s);
 int launch_dedup_export(dlrmb_tables* t, int k, cudaStream_t s);
 int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s);
+int launch_convert_rows(dlrmb_tables* t, int k, float* f32_buf, bool to_table, cudaStream_t s);
 int launch_check_indices(dlrmb_tables* t, const void* d_idx, int idx_bytes, int idx_base, int B,
                          int P, cudaStream_t s, long long* bad_table, long long* bad_pos,
                          long long* bad_val);

@@ -17,6 +17,10 @@ namespace dlrmb {
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
     using type = float4;
+    template <typename RowT>
+    static __device__ __forceinline__ float4 ldrow(const float* base, size_t r, size_t D, int c) {
+        return RowIO<RowT>::ldg4(RowIO<RowT>::row(base, r, D), c);
+    }
     static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
     static __device__ __forceinline__ float4 add(float4 a, float4 b) {
         return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
@@ -24,12 +28,16 @@ template <> struct Vec<4> {
 };
 template <> struct Vec<1> {
     using type = float;
+    template <typename RowT>
+    static __device__ __forceinline__ float ldrow(const float* base, size_t r, size_t D, int c) {
+        return RowIO<RowT>::ldg1(RowIO<RowT>::row(base, r, D), c);
+    }
     static __device__ __forceinline__ float zero() { return 0.f; }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 };
 
 // P == 1: plain gather.  U independent chains per thread.
-template <typename IdxT, int VEC, int U>
+template <typename IdxT, int VEC, int U, typename RowT>
 __global__ void __launch_bounds__(256)
 lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
                      uint32_t B, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
@@ -58,7 +66,7 @@ lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict_
         V v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (ok[u]) v[u] = __ldg(reinterpret_cast<const V*>(tb + (size_t)row[u] * D) + c[u]);
+            if (ok[u]) v[u] = Vec<VEC>::template ldrow<RowT>(tb, (size_t)row[u], D, c[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (ok[u]) reinterpret_cast<V*>(ob + (size_t)b[u] * ostride)[c[u]] = v[u];
@@ -66,7 +74,7 @@ lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict_
 }
 
 // P > 1: gather + sum-pool, ascending p.
-template <typename IdxT, int VEC>
+template <typename IdxT, int VEC, typename RowT>
 __global__ void __launch_bounds__(256)
 lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
                    uint32_t B, uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
@@ -91,10 +99,10 @@ lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
             int64_t r1 = (int64_t)__ldg(ip + p + 1) - idx_base;
             int64_t r2 = (int64_t)__ldg(ip + p + 2) - idx_base;
             int64_t r3 = (int64_t)__ldg(ip + p + 3) - idx_base;
-            V v0 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r0 * D) + c);
-            V v1 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r1 * D) + c);
-            V v2 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r2 * D) + c);
-            V v3 = __ldg(reinterpret_cast<const V*>(tb + (size_t)r3 * D) + c);
+            V v0 = Vec<VEC>::template ldrow<RowT>(tb, (size_t)r0, D, c);
+            V v1 = Vec<VEC>::template ldrow<RowT>(tb, (size_t)r1, D, c);
+            V v2 = Vec<VEC>::template ldrow<RowT>(tb, (size_t)r2, D, c);
+            V v3 = Vec<VEC>::template ldrow<RowT>(tb, (size_t)r3, D, c);
             acc = Vec<VEC>::add(acc, v0);
             acc = Vec<VEC>::add(acc, v1);
             acc = Vec<VEC>::add(acc, v2);
@@ -102,13 +110,13 @@ lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
         }
         for (; p < P; ++p) {
             int64_t r = (int64_t)__ldg(ip + p) - idx_base;
-            acc = Vec<VEC>::add(acc, __ldg(reinterpret_cast<const V*>(tb + (size_t)r * D) + c));
+            acc = Vec<VEC>::add(acc, Vec<VEC>::template ldrow<RowT>(tb, (size_t)r, D, c));
         }
         reinterpret_cast<V*>(ob + (size_t)b * ostride)[c] = acc;
     }
 }
 
-template <typename IdxT, int VEC>
+template <typename IdxT, int VEC, typename RowT>
 static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, float* out,
                            int slots, int slot0, cudaStream_t s) {
     const uint32_t C = t->D / VEC;
@@ -126,24 +134,32 @@ static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B
         while ((1u << cshift) < C) ++cshift;
     }
     if (P == 1)
-        lookup_gather_kernel<IdxT, VEC, U><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, cshift, out, slots, slot0);
+        lookup_gather_kernel<IdxT, VEC, U, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, cshift, out, slots, slot0);
     else
-        lookup_pool_kernel<IdxT, VEC><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0);
+        lookup_pool_kernel<IdxT, VEC, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }
 
-int launch_lookup(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
-                  float* out, int slots, int slot0, cudaStream_t s) {
+template <typename RowT>
+static int launch_lookup_r(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                           float* out, int slots, int slot0, cudaStream_t s) {
     const bool vec4 = (t->D % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (idx_bytes == 4) {
         const uint32_t* p = static_cast<const uint32_t*>(idx);
-        return vec4 ? launch_lookup_t<uint32_t, 4>(t, p, idx_base, B, P, out, slots, slot0, s)
-                    : launch_lookup_t<uint32_t, 1>(t, p, idx_base, B, P, out, slots, slot0, s);
+        return vec4 ? launch_lookup_t<uint32_t, 4, RowT>(t, p, idx_base, B, P, out, slots, slot0, s)
+                    : launch_lookup_t<uint32_t, 1, RowT>(t, p, idx_base, B, P, out, slots, slot0, s);
     }
     const int64_t* p = static_cast<const int64_t*>(idx);
-    return vec4 ? launch_lookup_t<int64_t, 4>(t, p, idx_base, B, P, out, slots, slot0, s)
-                : launch_lookup_t<int64_t, 1>(t, p, idx_base, B, P, out, slots, slot0, s);
+    return vec4 ? launch_lookup_t<int64_t, 4, RowT>(t, p, idx_base, B, P, out, slots, slot0, s)
+                : launch_lookup_t<int64_t, 1, RowT>(t, p, idx_base, B, P, out, slots, slot0, s);
+}
+
+int launch_lookup(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                  float* out, int slots, int slot0, cudaStream_t s) {
+    if (t->elem_bytes == 2)
+        return launch_lookup_r<__nv_bfloat16>(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, s);
+    return launch_lookup_r<float>(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, s);
 }
 
 // ---- ScaledUniform init (src/model/model.jl:61-65): U(-1/sqrt(rows), 1/sqrt(rows)) ------------
@@ -154,14 +170,38 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+template <typename RowT>
 __global__ void __launch_bounds__(256)
 init_uniform_kernel(float* __restrict__ base, int64_t elems, float scale, uint64_t stream_seed) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    auto* dst = RowIO<RowT>::row(base, 0, 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += step) {
         uint64_t h = mix64(stream_seed ^ mix64((uint64_t)i));
         float u = (float)(h >> 40) * (1.0f / 16777216.0f);  // [0, 1) on 24 bits
-        base[i] = (2.0f * u - 1.0f) * scale;
+        dst[i] = (RowT)((2.0f * u - 1.0f) * scale);
     }
+}
+
+// f32 staging buffer <-> table rows (only used for bf16 storage: upload rounds to nearest even)
+template <bool TO_TABLE>
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(__nv_bfloat16* __restrict__ table, float* __restrict__ buf, int64_t elems) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += step) {
+        if (TO_TABLE) table[i] = __float2bfloat16_rn(buf[i]);
+        else buf[i] = __bfloat162float(table[i]);
+    }
+}
+
+int launch_convert_rows(dlrmb_tables* t, int k, float* f32_buf, bool to_table, cudaStream_t s) {
+    const int64_t elems = t->h_rows[k] * (int64_t)t->D;
+    int64_t blocks = ceil_div64(elems, 256 * 4);
+    if (blocks > (int64_t)t->sm_count * 16) blocks = (int64_t)t->sm_count * 16;
+    auto* table = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(t->slab) + (size_t)t->h_offsets[k] * 2);
+    if (to_table) convert_rows_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(table, f32_buf, elems);
+    else convert_rows_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(table, f32_buf, elems);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
 }
 
 int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s) {
@@ -172,7 +212,11 @@ int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s) {
         int64_t cap = (int64_t)t->sm_count * 16;
         if (blocks > cap) blocks = cap;
         uint64_t stream_seed = seed * 0x9E3779B97F4A7C15ull + (uint64_t)(k + 1) * 0xD1B54A32D192ED03ull;
-        init_uniform_kernel<<<(unsigned)blocks, 256, 0, s>>>(t->slab + t->h_offsets[k], elems, scale, stream_seed);
+        float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(t->slab) + (size_t)t->h_offsets[k] * t->elem_bytes);
+        if (t->elem_bytes == 2)
+            init_uniform_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(base, elems, scale, stream_seed);
+        else
+            init_uniform_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(base, elems, scale, stream_seed);
         DLRMB_LAUNCH_CHECK();
     }
     return DLRMB_OK;

@@ -23,7 +23,14 @@ struct PeerPtrs {
 
 // Same mapping as lookup_gather_kernel (one thread per 16-byte chunk, 4 independent index -> row
 // chains), but sample b lives on rank b / B_local and table k lands in slot slotmap[k].
-template <typename IdxT, int VEC, int U>
+template <int VEC, typename RowT>
+__device__ __forceinline__ typename std::conditional<VEC == 4, float4, float>::type
+p2p_ldrow(const float* base, size_t r, size_t D, int c) {
+    if constexpr (VEC == 4) return RowIO<RowT>::ldg4(RowIO<RowT>::row(base, r, D), c);
+    else return RowIO<RowT>::ldg1(RowIO<RowT>::row(base, r, D), c);
+}
+
+template <typename IdxT, int VEC, int U, typename RowT>
 __global__ void __launch_bounds__(256)
 lookup_p2p_kernel(const TableDesc* __restrict__ desc, const int32_t* __restrict__ slotmap,
                   const IdxT* __restrict__ idx, int idx_base, uint32_t Bg, uint32_t B_local, uint32_t P,
@@ -55,15 +62,15 @@ lookup_p2p_kernel(const TableDesc* __restrict__ desc, const int32_t* __restrict_
             for (int u = 0; u < U; ++u) row[u] = ok[u] ? (int64_t)__ldg(ik + b[u]) - idx_base : 0;
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (ok[u]) acc[u] = __ldg(reinterpret_cast<const V*>(tb + (size_t)row[u] * D) + c[u]);
+                if (ok[u]) acc[u] = p2p_ldrow<VEC, RowT>(tb, (size_t)row[u], D, c[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!ok[u]) continue;
                 const IdxT* ip = ik + (size_t)b[u] * P;
-                V a = __ldg(reinterpret_cast<const V*>(tb + (size_t)((int64_t)__ldg(ip) - idx_base) * D) + c[u]);
+                V a = p2p_ldrow<VEC, RowT>(tb, (size_t)((int64_t)__ldg(ip) - idx_base), D, c[u]);
                 for (uint32_t p = 1; p < P; ++p) {
-                    V v = __ldg(reinterpret_cast<const V*>(tb + (size_t)((int64_t)__ldg(ip + p) - idx_base) * D) + c[u]);
+                    V v = p2p_ldrow<VEC, RowT>(tb, (size_t)((int64_t)__ldg(ip + p) - idx_base), D, c[u]);
                     if constexpr (VEC == 4) {
                         a = make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
                     } else {
@@ -84,7 +91,7 @@ lookup_p2p_kernel(const TableDesc* __restrict__ desc, const int32_t* __restrict_
     }
 }
 
-template <typename IdxT, int VEC>
+template <typename IdxT, int VEC, typename RowT>
 static int launch_p2p_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int Bg, int P, const PeerPtrs& peers,
                         int B_local, int slots, cudaStream_t s) {
     const uint32_t C = t->D / VEC;
@@ -95,7 +102,7 @@ static int launch_p2p_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int Bg, 
     const int64_t cap = (int64_t)t->sm_count * 32;
     if (bx * t->ntab > cap) bx = cap / t->ntab > 0 ? cap / t->ntab : 1;
     dim3 grid((unsigned)bx, (unsigned)t->ntab);
-    lookup_p2p_kernel<IdxT, VEC, U><<<grid, 256, 0, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
+    lookup_p2p_kernel<IdxT, VEC, U, RowT><<<grid, 256, 0, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
                                                          peers, slots);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
@@ -207,12 +214,20 @@ int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_by
     }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (idx_bytes == 4)
-        rc = aligned ? launch_p2p_t<uint32_t, 4>(t, (const uint32_t*)idx, idx_base, B_global, P, peers, B_local, slots, s)
-                     : launch_p2p_t<uint32_t, 1>(t, (const uint32_t*)idx, idx_base, B_global, P, peers, B_local, slots, s);
-    else
-        rc = aligned ? launch_p2p_t<int64_t, 4>(t, (const int64_t*)idx, idx_base, B_global, P, peers, B_local, slots, s)
-                     : launch_p2p_t<int64_t, 1>(t, (const int64_t*)idx, idx_base, B_global, P, peers, B_local, slots, s);
+    const bool bf = t->elem_bytes == 2;
+    if (idx_bytes == 4) {
+        const uint32_t* ip = (const uint32_t*)idx;
+        if (aligned) rc = bf ? launch_p2p_t<uint32_t, 4, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
+                             : launch_p2p_t<uint32_t, 4, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
+        else rc = bf ? launch_p2p_t<uint32_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
+                     : launch_p2p_t<uint32_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
+    } else {
+        const int64_t* ip = (const int64_t*)idx;
+        if (aligned) rc = bf ? launch_p2p_t<int64_t, 4, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
+                             : launch_p2p_t<int64_t, 4, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
+        else rc = bf ? launch_p2p_t<int64_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
+                     : launch_p2p_t<int64_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
+    }
     if (prev >= 0 && prev != t->device) cudaSetDevice(prev);
     return rc;
 }

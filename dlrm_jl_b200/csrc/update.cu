@@ -52,6 +52,25 @@ template <> struct UV<1> {
     }
 };
 
+// table-row access in the row's storage type (f32 or bf16); chunk c = floats [c*VEC, c*VEC + VEC)
+template <int VEC, typename RowT> struct RowV;
+template <typename RowT> struct RowV<4, RowT> {
+    static __device__ __forceinline__ float4 load(const float* base, size_t r, size_t D, int c) {
+        return RowIO<RowT>::load4(RowIO<RowT>::row(base, r, D), c);
+    }
+    static __device__ __forceinline__ void store(float* base, size_t r, size_t D, int c, float4 v) {
+        RowIO<RowT>::store4(RowIO<RowT>::row(base, r, D), c, v);
+    }
+};
+template <typename RowT> struct RowV<1, RowT> {
+    static __device__ __forceinline__ float load(const float* base, size_t r, size_t D, int c) {
+        return RowIO<RowT>::load1(RowIO<RowT>::row(base, r, D), c);
+    }
+    static __device__ __forceinline__ void store(float* base, size_t r, size_t D, int c, float v) {
+        RowIO<RowT>::store1(RowIO<RowT>::row(base, r, D), c, v);
+    }
+};
+
 // per-tile (shared memory) and per-chunk (global) run-boundary flags
 enum : uint8_t { FLAG_CARRY_IN = 1, FLAG_CARRY_ENDS = 2, FLAG_HEAD = 4 };
 
@@ -62,7 +81,7 @@ struct UpdateGeom {
     int64_t cap, pcap;   // stream stride per table; partial / flag stride per table (in chunks)
 };
 
-template <int VEC, int NCH, int THREADS>
+template <int VEC, int NCH, int THREADS, typename RowT>
 __global__ void __launch_bounds__(THREADS, (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1))
 update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
                     const uint32_t* __restrict__ pos, const float* __restrict__ dT, float lr,
@@ -138,10 +157,9 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const V* row = reinterpret_cast<const V*>(tb + (size_t)key[u] * D);
 #pragma unroll
                 for (int m = 0; m < NCH; ++m)
-                    if (is_end[u] && chunk_ok[m]) rv[u][m] = row[sl + m * lpr];
+                    if (is_end[u] && chunk_ok[m]) rv[u][m] = RowV<VEC, RowT>::load(tb, key[u], D, sl + m * lpr);
             }
             if (e + U >= e1) {
                 cout = (e1 < gm.L) && (e + U == e1) && (key[U] == key[U - 1]);
@@ -162,10 +180,10 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
                         for (int m = 0; m < NCH; ++m) s_carry[(grp * NCH + m) * lpr + sl] = acc[m];
                         fl |= FLAG_CARRY_ENDS;
                     } else {
-                        V* row = reinterpret_cast<V*>(tb + (size_t)key[u] * D);
 #pragma unroll
                         for (int m = 0; m < NCH; ++m)
-                            if (chunk_ok[m]) row[sl + m * lpr] = UV<VEC>::sgd(rv[u][m], acc[m], lr);
+                            if (chunk_ok[m])
+                                RowV<VEC, RowT>::store(tb, key[u], D, sl + m * lpr, UV<VEC>::sgd(rv[u][m], acc[m], lr));
                     }
                     first = false;
 #pragma unroll
@@ -205,10 +223,11 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             if (s_flag[j] & FLAG_CARRY_ENDS) { ended = true; break; }
         }
         if (ended) {
-            V* row = reinterpret_cast<V*>(tb + (size_t)last_key * D);
 #pragma unroll
             for (int m = 0; m < NCH; ++m)
-                if (chunk_ok[m]) row[sl + m * lpr] = UV<VEC>::sgd(row[sl + m * lpr], tot[m], lr);
+                if (chunk_ok[m])
+                    RowV<VEC, RowT>::store(tb, last_key, D, sl + m * lpr,
+                                           UV<VEC>::sgd(RowV<VEC, RowT>::load(tb, last_key, D, sl + m * lpr), tot[m], lr));
         } else {   // the run leaves the chunk: level 3 finishes it
 #pragma unroll
             for (int m = 0; m < NCH; ++m)
@@ -248,7 +267,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
 // added in group order on top of the head partial, and the row is updated once.  The order
 // depends only on the geometry, so the result is bit-reproducible (the work list's order is not,
 // but no arithmetic depends on it).
-template <int VEC, int NCH>
+template <int VEC, int NCH, typename RowT>
 __global__ void __launch_bounds__(256)
 update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys, float lr,
                     const float* __restrict__ partial, const uint8_t* __restrict__ flags,
@@ -310,14 +329,15 @@ update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             const int nact = min(nsub, u_last - g);
             int last = (g + 1) * chunk_entries - 1;          // last entry of the head chunk
             const uint32_t key = keys[(size_t)k * gm.cap + last];
-            V* row = reinterpret_cast<V*>(desc[k].base + (size_t)key * D);
+            float* tbase = desc[k].base;
             const V* hp = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D);
 #pragma unroll
             for (int m = 0; m < NCH; ++m) {
                 if (sl + m * lpr < gm.C) {
                     V total = hp[sl + m * lpr];
                     for (int j = 0; j < nact; ++j) total = UV<VEC>::add(total, red[(j * NCH + m) * lpr + sl]);
-                    row[sl + m * lpr] = UV<VEC>::sgd(row[sl + m * lpr], total, lr);
+                    RowV<VEC, RowT>::store(tbase, key, D, sl + m * lpr,
+                                           UV<VEC>::sgd(RowV<VEC, RowT>::load(tbase, key, D, sl + m * lpr), total, lr));
                 }
             }
         }
@@ -352,7 +372,7 @@ int64_t update_tiles_cap(int ntab, int D, int64_t max_lookups, int sm_count) {
     return ceil_div64(ceil_div64(max_lookups, 4), G) + 2;   // smallest tile (4) gives the most chunks
 }
 
-template <int VEC, int NCH>
+template <int VEC, int NCH, typename RowT>
 static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr,
                            cudaStream_t s) {
     UpdateGeom gm;
@@ -378,18 +398,19 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     const uint32_t* pos = t->pos[t->sorted_buf];
     DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, sizeof(uint32_t), s));
     dim3 grid((unsigned)gm.chunks, (unsigned)t->ntab);
-    update_tiles_kernel<VEC, NCH, THREADS><<<grid, THREADS, 0, s>>>(t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags,
+    update_tiles_kernel<VEC, NCH, THREADS, RowT><<<grid, THREADS, 0, s>>>(t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags,
                                                        t->head_list, t->head_count, gm);
     DLRMB_LAUNCH_CHECK();
     const int64_t total_chunks = (int64_t)t->ntab * gm.chunks;
     unsigned fgrid = (unsigned)(total_chunks < (int64_t)t->sm_count * 8 ? total_chunks : (int64_t)t->sm_count * 8);
-    update_fixup_kernel<VEC, NCH><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,
+    update_fixup_kernel<VEC, NCH, RowT><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,
                                                         t->head_list, t->head_count, gm);
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }
 
-int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s) {
+template <typename RowT>
+static int launch_update_r(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s) {
     const bool vec4 = (t->D % 4 == 0) && ((reinterpret_cast<uintptr_t>(dT) & 15) == 0);
     if (t->D % 4 == 0 && !vec4) {
         set_error("dT must be 16-byte aligned when D is a multiple of 4");
@@ -399,18 +420,23 @@ int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float 
     const int lpr = 1 << lanes_per_row_log2(C);
     const int nch = (C + lpr - 1) / lpr;
     if (vec4) {
-        if (nch == 1) return launch_update_t<4, 1>(t, dT, slots, slot0, lr, s);
-        if (nch == 2) return launch_update_t<4, 2>(t, dT, slots, slot0, lr, s);
-        if (nch <= 4) return launch_update_t<4, 4>(t, dT, slots, slot0, lr, s);
-        if (nch <= 8) return launch_update_t<4, 8>(t, dT, slots, slot0, lr, s);
+        if (nch == 1) return launch_update_t<4, 1, RowT>(t, dT, slots, slot0, lr, s);
+        if (nch == 2) return launch_update_t<4, 2, RowT>(t, dT, slots, slot0, lr, s);
+        if (nch <= 4) return launch_update_t<4, 4, RowT>(t, dT, slots, slot0, lr, s);
+        if (nch <= 8) return launch_update_t<4, 8, RowT>(t, dT, slots, slot0, lr, s);
     } else {
-        if (nch == 1) return launch_update_t<1, 1>(t, dT, slots, slot0, lr, s);
-        if (nch == 2) return launch_update_t<1, 2>(t, dT, slots, slot0, lr, s);
-        if (nch <= 4) return launch_update_t<1, 4>(t, dT, slots, slot0, lr, s);
-        if (nch <= 8) return launch_update_t<1, 8>(t, dT, slots, slot0, lr, s);
+        if (nch == 1) return launch_update_t<1, 1, RowT>(t, dT, slots, slot0, lr, s);
+        if (nch == 2) return launch_update_t<1, 2, RowT>(t, dT, slots, slot0, lr, s);
+        if (nch <= 4) return launch_update_t<1, 4, RowT>(t, dT, slots, slot0, lr, s);
+        if (nch <= 8) return launch_update_t<1, 8, RowT>(t, dT, slots, slot0, lr, s);
     }
     set_error("embedding dim %d unsupported by the update kernel", t->D);
     return DLRMB_EINVAL;
+}
+
+int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s) {
+    if (t->elem_bytes == 2) return launch_update_r<__nv_bfloat16>(t, dT, slots, slot0, lr, s);
+    return launch_update_r<float>(t, dT, slots, slot0, lr, s);
 }
 
 }  // namespace dlrmb

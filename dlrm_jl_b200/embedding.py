@@ -65,9 +65,9 @@ def _as_index_tensor(sparse, ntab: int, device: torch.device) -> torch.Tensor:
 class _DevicePtrView:
     """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
 
-    def __init__(self, ptr: int, shape, owner):
+    def __init__(self, ptr: int, shape, owner, typestr: str = "<f4"):
         self.__cuda_array_interface__ = {
-            "shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None,
+            "shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": None,
         }
         self._owner = owner
 
@@ -79,7 +79,13 @@ class EmbeddingTables:
     sized from it once, so no call allocates.
     """
 
-    def __init__(self, rows: Sequence[int], D: int, max_lookups: int, device: Union[int, torch.device] = 0):
+    def __init__(self, rows: Sequence[int], D: int, max_lookups: int, device: Union[int, torch.device] = 0,
+                 dtype: torch.dtype = torch.float32):
+        """``dtype``: storage type of the rows, ``torch.float32`` (default) or ``torch.bfloat16`` (the
+        reference's ``embedding_eltype`` option, src/model/model.jl:187); arithmetic is fp32 either way."""
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise _lib.DLRMB200Error(_lib.EINVAL, f"table dtype {dtype} not supported (float32 / bfloat16)")
+        self.dtype = dtype
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if dev.type != "cuda":
             raise _lib.DLRMB200Error(_lib.EINVAL, "EmbeddingTables live in HBM: a CUDA device is required")
@@ -91,17 +97,19 @@ class EmbeddingTables:
         self._lib = _lib.load()
         arr = (C.c_int64 * self.ntab)(*self.rows)
         handle = C.c_void_p()
-        _lib.check(self._lib.dlrmb_tables_create(dev.index or 0, self.ntab, arr, self.D, self.max_lookups, C.byref(handle)))
+        _lib.check(self._lib.dlrmb_tables_create_ex(dev.index or 0, self.ntab, arr, self.D, self.max_lookups,
+                                                   4 if dtype == torch.float32 else 2, C.byref(handle)))
         self._h = handle
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._sorted_event: Optional[torch.cuda.Event] = None
 
     # -- construction helpers -----------------------------------------------------------------
     @classmethod
-    def from_arrays(cls, arrays: Sequence[np.ndarray], max_lookups: int, device=0) -> "EmbeddingTables":
+    def from_arrays(cls, arrays: Sequence[np.ndarray], max_lookups: int, device=0,
+                    dtype: torch.dtype = torch.float32) -> "EmbeddingTables":
         """``SimpleEmbedding{Static{D}}(data)`` for each array ([rows][D], i.e. Julia D x rows)."""
         D = int(arrays[0].shape[1])
-        t = cls([a.shape[0] for a in arrays], D, max_lookups, device)
+        t = cls([a.shape[0] for a in arrays], D, max_lookups, device, dtype)
         for k, a in enumerate(arrays):
             t.upload(k, a)
         return t
@@ -134,9 +142,12 @@ class EmbeddingTables:
         return out
 
     def table(self, k: int) -> torch.Tensor:
-        """Zero-copy [rows_k][D] device view of table k."""
+        """Zero-copy [rows_k][D] device view of table k (float32 or bfloat16, as stored)."""
         p = C.c_void_p()
         _lib.check(self._lib.dlrmb_tables_device_ptr(self._h, k, C.byref(p)))
+        if self.dtype == torch.bfloat16:
+            raw = torch.as_tensor(_DevicePtrView(p.value, (self.rows[k], self.D), self, "<i2"), device=self.device)
+            return raw.view(torch.bfloat16)
         return torch.as_tensor(_DevicePtrView(p.value, (self.rows[k], self.D), self), device=self.device)
 
     def init_uniform(self, seed: int = 51234) -> None:

@@ -60,6 +60,13 @@ int64_t dlrmb_launch_count(void);
  * storage of src/cachedarrays.jl with HBM-resident tables. ------------------------------- */
 int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
                             int64_t max_lookups, dlrmb_tables** out);
+/* Same with a storage element size: 4 = Float32 rows, 2 = BFloat16 rows (the reference's
+ * `embedding_eltype` option, src/model/model.jl:187; src/cachedarrays.jl:5-19).  With bf16 storage
+ * every kernel still accumulates in fp32; rows are rounded to nearest even when written.  Host
+ * buffers of upload/download stay Float32.   */
+int32_t dlrmb_tables_create_ex(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
+                               int64_t max_lookups, int32_t elem_bytes, dlrmb_tables** out);
+int32_t dlrmb_tables_elem_bytes(const dlrmb_tables* t);
 int32_t dlrmb_tables_destroy(dlrmb_tables* t);
 int32_t dlrmb_tables_info(const dlrmb_tables* t, int32_t* ntab, int32_t* D, int64_t* max_lookups,
                           int64_t* total_rows);

@@ -354,3 +354,25 @@ def dac_unpack(records: np.ndarray):
     dense = np.ascontiguousarray(records["continuous"], dtype=F32)
     sparse = np.ascontiguousarray(records["categorical"].T)
     return labels, dense, sparse
+
+
+# --------------------------------------------------------------------------------------
+# BF16 table storage
+# --------------------------------------------------------------------------------------
+def to_bf16(x: np.ndarray) -> np.ndarray:
+    """Round float32 to bfloat16 (nearest even) and return it widened back to float32: what a
+    table stored as BFloat16 (the reference's `embedding_eltype`, src/model/model.jl:187) holds."""
+    u = np.ascontiguousarray(x, dtype=F32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(F32).reshape(np.shape(x))
+
+
+def sparse_sgd_update_bf16(table: np.ndarray, idx: np.ndarray, delta: np.ndarray, lr: float) -> None:
+    """sparse_sgd_update_fast for a bf16-stored table: fp32 arithmetic, the written rows rounded."""
+    B, D = delta.shape
+    ik = np.asarray(idx).reshape(B, -1)
+    P = ik.shape[1]
+    uniq, inv = np.unique(ik.reshape(-1), return_inverse=True)
+    acc = np.zeros((len(uniq), D), dtype=F32)
+    np.add.at(acc, inv, np.repeat(delta, P, axis=0) if P > 1 else delta)
+    table[uniq] = to_bf16((table[uniq] - (F32(lr) * acc).astype(F32)).astype(F32))

@@ -121,14 +121,26 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
     def rec(name, us, nbytes):
         res[name] = {"us": us, "algorithmic_bytes": int(nbytes), "gbs": nbytes / us / 1e3, "frac_hbm": nbytes / us / 1e3 / peak}
 
-    if only and only.startswith("interaction"):
+    def interaction_inputs():
+        # a different T / dOut per launch, together larger than the 126 MB L2 when nb * B * F * D * 4
+        # allows it, so a launch cannot find the previous launch's tile in L2
         w = interaction_width(F, D)
-        t.lookup(idx[0], T, 1)
-        g = torch.randn((B, w), device=dev)
+        Ts, gs = [], []
+        for i in range(nb):
+            Ti = torch.empty((B, F, D), device=dev)
+            t.lookup(idx[i], Ti, 1)
+            Ti[:, 0] = torch.randn((B, D), device=dev)
+            Ts.append(Ti)
+            gs.append(torch.randn((B, w), device=dev))
+        res["interaction_inputs_mb"] = nb * B * F * D * 4 / 1e6
+        return w, Ts, gs
+
+    if only and only.startswith("interaction"):
+        w, Ts, gs = interaction_inputs()
         if only == "interaction_fwd":
-            rec("interaction_fwd", time_graph(lambda i: interaction_fwd(T), nb, use_graph, iters), B * (F * D + w) * 4)
+            rec("interaction_fwd", time_graph(lambda i: interaction_fwd(Ts[i]), nb, use_graph, iters), B * (F * D + w) * 4)
         else:
-            rec("interaction_bwd", time_graph(lambda i: interaction_bwd(g, T), nb, use_graph, iters), B * (w + 2 * F * D + D) * 4)
+            rec("interaction_bwd", time_graph(lambda i: interaction_bwd(gs[i], Ts[i]), nb, use_graph, iters), B * (w + 2 * F * D + D) * 4)
         t.close()
         return res
     us = time_graph(lambda i: t.lookup(idx[i], T, 1), nb, use_graph, iters)
@@ -146,14 +158,14 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
     rec("update_only", max(us_both - us_sort, 1e-3), update_bytes)
     rec("embedding_lookup_plus_update", res["lookup"]["us"] + us_both, lookup_bytes + update_bytes)
     if interaction and D % 4 == 0 and F <= 64:
-        w = interaction_width(F, D)
-        g = torch.randn((B, w), device=dev)
-        us = time_graph(lambda i: interaction_fwd(T), nb, use_graph, iters)
+        w, Ts, gs = interaction_inputs()
+        us = time_graph(lambda i: interaction_fwd(Ts[i]), nb, use_graph, iters)
         rec("interaction_fwd", us, B * (F * D + w) * 4)
         res["interaction_fwd"]["gflops_useful"] = 2.0 * B * (F * (F - 1) // 2) * D / us / 1e3
-        us = time_graph(lambda i: interaction_bwd(g, T), nb, use_graph, iters)
+        us = time_graph(lambda i: interaction_bwd(gs[i], Ts[i]), nb, use_graph, iters)
         rec("interaction_bwd", us, B * (w + 2 * F * D + D) * 4)
         res["interaction_bwd"]["gflops"] = 2.0 * B * F * F * D / us / 1e3
+    res["interaction_path"] = os.environ.get("DLRMB_INTERACT", "warp")
     t.close()
     del T, dT, idx
     torch.cuda.empty_cache()

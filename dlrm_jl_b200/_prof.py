@@ -3,6 +3,13 @@
 Disabled by default (zero overhead beyond one attribute test).  When enabled, every call into
 libdlrm_b200.so made through the host mirror is bracketed by a pair of events recorded on the
 stream the kernels are launched on, so durations are device time of exactly those kernels.
+
+Two modes:
+  * eager: a fresh event pair per call; `summary()` after a device synchronize.
+  * graph (`enable(True, external=True)` while a CUDA graph is being captured): the pairs become
+    event-record NODES of the graph (cudaEventRecordExternal), so every replay re-stamps them with
+    the kernels running back to back exactly as in the replayed step; call `read_replay()` after
+    each replay + synchronize.
 """
 from __future__ import annotations
 
@@ -13,13 +20,15 @@ from typing import Dict, List, Tuple
 import torch
 
 _enabled = False
+_external = False
 _events: Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = defaultdict(list)
 
 
-def enable(flag: bool = True) -> None:
-    global _enabled
+def enable(flag: bool = True, external: bool = False) -> None:
+    global _enabled, _external
     _enabled = flag
     if flag:
+        _external = external
         _events.clear()
 
 
@@ -28,8 +37,8 @@ def range(name: str):  # noqa: A001 - mirrors nvtx.range
     if not _enabled:
         yield
         return
-    a = torch.cuda.Event(enable_timing=True)
-    b = torch.cuda.Event(enable_timing=True)
+    a = torch.cuda.Event(enable_timing=True, external=_external)
+    b = torch.cuda.Event(enable_timing=True, external=_external)
     a.record()
     try:
         yield
@@ -45,3 +54,8 @@ def summary() -> Dict[str, Dict[str, float]]:
         ms = [a.elapsed_time(b) for a, b in pairs]
         out[name] = {"count": len(ms), "total_ms": float(sum(ms)), "avg_ms": float(sum(ms) / max(1, len(ms)))}
     return out
+
+
+def read_replay() -> Dict[str, List[float]]:
+    """Graph mode: name -> milliseconds of every captured call, as stamped by the last replay."""
+    return {name: [a.elapsed_time(b) for a, b in pairs] for name, pairs in _events.items()}

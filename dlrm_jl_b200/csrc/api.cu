@@ -321,6 +321,8 @@ int32_t dlrmb_interaction_bwd(int32_t device, const float* dOut, const float* T,
     return launch_interaction_bwd(dOut, T, B, F, d, pad_to_mul, dT, dx, device_sm_count(device), (cudaStream_t)stream);
 }
 
+int32_t dlrmb_interaction_has_warp_path(int32_t F, int32_t d) { return interaction_has_warp_path(F, d) ? 1 : 0; }
+
 int32_t dlrmb_interaction_bwd_scatter(int32_t device, const float* dOut, const float* T, int32_t B,
                                       int32_t F, int32_t d, int32_t pad_to_mul,
                                       const dlrmb_slot_dest* dests, int64_t sample_offset, float* dx,

@@ -150,6 +150,7 @@ int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int 
 int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
                               float* dT, float* dx, const void* dests, long long sample_offset,
                               int sm_count, cudaStream_t s);
+bool interaction_has_warp_path(int F, int d);
 int launch_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
                 cudaStream_t s);
 int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s);

@@ -302,11 +302,22 @@ static int launch_fwd_tb(float* T, const float* x, int B, int F, int d, int widt
     return DLRMB_OK;
 }
 
+// interact_warp.cu: warp-per-sample FFMA2 kernels for the DLRM shapes (-1 = no specialisation)
+int try_interaction_fwd_warp(float* T, const float* x, int B, int F, int d, int width, float* out,
+                             cudaStream_t s);
+int try_interaction_bwd_warp(const float* dOut, const float* T, int B, int F, int d, int width,
+                             float* dT, float* dx, const void* dests, long long sample_offset,
+                             cudaStream_t s);
+
 int launch_interaction_fwd(float* T, const float* x, int B, int F, int d, int pad_to_mul,
                            float* out, int sm_count, cudaStream_t s) {
     const int width = interaction_width(F, d, pad_to_mul);
     const bool aligned = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(T) & 15) == 0) &&
                          (x == nullptr || (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (aligned) {
+        int rc = try_interaction_fwd_warp(T, x, B, F, d, width, out, s);
+        if (rc >= 0) return rc;
+    }
     if (!aligned || F < 2) {
         int64_t total = (int64_t)B * width;
         int64_t blocks = ceil_div64(total, 256);
@@ -497,6 +508,10 @@ int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, i
         interaction_bwd_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(dOut, T, B, F, d, width, dT, dx);
         DLRMB_LAUNCH_CHECK();
         return DLRMB_OK;
+    }
+    {
+        int rc = try_interaction_bwd_warp(dOut, T, B, F, d, width, dT, dx, dests, sample_offset, s);
+        if (rc >= 0) return rc;
     }
     const int d4 = d / 4;
     const int Fp = (F + 3) & ~3;

@@ -1,0 +1,381 @@
+// Dot-product feature interaction for the DLRM shapes: one WARP per sample, packed FP32 FMAs.
+//
+// Same contract as interact.cu (DLRM.jl src/model/interact.jl:394-411 forward, :424-436 and
+// :469-489 backward), specialised at compile time for the (F, d) pairs the Criteo models use so
+// every loop bound and shared-memory offset is an immediate.  What the tiled kernels of interact.cu
+// lose at DLRM batch sizes -- CTA-wide barriers between load / compute / store phases, a shared-
+// memory pipe saturated by 3x3 register blocks, and an issue stream that is half address
+// arithmetic -- is what this design removes:
+//
+//   * a warp owns its samples from first load to last store; there is no __syncthreads and a CTA is
+//     only a container of independent warps, so the warps of an SM drift into different phases and
+//     the DRAM stream, the FMA pipe and the store stream overlap;
+//   * all FMAs are FFMA2 (PTX fma.rn.f32x2, sm_100+): two IEEE fp32 FMAs per issue slot, operands
+//     taken as the natural 64-bit halves of 128-bit loads;
+//   * backward: a lane keeps its float4 column slice of ALL F rows of T in registers (F LDG.128 in
+//     flight per lane, no shared-memory staging of T at all); S is expanded once per sample into
+//     shared memory with every entry duplicated, so one broadcast LDS.128 feeds four FFMA2.  The
+//     per-output summation order (j ascending, one fused multiply-add per term) is the tiled
+//     kernel's, so both produce the same bits;
+//   * forward: T rows arrive by TMA bulk copies (cp.async.bulk, one per row, one mbarrier per
+//     warp) at bank-staggered row addresses; a lane owns a 4 x 4 block of the Gram lower triangle
+//     (28 blocks for F = 27: one warp), 8 LDS.128 per 32 FFMA2, even and odd k accumulated in the
+//     two halves of a register pair; the sample's output row is assembled in the dead part of the
+//     tile and leaves as one contiguous coalesced range.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace dlrmb {
+
+namespace {
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// d = a * b + c on both halves (two independent round-to-nearest fp32 FMAs; SASS FFMA2)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+struct SlotDestW {   // same layout as SlotDest in interact.cu / dlrmb_slot_dest
+    float* base;
+    long long sample_stride;
+    long long offset;
+};
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+template <int F, int D>
+struct BwdGeom {
+    static constexpr int LPS = D / 4;            // lanes per sample (one float4 of k each)
+    static constexpr int SPW = 32 / LPS;         // samples per warp
+    static constexpr int FP2 = (F + 1) & ~1;     // S row length, even
+    static constexpr int NPAIR = F * (F - 1) / 2;
+    static constexpr int SSTRIDE = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
+    static constexpr int NF = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);   // output rows per pass
+    static constexpr int WARPS = 2;
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4 + (size_t)NPAIR * 2 + 16; }
+};
+
+template <int F, int D, bool SCATTER>
+__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32)
+interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
+                            float* __restrict__ dT, float* __restrict__ dx,
+                            const SlotDestW* __restrict__ dests, long long sample_offset) {
+    using G = BwdGeom<F, D>;
+    extern __shared__ float4 smem4[];
+    float* Sd = reinterpret_cast<float*>(smem4);                                   // [WARPS][SPW][SSTRIDE]
+    unsigned char* pr = reinterpret_cast<unsigned char*>(Sd + G::WARPS * G::SPW * G::SSTRIDE);   // [NPAIR][2]
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int group = blockIdx.x * G::WARPS + warp;          // SPW consecutive samples
+    const int sub = lane / G::LPS;
+    const int kl = lane - sub * G::LPS;
+    const long long b = (long long)group * G::SPW + sub;
+    const bool valid = b < B;
+
+    // T column slices: F independent 16-byte loads per lane, issued before anything else
+    float4 t[F];
+    {
+        const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)(valid ? b : 0) * F * G::LPS + kl;
+#pragma unroll
+        for (int j = 0; j < F; ++j) t[j] = valid ? __ldg(Tp + (size_t)j * G::LPS) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // pair table m -> (hi, lo), once per CTA
+    for (int m = threadIdx.x; m < G::NPAIR; m += G::WARPS * 32) {
+        int j = (int)((sqrtf(8.f * m + 1.f) + 1.f) * 0.5f);
+        while (j * (j - 1) / 2 > m) --j;
+        while ((j + 1) * j / 2 <= m) ++j;
+        pr[2 * m] = (unsigned char)j;
+        pr[2 * m + 1] = (unsigned char)(m - j * (j - 1) / 2);
+    }
+    __syncthreads();
+
+    // duplicated S of the warp's samples: Sd[s][f][j] = (S[j][f], S[j][f]), zero diagonal / padding
+    float* Sw = Sd + (size_t)warp * G::SPW * G::SSTRIDE;
+#pragma unroll 1
+    for (int s2 = 0; s2 < G::SPW; ++s2) {
+        const long long bb = (long long)group * G::SPW + s2;
+        if (bb >= B) break;                                  // warp-uniform
+        const float* gp = dOut + (size_t)bb * width + D;
+        float2* Sb = reinterpret_cast<float2*>(Sw + (size_t)s2 * G::SSTRIDE);
+        for (int m = lane; m < G::NPAIR; m += 32) {
+            const float v = __ldg(gp + m);
+            const int hi = pr[2 * m], lo = pr[2 * m + 1];
+            Sb[hi * G::FP2 + lo] = make_float2(v, v);
+            Sb[lo * G::FP2 + hi] = make_float2(v, v);
+        }
+        for (int f = lane; f < F; f += 32) {
+            Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
+            if (G::FP2 > F) Sb[f * G::FP2 + F] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncwarp();
+    if (!valid) return;
+
+    const float* Srow = Sw + (size_t)sub * G::SSTRIDE;
+    const float* gb = dOut + (size_t)b * width;
+#pragma unroll 1
+    for (int f0 = 0; f0 < F; f0 += G::NF) {
+        float2 lo2[G::NF], hi2[G::NF];
+#pragma unroll
+        for (int q = 0; q < G::NF; ++q) lo2[q] = hi2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int jp = 0; jp < G::FP2 / 2; ++jp) {
+#pragma unroll
+            for (int q = 0; q < G::NF; ++q) {
+                const float4 sv = *reinterpret_cast<const float4*>(Srow + ((f0 + q) * G::FP2 + 2 * jp) * 2);
+                lo2[q] = ffma2(make_float2(sv.x, sv.y), make_float2(t[2 * jp].x, t[2 * jp].y), lo2[q]);
+                hi2[q] = ffma2(make_float2(sv.x, sv.y), make_float2(t[2 * jp].z, t[2 * jp].w), hi2[q]);
+                if (2 * jp + 1 < F) {
+                    lo2[q] = ffma2(make_float2(sv.z, sv.w), make_float2(t[2 * jp + 1].x, t[2 * jp + 1].y), lo2[q]);
+                    hi2[q] = ffma2(make_float2(sv.z, sv.w), make_float2(t[2 * jp + 1].z, t[2 * jp + 1].w), hi2[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < G::NF; ++q) {
+            const int f = f0 + q;
+            const float4 r = make_float4(lo2[q].x, lo2[q].y, hi2[q].x, hi2[q].y);
+            if (SCATTER) {
+                if (f >= 1) {
+                    const SlotDestW dd = dests[f];
+                    float* row = dd.base + (sample_offset + b) * dd.sample_stride + dd.offset;
+                    reinterpret_cast<float4*>(row)[kl] = r;
+                }
+            } else {
+                reinterpret_cast<float4*>(dT)[((size_t)b * F + f) * G::LPS + kl] = r;
+            }
+            if (f == 0) {
+                const float* g = gb + 4 * kl;    // row width is odd in general: 4-byte aligned only
+                reinterpret_cast<float4*>(dx)[(size_t)b * G::LPS + kl] =
+                    make_float4(__fadd_rn(__ldg(g), r.x), __fadd_rn(__ldg(g + 1), r.y),
+                                __fadd_rn(__ldg(g + 2), r.z), __fadd_rn(__ldg(g + 3), r.w));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int F, int D>
+struct FwdGeom {
+    static constexpr int D4 = D / 4;
+    static constexpr int LD4 = D4 + 1;                 // row pitch in float4 (16 bytes of padding)
+    static constexpr int NB = (F + 3) / 4;             // 4-row blocks
+    static constexpr int TPS = NB * (NB + 1) / 2;      // lower-triangle block pairs = lanes per sample
+    static constexpr int SPW = 32 / TPS;               // samples per warp
+    static constexpr int NPAIR = F * (F - 1) / 2;
+    // row f starts at float4 index f * LD4 + f / 4: rows 4*bi + r of different blocks (and rows
+    // 4*bj + c) then start in different 16-byte bank groups, so an operand load of a warp -- one
+    // 16-byte chunk per distinct row -- is served without bank conflicts
+    static __host__ __device__ constexpr int row_at(int f) { return f * LD4 + (f >> 2); }
+    static constexpr int SSZ = (row_at(F - 1) + LD4 + 3) & ~3;   // float4 per sample (64-byte multiple)
+    static constexpr int WARPS = 2;
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSZ * 16 + (size_t)WARPS * 8; }
+    static_assert(TPS <= 32, "one warp must cover a sample's block pairs");
+    static_assert(NPAIR <= (SSZ - LD4) * 4, "output staging must fit behind row 0");
+};
+
+template <int F, int D>
+__global__ void __launch_bounds__(FwdGeom<F, D>::WARPS * 32)
+interaction_fwd_warp_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int width,
+                            float* __restrict__ out) {
+    using G = FwdGeom<F, D>;
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float4* Ts = smem4 + (size_t)warp * G::SPW * G::SSZ;                              // [SPW][SSZ]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem4 + (size_t)G::WARPS * G::SPW * G::SSZ) + warp;
+
+    const long long s0 = ((long long)blockIdx.x * G::WARPS + warp) * G::SPW;          // first sample of the warp
+    if (s0 >= B) return;
+    const int ns = (int)((B - s0 < G::SPW) ? (B - s0) : G::SPW);
+
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                     ::"r"(smem_addr(bar)), "r"((unsigned)(ns * F * D * sizeof(float))) : "memory");
+    }
+    __syncwarp();
+    // one TMA bulk copy per feature row (slot 0 from x when it is handed separately)
+    for (int r = lane; r < ns * F; r += 32) {
+        const int s = r / F, f = r - s * F;
+        const float* src = (x != nullptr && f == 0) ? x + (size_t)(s0 + s) * D
+                                                    : T + ((size_t)(s0 + s) * F + f) * D;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(smem_addr(Ts + (size_t)s * G::SSZ + G::row_at(f))), "l"(src),
+                       "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar)) : "memory");
+    }
+
+    // lane -> (sample, block pair bi >= bj)
+    const int sub = lane / G::TPS;
+    const int q = lane - sub * G::TPS;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
+    const int bj = q - bi * (bi + 1) / 2;
+    const bool live = sub < ns;
+    const float4* Tb = Ts + (size_t)(live ? sub : 0) * G::SSZ;
+    int ra[4], rb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int fa = min(4 * bi + r, F - 1), fb = min(4 * bj + r, F - 1);   // clamped rows are discarded below
+        ra[r] = fa * G::LD4 + (fa >> 2);
+        rb[r] = fb * G::LD4 + (fb >> 2);
+    }
+
+    {   // wait for the tile
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done) : "r"(smem_addr(bar)), "r"(0) : "memory");
+        }
+    }
+
+    // fused fast_vcat: x also becomes slot 0 of T in global memory
+    if (x != nullptr) {
+        for (int i = lane; i < ns * G::D4; i += 32) {
+            const int s = i / G::D4, c = i - s * G::D4;
+            reinterpret_cast<float4*>(T + (size_t)(s0 + s) * F * D)[c] = Ts[(size_t)s * G::SSZ + c];
+        }
+    }
+
+    float2 acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    if (live) {
+#pragma unroll 4
+        for (int k = 0; k < G::D4; ++k) {
+            float4 a[4], bv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = Tb[ra[r] + k];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bv[c] = Tb[rb[c] + k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[r][c] = ffma2(make_float2(a[r].x, a[r].y), make_float2(bv[c].x, bv[c].y), acc[r][c]);
+                    acc[r][c] = ffma2(make_float2(a[r].z, a[r].w), make_float2(bv[c].z, bv[c].w), acc[r][c]);
+                }
+        }
+    }
+    __syncwarp();   // every lane is done reading rows >= 1: their space becomes the output staging
+
+    float* Os = reinterpret_cast<float*>(Ts);   // sample s: row 0 at [s*SSZ*4, +D), pairs at [s*SSZ*4 + 4*LD4, +NPAIR)
+    if (live) {
+        float* o = Os + (size_t)sub * G::SSZ * 4 + 4 * G::LD4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = 4 * bi + r, i = 4 * bj + c;
+                if (i < j && j < F) o[j * (j - 1) / 2 + i] = acc[r][c].x + acc[r][c].y;
+            }
+    }
+    __syncwarp();
+
+    // the warp's samples are one contiguous range of the output; each row leaves coalesced
+#pragma unroll 1
+    for (int s = 0; s < ns; ++s) {
+        const float* base = Os + (size_t)s * G::SSZ * 4;
+        float* og = out + (size_t)(s0 + s) * width;
+        for (int c = lane; c < D; c += 32) og[c] = base[c];
+        for (int c = lane; c < G::NPAIR; c += 32) og[D + c] = base[4 * G::LD4 + c];
+        for (int c = D + G::NPAIR + lane; c < width; c += 32) og[c] = 0.f;   // pad_to_mul padding
+    }
+}
+
+template <int F, int D>
+int launch_fwd_warp(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
+    using G = FwdGeom<F, D>;
+    static unsigned long long attr_done = 0;
+    const size_t smem = G::smem_bytes();
+    int rc = ensure_smem_attr((const void*)interaction_fwd_warp_kernel<F, D>, (int)smem, &attr_done);
+    if (rc) return rc;
+    const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
+    const long long grid = (groups + G::WARPS - 1) / G::WARPS;
+    interaction_fwd_warp_kernel<F, D><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(T, x, B, width, out);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+template <int F, int D>
+int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
+                    const void* dests, long long sample_offset, cudaStream_t s) {
+    using G = BwdGeom<F, D>;
+    static unsigned long long attr_done[2] = {0, 0};
+    const size_t smem = G::smem_bytes();
+    const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
+    const long long grid = (groups + G::WARPS - 1) / G::WARPS;
+    if (dests) {
+        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, true>, (int)smem, &attr_done[1]);
+        if (rc) return rc;
+        interaction_bwd_warp_kernel<F, D, true><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
+            dOut, T, B, width, dT, dx, static_cast<const SlotDestW*>(dests), sample_offset);
+    } else {
+        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, false>, (int)smem, &attr_done[0]);
+        if (rc) return rc;
+        interaction_bwd_warp_kernel<F, D, false><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
+            dOut, T, B, width, dT, dx, nullptr, 0);
+    }
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+bool warp_path_enabled() {
+    const char* e = getenv("DLRMB_INTERACT");   // "tiled" forces the general kernels of interact.cu (A/B runs, tests)
+    return !(e && strcmp(e, "tiled") == 0);
+}
+
+}  // namespace
+
+// Shapes with a compiled warp-per-sample specialisation: the Criteo models (26 tables + the dense
+// slot, d = 16..128) and the geometry of the reference's golden files (7 tables, d = 16).
+#define DLRMB_WARP_SHAPES(X) X(27, 128) X(27, 64) X(27, 32) X(27, 16) X(8, 16)
+
+bool interaction_has_warp_path(int F, int d) {
+#define X(FF, DD) if (F == FF && d == DD) return true;
+    DLRMB_WARP_SHAPES(X)
+#undef X
+    return false;
+}
+
+// Returns DLRMB_OK after launching, or -1 when there is no specialisation for (F, d) and the caller
+// must take the general path.
+int try_interaction_fwd_warp(float* T, const float* x, int B, int F, int d, int width, float* out,
+                             cudaStream_t s) {
+    if (!warp_path_enabled()) return -1;
+#define X(FF, DD) if (F == FF && d == DD) return launch_fwd_warp<FF, DD>(T, x, B, width, out, s);
+    DLRMB_WARP_SHAPES(X)
+#undef X
+    return -1;
+}
+
+int try_interaction_bwd_warp(const float* dOut, const float* T, int B, int F, int d, int width,
+                             float* dT, float* dx, const void* dests, long long sample_offset,
+                             cudaStream_t s) {
+    if (!warp_path_enabled()) return -1;
+#define X(FF, DD) \
+    if (F == FF && d == DD) return launch_bwd_warp<FF, DD>(dOut, T, B, width, dT, dx, dests, sample_offset, s);
+    DLRMB_WARP_SHAPES(X)
+#undef X
+    return -1;
+}
+
+}  // namespace dlrmb

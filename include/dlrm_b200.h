@@ -100,6 +100,11 @@ int32_t dlrmb_interaction_fwd(int32_t device, float* T, const float* x, int32_t 
 int32_t dlrmb_interaction_bwd(int32_t device, const float* dOut, const float* T, int32_t B,
                               int32_t F, int32_t d, int32_t pad_to_mul, float* dT, float* dx,
                               dlrmb_stream stream);
+/* 1 if (F, d) has a compiled warp-per-sample specialisation (the Criteo / golden geometries; every
+ * other shape runs the general tiled kernels), else 0.  Introspection for tests and benchmarks: the
+ * reference picks its interaction implementation per type the same way (src/model/interact.jl:390-411
+ * vs :503-513). */
+int32_t dlrmb_interaction_has_warp_path(int32_t F, int32_t d);
 
 /* ---- sparse SGD: lookup pullback -> SparseEmbeddingUpdate(delta = dT[:, slot0+k, :],
  * indices) (src/train/train.jl:144) followed by EmbeddingTables.update!(Flux.Descent(lr), ...)

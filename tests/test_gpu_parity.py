@@ -225,6 +225,61 @@ def test_interaction_host_entry_points():
     assert O.rel_err(dT, dT_ref) < FWD_RTOL and O.rel_err(dx, dx_ref) < FWD_RTOL
 
 
+WARP_SHAPES = [  # (B, F, d): every compiled warp-per-sample specialisation, ragged batches included
+    (2049, 27, 128), (1, 27, 128), (301, 27, 64), (37, 27, 32), (45, 27, 16), (131, 8, 16), (3, 8, 16),
+]
+
+
+@pytest.mark.parametrize("B,F,d", WARP_SHAPES)
+def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypatch):
+    """The FFMA2 warp-per-sample kernels (csrc/interact_warp.cu) against the oracle and against the
+    general tiled kernels (csrc/interact.cu) on the same inputs.  Backward keeps the tiled kernel's
+    summation order, so it must match bit for bit; forward sums even and odd k separately."""
+    from dlrm_jl_b200 import _lib
+    from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
+    assert _lib.load().dlrmb_interaction_has_warp_path(F, d) == 1
+    rng = np.random.default_rng(B + 31 * F + d)
+    T = rng.standard_normal((B, F, d)).astype(np.float32)
+    Td = torch.from_numpy(T).to(_dev())
+    res = {}
+    for path in ("tiled", "warp"):
+        if path == "tiled":
+            monkeypatch.setenv("DLRMB_INTERACT", "tiled")
+        else:
+            monkeypatch.delenv("DLRMB_INTERACT", raising=False)
+        outs = []
+        for pad in (1, 16):
+            w = interaction_width(F, d, pad)
+            out = interaction_fwd(Td, pad_to_mul=pad)
+            Tz = T.copy()
+            Tz[:, 0] = 0
+            Tzd = torch.from_numpy(Tz).to(_dev())
+            out_x = interaction_fwd(Tzd, torch.from_numpy(T[:, 0].copy()).to(_dev()), pad_to_mul=pad)
+            assert torch.equal(out, out_x) and torch.equal(Tzd, Td)
+            g = np.random.default_rng(pad).standard_normal((B, w)).astype(np.float32)
+            dx, dT = interaction_bwd(torch.from_numpy(g).to(_dev()), Td, pad)
+            outs.append((out.cpu().numpy(), dx.cpu().numpy(), dT.cpu().numpy(), g, w, pad))
+        res[path] = outs
+    for (o_t, dx_t, dT_t, g, w, pad), (o_w, dx_w, dT_w, _, _, _) in zip(res["tiled"], res["warp"]):
+        ref = O.interaction_fwd(T, pad)
+        assert ref.shape == o_w.shape and O.rel_err(o_w, ref) < FWD_RTOL
+        assert np.array_equal(o_w[:, :d], T[:, 0])
+        assert np.all(o_w[:, d + F * (F - 1) // 2:] == 0)
+        assert O.rel_err(o_w, o_t) < FWD_RTOL
+        dx_ref, dT_ref = O.interaction_bwd(g, T, w - d - F * (F - 1) // 2)
+        assert O.rel_err(dT_w, dT_ref) < FWD_RTOL and O.rel_err(dx_w, dx_ref) < FWD_RTOL
+        assert np.array_equal(dT_w, dT_t) and np.array_equal(dx_w, dx_t)
+
+
+def test_interaction_warp_path_coverage():
+    from dlrm_jl_b200 import _lib
+    lib = _lib.load()
+    for F, d in [(27, 128), (27, 64), (8, 16)]:
+        assert lib.dlrmb_interaction_has_warp_path(F, d) == 1
+    for F, d in [(11, 128), (21, 256), (6, 10), (100, 128)]:
+        assert lib.dlrmb_interaction_has_warp_path(F, d) == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # sort / dedup (bit-exact integers)
 # ------------------------------------------------------------------------------------------------

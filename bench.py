@@ -491,6 +491,18 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(f0.elapsed_time(f1))
 
+    # ---- per-launch device time of each kernel of this repo, launched back to back over the timed
+    # batches (one CUDA graph of nb launches per kernel, every launch on a different batch; the
+    # interaction inputs of the nb batches together exceed the L2).  This is the figure the roofline
+    # uses: an event-record node on either side of a kernel inside the step graph adds several
+    # microseconds of graph-dependency latency to a 10-20 us kernel.
+    replay = None
+    if world == 1:
+        try:
+            replay = kernel_replays(se, devb[W:W + K], wl, dev)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] kernel replays failed ({type(exc).__name__}: {exc})", file=sys.stderr)
+
     if world > 1:
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
@@ -509,7 +521,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        line.update(hot_path_report(wl, world, rank, se, prof, ms_step, devb[W:W + K]))
+        line.update(hot_path_report(wl, world, rank, se, prof, ms_step, replay))
         line["hot_path"]["kernel_timing"] = prof_mode
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_arm(wl, 20, 2, args.cpu_rows_cap, budget_s=20.0)
@@ -525,7 +537,51 @@ def run_ours(args):
         os._exit(0)
 
 
-def hot_path_report(wl, world, rank, se, prof, ms_step, batches):
+def kernel_replays(se, batches, wl, dev):
+    """name -> microseconds per launch, kernels launched back to back (dlrm_jl_b200._prof.time_launches)."""
+    import torch
+    from dlrm_jl_b200 import _lib, _prof
+    from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
+    t = se.tables
+    B, D, F = wl["B"], wl["D"], wl["F"]
+    nb = min(len(batches), 16)
+    idx = [b[2] for b in batches[:nb]]
+    w = interaction_width(F, D)
+    Ts, gs = [], []
+    for i in range(nb):
+        Ti = torch.empty((B, F, D), device=dev)
+        t.lookup(idx[i], Ti, 1)
+        Ti[:, 0] = torch.randn((B, D), device=dev)
+        Ts.append(Ti)
+        gs.append(torch.randn((B, w), device=dev) * 1e-3)
+    dT = torch.randn((B, F, D), device=dev) * 1e-3
+    out = {}
+    out["lookup"] = _prof.time_launches(lambda i: t.lookup(idx[i], Ts[i], 1), nb)
+    out["sort"] = _prof.time_launches(lambda i: t.sort(idx[i]), nb)
+
+    def sort_update(i):
+        t.sort(idx[i])
+        t.update_sorted(dT, 1, 1e-6)
+    out["update"] = max(_prof.time_launches(sort_update, nb) - out["sort"], 1e-3)
+    out["interaction_fwd"] = _prof.time_launches(lambda i: interaction_fwd(Ts[i]), nb)
+    out["interaction_bwd"] = _prof.time_launches(lambda i: interaction_bwd(gs[i], Ts[i]), nb)
+    z = torch.randn((B,), device=dev)
+    y = (torch.rand((B,), device=dev) < 0.25).float()
+    prob, dz, loss, scratch = torch.empty_like(z), torch.empty_like(z), torch.zeros(1, device=dev), torch.zeros(128, device=dev)
+    lib = _lib.load()
+    s_ptr = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    try:
+        out["bce"] = _prof.time_launches(lambda i: _lib.check(lib.dlrmb_bce_sigmoid_fwd_bwd(
+            dev.index or 0, z.data_ptr(), y.data_ptr(), B, prob.data_ptr(), dz.data_ptr(), loss.data_ptr(),
+            scratch.data_ptr(), s_ptr())), nb)
+    except Exception:  # noqa: BLE001 - signature drift must not cost the bench line
+        pass
+    out["_nb"] = nb
+    out["_interaction_inputs_mb"] = nb * B * F * D * 4 / 1e6
+    return out
+
+
+def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     """Per-kernel device time (CUDA events recorded inside the timed region) and the roofline of the
     dominant kernel of this repo.  Algorithmic bytes per SURVEY.md section 8(d), rank 0's share."""
     peaks = {}
@@ -552,13 +608,16 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, batches):
     alg = {"lookup": lookup_bytes, "update": update_bytes, "interaction_fwd": ifwd_bytes, "interaction_bwd": ibwd_bytes}
     kernels = {}
     for name, st in prof.items():
-        k = {"launches": st["count"], "avg_us": 1e3 * st["avg_ms"]}
-        if name in alg and st["avg_ms"] > 0:
+        k = {"launches": st["count"], "in_step_us": 1e3 * st["avg_ms"]}
+        k["avg_us"] = float(replay[name]) if (replay and name in replay) else k["in_step_us"]
+        k["avg_us_method"] = "back-to-back launches over the timed batches" if (replay and name in replay) else "in-step event pair"
+        if name in alg and k["avg_us"] > 0:
             k["algorithmic_bytes"] = int(alg[name])
-            k["gbs"] = alg[name] / (st["avg_ms"] * 1e-3) / 1e9
+            k["gbs"] = alg[name] / (k["avg_us"] * 1e-6) / 1e9
             k["frac_hbm"] = k["gbs"] / hbm_peak
         kernels[name] = k
-    own_ms = sum(st["avg_ms"] for st in prof.values())
+    own_ms = sum(k["avg_us"] for k in kernels.values()) * 1e-3
+    prof = {n: {"avg_ms": kernels[n]["avg_us"] * 1e-3} for n in kernels}
     cand = [n for n in ("update", "lookup", "interaction_fwd", "interaction_bwd") if n in kernels]
     dom = max(cand, key=lambda n: prof[n]["avg_ms"]) if cand else None
     out = {"kernels": kernels,
@@ -584,7 +643,8 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, batches):
                            "unit": "GB/s", "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": traffic,
                            "traffic_source": traffic_src,
                            "peak_source": peak_src,
-                           "note": "achieved = algorithmic bytes per launch / CUDA-event duration inside the timed region"}
+                           "note": ("achieved = algorithmic bytes per launch / per-launch device time (CUDA events; "
+                                    + kernels[dom]["avg_us_method"] + ")")}
     return out
 
 

@@ -56,6 +56,48 @@ static void run(const char* name, int sms, int ctas_per_sm) {
     cudaFree(out);
 }
 
+// legacy warp-level tensor-core MMA (mma.sync.m16n8k8 TF32), TILES independent accumulator tiles per warp
+template <int TILES>
+__global__ void __launch_bounds__(256) mma_rate_kernel(float* out, int iters, unsigned a0, unsigned b0) {
+    float c[TILES][4];
+#pragma unroll
+    for (int i = 0; i < TILES; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+    unsigned a[4] = {a0, a0 + 8192u, a0 + 16384u, a0 + 24576u};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < TILES; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b0 + 8192u));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < TILES; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int TILES>
+static void run_mma(int sms, int ctas_per_sm) {
+    const int iters = 4096;
+    const int grid = sms * ctas_per_sm;
+    float* out;
+    cudaMalloc(&out, (size_t)grid * 256 * sizeof(float));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    mma_rate_kernel<TILES><<<grid, 256>>>(out, iters, 0x3f800000u, 0x3f000000u);
+    cudaEventRecord(e0);
+    for (int r = 0; r < 5; ++r) mma_rate_kernel<TILES><<<grid, 256>>>(out, iters, 0x3f800000u, 0x3f000000u);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double mmas = 5.0 * grid * 8.0 * iters * TILES;
+    printf("{\"kernel\": \"mma.sync.m16n8k8.tf32\", \"tiles\": %d, \"warps_per_sm\": %d, \"tflops\": %.2f, \"mma_per_clk_per_sm\": %.3f}\n",
+           TILES, ctas_per_sm * 8, mmas * 2.0 * 16 * 8 * 8 / (ms * 1e-3) / 1e12, mmas / (ms * 1e-3) / sms / 1.965e9);
+    cudaFree(out);
+}
+
 int main() {
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
@@ -66,5 +108,8 @@ int main() {
     run<8, true>("ffma2", p.multiProcessorCount, 4);
     run<16, false>("ffma", p.multiProcessorCount, 1);
     run<16, true>("ffma2", p.multiProcessorCount, 1);
+    run_mma<6>(p.multiProcessorCount, 1);
+    run_mma<6>(p.multiProcessorCount, 2);
+    run_mma<6>(p.multiProcessorCount, 4);
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
 }

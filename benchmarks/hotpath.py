@@ -26,6 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+from dlrm_jl_b200 import _prof  # noqa: E402
 from dlrm_jl_b200.embedding import EmbeddingTables  # noqa: E402
 from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width  # noqa: E402
 from dlrm_jl_b200.model import KAGGLE_EMBEDDING_SIZES, TERABYTE_EMBEDDING_SIZES  # noqa: E402
@@ -64,39 +65,7 @@ def make_indices(rng, rows, B, P, alpha):
 
 def time_graph(fn, nb: int, use_graph: bool, iters: int) -> float:
     """fn(i) launches batch i.  Returns microseconds per launch."""
-    torch.cuda.synchronize()
-    if use_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            fn(0)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for i in range(nb):
-                fn(i)
-        for _ in range(3):
-            g.replay()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            g.replay()
-        b.record()
-        torch.cuda.synchronize()
-        return 1e3 * a.elapsed_time(b) / (iters * nb)
-    for i in range(min(nb, 2)):
-        fn(i)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
-        for i in range(nb):
-            fn(i)
-    b.record()
-    torch.cuda.synchronize()
-    return 1e3 * a.elapsed_time(b) / (iters * nb)
+    return _prof.time_launches(fn, nb, iters, use_graph)
 
 
 def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label="", only=None, dtype="f32"):
@@ -188,6 +157,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="table storage type")
     ap.add_argument("--only", default=None, help="time just this kernel (e.g. interaction_fwd)")
+    ap.add_argument("--no-interaction", action="store_true", help="embedding kernels only")
     ap.add_argument("--small-tables", action="store_true",
                     help="cap every table at 1000 rows (the interaction kernels do not depend on table size; keeps ncu replays cheap)")
     a = ap.parse_args()
@@ -215,7 +185,8 @@ def main():
             D = a.D
         if a.small_tables:
             rows = [min(r, 1000) for r in rows]
-        r = run_case(rows, D, a.B, a.P, a.zipf, a.nb, not a.no_graph, a.iters, label=a.workload or "custom", only=a.only, dtype=a.dtype)
+        r = run_case(rows, D, a.B, a.P, a.zipf, a.nb, not a.no_graph, a.iters, interaction=not a.no_interaction,
+                     label=a.workload or "custom", only=a.only, dtype=a.dtype)
         results.append(r)
         print(json.dumps(r), flush=True)
     if a.out:

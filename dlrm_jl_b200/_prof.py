@@ -17,8 +17,11 @@ from collections import defaultdict
 from contextlib import contextmanager
 from typing import Dict, List, Tuple
 
+import builtins
+
 import torch
 
+_builtin_range = builtins.range   # this module defines its own `range` (the profiling context manager)
 _enabled = False
 _external = False
 _events: Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = defaultdict(list)
@@ -59,3 +62,42 @@ def summary() -> Dict[str, Dict[str, float]]:
 def read_replay() -> Dict[str, List[float]]:
     """Graph mode: name -> milliseconds of every captured call, as stamped by the last replay."""
     return {name: [a.elapsed_time(b) for a, b in pairs] for name, pairs in _events.items()}
+
+
+def time_launches(fn, nb: int, iters: int = 10, use_graph: bool = True) -> float:
+    """Microseconds per launch of `fn(i)`, i = 0..nb-1 (each i a different input batch): the nb launches
+    are captured into one CUDA graph and the replays are timed with CUDA events, so the figure is
+    device time per launch with the launches back to back on one stream (no host gaps)."""
+    torch.cuda.synchronize()
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn(0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in _builtin_range(nb):
+                fn(i)
+        for _ in _builtin_range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in _builtin_range(iters):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return 1e3 * a.elapsed_time(b) / (iters * nb)
+    for i in _builtin_range(min(nb, 2)):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in _builtin_range(iters):
+        for i in _builtin_range(nb):
+            fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return 1e3 * a.elapsed_time(b) / (iters * nb)

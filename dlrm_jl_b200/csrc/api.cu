@@ -158,7 +158,8 @@ int32_t dlrmb_tables_create_ex(int32_t device, int32_t ntab, const int64_t* rows
                         sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)D));
     TRY_CUDA(cudaMalloc((void**)&t->tile_flags, (size_t)ntab * (size_t)t->partial_tiles_cap));
     TRY_CUDA(cudaMalloc((void**)&t->head_list, sizeof(uint32_t) * (size_t)ntab * (size_t)t->partial_tiles_cap));
-    TRY_CUDA(cudaMalloc((void**)&t->head_count, sizeof(uint32_t)));
+    TRY_CUDA(cudaMalloc((void**)&t->head_count, 4 * sizeof(uint32_t)));   // heads, CTAs done, tail CTAs done
+    TRY_CUDA(cudaMemset(t->head_count, 0, 4 * sizeof(uint32_t)));
     TRY_CUDA(cudaMalloc((void**)&t->d_seg, sizeof(int32_t) * ((size_t)max_lookups + 1)));
     TRY_CUDA(cudaMalloc((void**)&t->d_uniq, sizeof(int64_t) * (size_t)max_lookups));
     TRY_CUDA(cudaMalloc((void**)&t->d_nuniq, sizeof(int32_t)));

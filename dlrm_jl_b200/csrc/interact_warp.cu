@@ -53,37 +53,68 @@ struct SlotDestW {   // same layout as SlotDest in interact.cu / dlrmb_slot_dest
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
+// flat pair index m = hi(hi-1)/2 + lo  ->  (hi << 8) | lo, for hi < 32 (constant-initialised)
+struct PairTable {
+    unsigned short v[496];
+    constexpr PairTable() : v() {
+        int m = 0;
+        for (int hi = 1; hi < 32; ++hi)
+            for (int lo = 0; lo < hi; ++lo) v[m++] = (unsigned short)((hi << 8) | lo);
+    }
+};
+__device__ const PairTable kPairTable{};
+
 template <int F, int D>
 struct BwdGeom {
     static constexpr int LPS = D / 4;            // lanes per sample (one float4 of k each)
     static constexpr int SPW = 32 / LPS;         // samples per warp
     static constexpr int FP2 = (F + 1) & ~1;     // S row length, even
     static constexpr int NPAIR = F * (F - 1) / 2;
+    static constexpr int NI = (NPAIR + 31) / 32; // pair entries per lane
     static constexpr int SSTRIDE = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
     static constexpr int NF = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);   // output rows per pass
     static constexpr int WARPS = 2;
-    static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4 + (size_t)NPAIR * 2 + 16; }
+    // d = 128 (one sample per warp): 7 CTAs = 14 warps per SM make 2048 samples a single wave on 148
+    // SMs, which caps the kernel at 128 registers; the variants that would spill at that cap (several
+    // samples per warp, peer-store epilogue) need half the warps for the same batch and keep 6 CTAs
+    static constexpr int min_ctas(bool scatter) { return (SPW == 1 && !scatter) ? 7 : 6; }
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4; }
+    static_assert(F <= 32, "pair table covers F <= 32");
 };
 
 template <int F, int D, bool SCATTER>
-__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32)
+__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32, BwdGeom<F, D>::min_ctas(SCATTER))
 interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
                             float* __restrict__ dT, float* __restrict__ dx,
                             const SlotDestW* __restrict__ dests, long long sample_offset) {
     using G = BwdGeom<F, D>;
     extern __shared__ float4 smem4[];
     float* Sd = reinterpret_cast<float*>(smem4);                                   // [WARPS][SPW][SSTRIDE]
-    unsigned char* pr = reinterpret_cast<unsigned char*>(Sd + G::WARPS * G::SPW * G::SSTRIDE);   // [NPAIR][2]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int group = blockIdx.x * G::WARPS + warp;          // SPW consecutive samples
+    const long long group = (long long)blockIdx.x * G::WARPS + warp;     // SPW consecutive samples
+    if (group * G::SPW >= B) return;                                     // warp-uniform
     const int sub = lane / G::LPS;
     const int kl = lane - sub * G::LPS;
-    const long long b = (long long)group * G::SPW + sub;
+    const long long b = group * G::SPW + sub;
     const bool valid = b < B;
 
-    // T column slices: F independent 16-byte loads per lane, issued before anything else
+    // the lane's share of the pair table and of the first sample's pair gradients: issued first so
+    // that their latency hides behind the T loads
+    unsigned short pv[G::NI];
+    float gv[G::NI];
+    {
+        const float* gp = dOut + (size_t)(group * G::SPW) * width + D;
+#pragma unroll
+        for (int i = 0; i < G::NI; ++i) {
+            const int m = lane + 32 * i;
+            pv[i] = kPairTable.v[m < G::NPAIR ? m : 0];
+            gv[i] = (m < G::NPAIR) ? __ldg(gp + m) : 0.f;
+        }
+    }
+
+    // T column slices: F independent 16-byte loads per lane
     float4 t[F];
     {
         const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)(valid ? b : 0) * F * G::LPS + kl;
@@ -91,29 +122,28 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
         for (int j = 0; j < F; ++j) t[j] = valid ? __ldg(Tp + (size_t)j * G::LPS) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    // pair table m -> (hi, lo), once per CTA
-    for (int m = threadIdx.x; m < G::NPAIR; m += G::WARPS * 32) {
-        int j = (int)((sqrtf(8.f * m + 1.f) + 1.f) * 0.5f);
-        while (j * (j - 1) / 2 > m) --j;
-        while ((j + 1) * j / 2 <= m) ++j;
-        pr[2 * m] = (unsigned char)j;
-        pr[2 * m + 1] = (unsigned char)(m - j * (j - 1) / 2);
-    }
-    __syncthreads();
-
     // duplicated S of the warp's samples: Sd[s][f][j] = (S[j][f], S[j][f]), zero diagonal / padding
     float* Sw = Sd + (size_t)warp * G::SPW * G::SSTRIDE;
 #pragma unroll 1
     for (int s2 = 0; s2 < G::SPW; ++s2) {
-        const long long bb = (long long)group * G::SPW + s2;
+        const long long bb = group * G::SPW + s2;
         if (bb >= B) break;                                  // warp-uniform
-        const float* gp = dOut + (size_t)bb * width + D;
         float2* Sb = reinterpret_cast<float2*>(Sw + (size_t)s2 * G::SSTRIDE);
-        for (int m = lane; m < G::NPAIR; m += 32) {
-            const float v = __ldg(gp + m);
-            const int hi = pr[2 * m], lo = pr[2 * m + 1];
-            Sb[hi * G::FP2 + lo] = make_float2(v, v);
-            Sb[lo * G::FP2 + hi] = make_float2(v, v);
+        if (s2 > 0) {
+            const float* gp = dOut + (size_t)bb * width + D;
+#pragma unroll
+            for (int i = 0; i < G::NI; ++i) {
+                const int m = lane + 32 * i;
+                gv[i] = (m < G::NPAIR) ? __ldg(gp + m) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < G::NI; ++i) {
+            if (lane + 32 * i < G::NPAIR) {
+                const int hi = pv[i] >> 8, lo = pv[i] & 0xff;
+                Sb[hi * G::FP2 + lo] = make_float2(gv[i], gv[i]);
+                Sb[lo * G::FP2 + hi] = make_float2(gv[i], gv[i]);
+            }
         }
         for (int f = lane; f < F; f += 32) {
             Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
@@ -301,6 +331,155 @@ interaction_fwd_warp_kernel(float* __restrict__ T, const float* __restrict__ x, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// forward on the tensor cores: 3xTF32 (error-compensated) warp-level MMA
+// ------------------------------------------------------------------------------------------
+// The FFMA2 forward above is bound by the shared-memory -> register path: a 4 x 4 register block
+// reads 8 floats per 16 FMAs, and that path delivers 32 floats per clock per SM against 128 FMAs per
+// clock (ncu: 1,090 shared wavefronts per sample, 7 us of shared-memory pipe per SM at B = 2048,
+// above the 5 us the HBM traffic takes).  The k-reduction is what the tensor core does internally,
+// so here a warp computes its sample's Gram matrix with mma.sync.m16n8k8 TF32 MMAs: every operand
+// fragment of a k-step -- A and B are both rows of T -- comes from 2 * ceil(F / 8) conflict-free
+// 32-bit loads (128 wavefronts per sample), and fp32 accuracy is kept by splitting each operand into
+// a TF32 head and a TF32 tail and accumulating  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  in fp32 (the
+// dropped a_lo*b_lo term is 2^-22 relative).  Integer-valued inputs stay exact.
+template <int F, int D>
+struct MmaGeom {
+    static constexpr int LDF = D + 4;                  // row pitch in floats: (D + 4) / 4 is odd, so the 8 rows x 4 k of a
+                                                       // fragment load fall into 32 different banks
+    static constexpr int MT = (F + 15) / 16;           // 16-row tiles (M)
+    static constexpr int RBP = 2 * MT;                 // 8-row blocks loaded per k-step
+    static constexpr int NT = (F + 7) / 8;             // 8-column tiles (N)
+    static constexpr int NPAIR = F * (F - 1) / 2;
+    static constexpr int SSZ = F * LDF;                // floats per sample
+    static constexpr int WARPS = 2;
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * SSZ * 4 + (size_t)WARPS * 8; }
+    static_assert(F <= 32 && D % 8 == 0, "one warp covers F <= 32 rows; k-steps of 8");
+    static_assert(((D + 4) / 4) % 2 == 1, "row pitch must stagger the banks");
+    static_assert(NPAIR <= (F - 1) * LDF || F == 1, "output staging must fit behind row 0");
+};
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int F, int D>
+__global__ void __launch_bounds__(MmaGeom<F, D>::WARPS * 32)
+interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int width,
+                           float* __restrict__ out) {
+    using G = MmaGeom<F, D>;
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* Ts = reinterpret_cast<float*>(smem4) + (size_t)warp * G::SSZ;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<float*>(smem4) + (size_t)G::WARPS * G::SSZ) + warp;
+
+    const long long b = (long long)blockIdx.x * G::WARPS + warp;     // the warp's sample
+    if (b >= B) return;
+
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                     ::"r"(smem_addr(bar)), "r"((unsigned)(F * D * sizeof(float))) : "memory");
+    }
+    __syncwarp();
+    if (lane < F) {   // one TMA bulk copy per feature row (slot 0 from x when it is handed separately)
+        const float* src = (x != nullptr && lane == 0) ? x + (size_t)b * D : T + ((size_t)b * F + lane) * D;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(smem_addr(Ts + lane * G::LDF)), "l"(src), "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar))
+                     : "memory");
+    }
+
+    const int g = lane >> 2, t = lane & 3;
+    int roff[G::RBP];
+#pragma unroll
+    for (int rb = 0; rb < G::RBP; ++rb) roff[rb] = min(8 * rb + g, F - 1) * G::LDF + t;   // clamped rows are discarded below
+
+    float acc[G::MT][G::NT][4];
+#pragma unroll
+    for (int i = 0; i < G::MT; ++i)
+#pragma unroll
+        for (int j = 0; j < G::NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+    {   // wait for the tile
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done) : "r"(smem_addr(bar)), "r"(0) : "memory");
+        }
+    }
+    if (x != nullptr) {   // fused fast_vcat: x also becomes slot 0 of T in global memory
+        for (int c = lane; c < D / 4; c += 32)
+            reinterpret_cast<float4*>(T + (size_t)b * F * D)[c] = reinterpret_cast<const float4*>(Ts)[c];
+    }
+
+#pragma unroll 2
+    for (int k0 = 0; k0 < D; k0 += 8) {
+        unsigned hi[G::RBP][2], lo[G::RBP][2];
+#pragma unroll
+        for (int rb = 0; rb < G::RBP; ++rb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float v = Ts[roff[rb] + k0 + 4 * h];
+                const unsigned vh = __float_as_uint(v) & 0xffffe000u;                 // TF32 head (truncated)
+                hi[rb][h] = vh;
+                lo[rb][h] = __float_as_uint(v - __uint_as_float(vh)) & 0xffffe000u;   // TF32 tail of the exact remainder
+            }
+#pragma unroll
+        for (int i = 0; i < G::MT; ++i) {
+            const unsigned ah[4] = {hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1]};
+            const unsigned al[4] = {lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1]};
+#pragma unroll
+            for (int j = 0; j < G::NT; ++j) {
+                if (j > 2 * i + 1) continue;            // tile entirely above the diagonal
+                mma_tf32(acc[i][j], al, hi[j][0], hi[j][1]);
+                mma_tf32(acc[i][j], ah, lo[j][0], lo[j][1]);
+                mma_tf32(acc[i][j], ah, hi[j][0], hi[j][1]);
+            }
+        }
+    }
+    __syncwarp();   // every lane is done reading rows >= 1: their space becomes the output staging
+
+    float* Os = Ts + G::LDF;   // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
+#pragma unroll
+    for (int i = 0; i < G::MT; ++i)
+#pragma unroll
+        for (int j = 0; j < G::NT; ++j) {
+            if (j > 2 * i + 1) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = 16 * i + g + ((e & 2) ? 8 : 0);
+                const int col = 8 * j + 2 * t + (e & 1);
+                if (col < row && row < F) Os[row * (row - 1) / 2 + col] = acc[i][j][e];
+            }
+        }
+    __syncwarp();
+
+    float* og = out + (size_t)b * width;
+    for (int c = lane; c < D; c += 32) og[c] = Ts[c];
+    for (int c = lane; c < G::NPAIR; c += 32) og[D + c] = Os[c];
+    for (int c = D + G::NPAIR + lane; c < width; c += 32) og[c] = 0.f;   // pad_to_mul padding
+}
+
+template <int F, int D>
+int launch_fwd_mma(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
+    using G = MmaGeom<F, D>;
+    static unsigned long long attr_done = 0;
+    const size_t smem = G::smem_bytes();
+    int rc = ensure_smem_attr((const void*)interaction_fwd_mma_kernel<F, D>, (int)smem, &attr_done);
+    if (rc) return rc;
+    const long long grid = ((long long)B + G::WARPS - 1) / G::WARPS;
+    interaction_fwd_mma_kernel<F, D><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(T, x, B, width, out);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
 template <int F, int D>
 int launch_fwd_warp(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
     using G = FwdGeom<F, D>;
@@ -338,9 +517,15 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
     return DLRMB_OK;
 }
 
+// DLRMB_INTERACT = "tiled" forces the general kernels of interact.cu, "ffma2" the FFMA2 forward
+// instead of the tensor-core forward (A/B runs, tests); unset = the fastest measured path.
 bool warp_path_enabled() {
-    const char* e = getenv("DLRMB_INTERACT");   // "tiled" forces the general kernels of interact.cu (A/B runs, tests)
+    const char* e = getenv("DLRMB_INTERACT");
     return !(e && strcmp(e, "tiled") == 0);
+}
+bool fwd_use_mma() {
+    const char* e = getenv("DLRMB_INTERACT");
+    return !(e && strcmp(e, "ffma2") == 0);
 }
 
 }  // namespace
@@ -361,6 +546,11 @@ bool interaction_has_warp_path(int F, int d) {
 int try_interaction_fwd_warp(float* T, const float* x, int B, int F, int d, int width, float* out,
                              cudaStream_t s) {
     if (!warp_path_enabled()) return -1;
+    if (fwd_use_mma()) {
+#define X(FF, DD) if (F == FF && d == DD) return launch_fwd_mma<FF, DD>(T, x, B, width, out, s);
+        DLRMB_WARP_SHAPES(X)
+#undef X
+    }
 #define X(FF, DD) if (F == FF && d == DD) return launch_fwd_warp<FF, DD>(T, x, B, width, out, s);
     DLRMB_WARP_SHAPES(X)
 #undef X

@@ -19,16 +19,25 @@
 //            the run's first tile.
 //   level 3  only runs that cross CHUNK boundaries (hot rows: Zipf heads, tables with a handful of
 //            rows) touch global scratch: one "head" and one "carry" partial per chunk, plus a work
-//            list of head chunks; update_fixup_kernel gives every listed run a CTA whose lane
-//            groups add the carried partials in a fixed strided order and update the row once.
+//            list of head chunks; every listed run gets a CTA whose lane groups add the carried
+//            partials in a fixed strided order and update the row once.  For large batches that is
+//            a second launch (update_fixup_kernel).  At DLRM batch sizes, where a launch costs as
+//            much as the whole fix-up, the LAST CTAs of update_tiles_kernel to finish stay behind,
+//            wait for the grid's completion count and run level 3 themselves (TAIL = true): one
+//            launch per update, no memset (the last CTA out re-arms the counters).
 //
 // HBM traffic per entry: 8 B of (key, position), one D*4-byte gradient row read, and per distinct
 // row one D*4-byte read + one D*4-byte write.  The 4 keys / 4 positions of a batch are one 16-byte
 // load each, the next batch's are requested before the current batch's rows, and the rows of a
 // batch (gradient rows plus the table rows of the runs ending in it) are all in flight together.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dlrmb {
+
+// Batches of at most this many (table, lookup) entries run the fix-up in the tail of the tiles launch.
+constexpr int64_t kUpdateTailMaxEntries = 1 << 18;
 
 template <int VEC> struct UV;
 template <> struct UV<4> {
@@ -81,18 +90,105 @@ struct UpdateGeom {
     int64_t cap, pcap;   // stream stride per table; partial / flag stride per table (in chunks)
 };
 
+// Level 3: runs that cross chunk boundaries.  One CTA per listed head chunk: the end of the run is
+// found by probing the chunk flags THREADS at a time, lane group `sub` adds the carry partials of
+// chunks g+1+sub, g+1+sub+nsub, ... (ascending, four loads in flight), the groups' sums are then
+// added in group order on top of the head partial, and the row is updated once.  The order
+// depends only on the geometry, so the result is bit-reproducible (the work list's order is not,
+// but no arithmetic depends on it).  Scratch written by other CTAs of the same launch is read with
+// L1-bypassing loads.
 template <int VEC, int NCH, int THREADS, typename RowT>
+__device__ __forceinline__ void fixup_runs(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
+                                           float lr, const float* partial, const uint8_t* flags,
+                                           const uint32_t* head_list, uint32_t n_heads, uint32_t first,
+                                           uint32_t stride, const UpdateGeom& gm,
+                                           typename UV<VEC>::type* red, int* s_first) {
+    using V = typename UV<VEC>::type;
+    const int lpr = 1 << gm.lpr_log2;
+    const int tid = threadIdx.x;
+    const int sl = tid & (lpr - 1);
+    const int sub = tid >> gm.lpr_log2;
+    const int nsub = THREADS >> gm.lpr_log2;
+    const size_t D = (size_t)gm.C * VEC;
+    const int chunk_entries = gm.G * gm.tile;
+
+    for (uint32_t h = first; h < n_heads; h += stride) {
+        const int gid = (int)__ldcg(head_list + h);
+        const int k = gid / gm.chunks;
+        const int g = gid - k * gm.chunks;
+        const uint8_t* fk = flags + (size_t)k * gm.pcap;
+        const float* pk = partial + (size_t)k * gm.pcap * 2 * D;
+        // where the run ends: the first later chunk whose carried run stops inside it (the table's
+        // last chunk always stops it)
+        if (tid == 0) *s_first = 0x7fffffff;
+        __syncthreads();
+        for (int base = g + 1;; base += THREADS) {
+            const int u = base + tid;
+            const uint8_t f = (u < gm.chunks) ? __ldcg(fk + u) : (uint8_t)FLAG_CARRY_ENDS;
+            if (f & FLAG_CARRY_ENDS) atomicMin(s_first, u);
+            __syncthreads();
+            if (*s_first != 0x7fffffff) break;
+        }
+        const int u_last = *s_first;
+        V acc[NCH];
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) acc[m] = UV<VEC>::zero();
+        for (int u = g + 1 + sub; u <= u_last; u += 4 * nsub) {
+            V v[4][NCH];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int uu = u + q * nsub;
+                const V* src = reinterpret_cast<const V*>(pk + (size_t)uu * 2 * D);
+#pragma unroll
+                for (int m = 0; m < NCH; ++m)
+                    if (uu <= u_last && sl + m * lpr < gm.C) v[q][m] = __ldcg(src + sl + m * lpr);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int m = 0; m < NCH; ++m)
+                    if (u + q * nsub <= u_last && sl + m * lpr < gm.C) acc[m] = UV<VEC>::add(acc[m], v[q][m]);
+        }
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) red[(sub * NCH + m) * lpr + sl] = acc[m];
+        __syncthreads();
+        if (sub == 0) {
+            const int nact = min(nsub, u_last - g);
+            int last = (g + 1) * chunk_entries - 1;          // last entry of the head chunk
+            const uint32_t key = keys[(size_t)k * gm.cap + last];
+            float* tbase = desc[k].base;
+            const V* hp = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D);
+#pragma unroll
+            for (int m = 0; m < NCH; ++m) {
+                if (sl + m * lpr < gm.C) {
+                    V total = __ldcg(hp + sl + m * lpr);
+                    for (int j = 0; j < nact; ++j) total = UV<VEC>::add(total, red[(j * NCH + m) * lpr + sl]);
+                    RowV<VEC, RowT>::store(tbase, key, D, sl + m * lpr,
+                                           UV<VEC>::sgd(RowV<VEC, RowT>::load(tbase, key, D, sl + m * lpr), total, lr));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// head_count points at three counters: [0] listed head chunks, [1] CTAs done, [2] tail CTAs done.
+// TAIL: the last `tail_ctas` CTAs to finish wait for the rest of the grid and run level 3.
+template <int VEC, int NCH, int THREADS, typename RowT, bool TAIL>
 __global__ void __launch_bounds__(THREADS, (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1))
 update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
                     const uint32_t* __restrict__ pos, const float* __restrict__ dT, float lr,
                     float* __restrict__ partial, uint8_t* __restrict__ flags,
-                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm) {
+                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm,
+                    unsigned tail_ctas) {
     using V = typename UV<VEC>::type;
     constexpr int U = 4;
     __shared__ V s_carry[THREADS * NCH];   // per group: partial of the run carried in from the previous tile
     __shared__ V s_head[THREADS * NCH];    // per group: partial of the run that continues into the next tile
     __shared__ uint8_t s_flag[THREADS];
     __shared__ int s_cta_head;
+    __shared__ int s_first;
+    __shared__ unsigned s_ticket;
 
     const int lpr = 1 << gm.lpr_log2;
     const int G = THREADS >> gm.lpr_log2;
@@ -251,6 +347,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         for (int m = 0; m < NCH; ++m)
             if (chunk_ok[m]) reinterpret_cast<V*>(pcarry)[sl + m * lpr] = tot[m];
     }
+    if (TAIL) __threadfence();      // partials of this CTA are visible before its completion is counted
     __syncthreads();
     if (tid == 0) {
         if (s_cta_head) {
@@ -258,15 +355,48 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             head_list[atomicAdd(head_count, 1u)] = (uint32_t)(k * gm.chunks + cta);
         }
         flags[(size_t)k * gm.pcap + cta] = cta_flag;
+        if (TAIL) {
+            __threadfence();
+            s_ticket = atomicAdd(head_count + 1, 1u);
+        }
+    }
+    if (!TAIL) return;
+
+    // ---- level 3 inside this launch: the last `tail_ctas` CTAs to finish stay behind.  They hold at
+    // most tail_ctas of the machine's CTA slots (the launcher keeps that below half of them), so the
+    // CTAs still running or not yet scheduled always find a slot and the wait cannot deadlock.
+    __syncthreads();
+    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned ticket = s_ticket;
+    if (ticket + tail_ctas < total) return;
+    if (tid == 0) {
+        // bounded (about a second): a lost completion would otherwise hang the device; head_count[3]
+        // counts the give-ups so a debugging host can see them
+        unsigned spins = 0;
+        while (*reinterpret_cast<volatile uint32_t*>(head_count + 1) < total) {
+            __nanosleep(64);
+            if (++spins > (1u << 23)) {
+                atomicAdd(head_count + 3, 1u);
+                break;
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    const uint32_t n_heads = *reinterpret_cast<volatile uint32_t*>(head_count);
+    fixup_runs<VEC, NCH, THREADS, RowT>(desc, keys, lr, partial, flags, head_list, n_heads,
+                                        ticket - (total - tail_ctas), tail_ctas, gm, s_carry, &s_first);
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(head_count + 2, 1u) == tail_ctas - 1) {   // last one out re-arms the counters
+            head_count[0] = 0;
+            head_count[1] = 0;
+            head_count[2] = 0;
+        }
     }
 }
 
-// Level 3: runs that cross chunk boundaries.  One CTA per listed head chunk: the end of the run is
-// found by probing the chunk flags 256 at a time, lane group `sub` adds the carry partials of
-// chunks g+1+sub, g+1+sub+nsub, ... (ascending, four loads in flight), the groups' sums are then
-// added in group order on top of the head partial, and the row is updated once.  The order
-// depends only on the geometry, so the result is bit-reproducible (the work list's order is not,
-// but no arithmetic depends on it).
+
 template <int VEC, int NCH, typename RowT>
 __global__ void __launch_bounds__(256)
 update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys, float lr,
@@ -276,73 +406,8 @@ update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     using V = typename UV<VEC>::type;
     __shared__ V red[256 * NCH];
     __shared__ int s_first;
-    const int lpr = 1 << gm.lpr_log2;
-    const int tid = threadIdx.x;
-    const int sl = tid & (lpr - 1);
-    const int sub = tid >> gm.lpr_log2;
-    const int nsub = 256 >> gm.lpr_log2;
-    const size_t D = (size_t)gm.C * VEC;
-    const int chunk_entries = gm.G * gm.tile;
-    const uint32_t n_heads = *head_count;
-
-    for (uint32_t h = blockIdx.x; h < n_heads; h += gridDim.x) {
-        const int gid = (int)head_list[h];
-        const int k = gid / gm.chunks;
-        const int g = gid - k * gm.chunks;
-        const uint8_t* fk = flags + (size_t)k * gm.pcap;
-        const float* pk = partial + (size_t)k * gm.pcap * 2 * D;
-        // where the run ends: the first later chunk whose carried run stops inside it (the table's
-        // last chunk always stops it)
-        if (tid == 0) s_first = 0x7fffffff;
-        __syncthreads();
-        for (int base = g + 1;; base += 256) {
-            const int u = base + tid;
-            const uint8_t f = (u < gm.chunks) ? fk[u] : (uint8_t)FLAG_CARRY_ENDS;
-            if (f & FLAG_CARRY_ENDS) atomicMin(&s_first, u);
-            __syncthreads();
-            if (s_first != 0x7fffffff) break;
-        }
-        const int u_last = s_first;
-        V acc[NCH];
-#pragma unroll
-        for (int m = 0; m < NCH; ++m) acc[m] = UV<VEC>::zero();
-        for (int u = g + 1 + sub; u <= u_last; u += 4 * nsub) {
-            V v[4][NCH];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int uu = u + q * nsub;
-                const V* src = reinterpret_cast<const V*>(pk + (size_t)uu * 2 * D);
-#pragma unroll
-                for (int m = 0; m < NCH; ++m)
-                    if (uu <= u_last && sl + m * lpr < gm.C) v[q][m] = src[sl + m * lpr];
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int m = 0; m < NCH; ++m)
-                    if (u + q * nsub <= u_last && sl + m * lpr < gm.C) acc[m] = UV<VEC>::add(acc[m], v[q][m]);
-        }
-#pragma unroll
-        for (int m = 0; m < NCH; ++m) red[(sub * NCH + m) * lpr + sl] = acc[m];
-        __syncthreads();
-        if (sub == 0) {
-            const int nact = min(nsub, u_last - g);
-            int last = (g + 1) * chunk_entries - 1;          // last entry of the head chunk
-            const uint32_t key = keys[(size_t)k * gm.cap + last];
-            float* tbase = desc[k].base;
-            const V* hp = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D);
-#pragma unroll
-            for (int m = 0; m < NCH; ++m) {
-                if (sl + m * lpr < gm.C) {
-                    V total = hp[sl + m * lpr];
-                    for (int j = 0; j < nact; ++j) total = UV<VEC>::add(total, red[(j * NCH + m) * lpr + sl]);
-                    RowV<VEC, RowT>::store(tbase, key, D, sl + m * lpr,
-                                           UV<VEC>::sgd(RowV<VEC, RowT>::load(tbase, key, D, sl + m * lpr), total, lr));
-                }
-            }
-        }
-        __syncthreads();
-    }
+    fixup_runs<VEC, NCH, 256, RowT>(desc, keys, lr, partial, flags, head_list, *head_count, blockIdx.x,
+                                    gridDim.x, gm, red, &s_first);
 }
 
 static int lanes_per_row_log2(int C) {
@@ -351,12 +416,15 @@ static int lanes_per_row_log2(int C) {
     return l;
 }
 
-// Entries per lane-group tile: as small as 4 while the whole batch still fits one wave of the
-// machine (latency-bound regime of DLRM-sized batches), up to 32 for large batches.
-static int choose_update_tile(int64_t total_entries, int lpr, int sm_count) {
-    const int64_t capacity = (int64_t)sm_count * 2048 / lpr;
+// Entries per lane-group tile: the smallest of 4..32 with which the whole batch is ONE wave of
+// resident CTAs (`resident_threads` per SM follow from the kernel's launch bound).  At DLRM batch
+// sizes a second wave costs a full dependent key -> row -> store latency chain; measured on B200
+// (26 tables x 2048 lookups): D = 128 tile 4 / 8 / 16 -> 24.2 / 17.8 / 16.0 us, D = 64 -> 14.9 /
+// 11.3 / 12.2 us, i.e. the first tile that fits one wave wins.
+static int choose_update_tile(int64_t total_entries, int lpr, int sm_count, int resident_threads) {
+    const int64_t capacity = (int64_t)sm_count * resident_threads / lpr;
     int tile = 4;
-    while (tile < 32 && total_entries / tile > capacity) tile *= 2;
+    while (tile < 32 && total_entries > capacity * tile) tile *= 2;
     return tile;
 }
 
@@ -384,7 +452,12 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     constexpr int THREADS = (NCH > 4) ? 128 : 256;   // keeps the two partial arrays within 48 KB
     const int G = THREADS / lpr;
     gm.G = G;
-    gm.tile = choose_update_tile((int64_t)t->ntab * gm.L, lpr, t->sm_count);
+    gm.tile = choose_update_tile((int64_t)t->ntab * gm.L, lpr, t->sm_count,
+                                 THREADS * ((NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1)));
+    if (const char* e = getenv("DLRMB_UPDATE_TILE")) {   // tuning aid: 4, 8, 16 or 32 entries per lane group
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16 || v == 32) gm.tile = v;
+    }
     gm.tiles = (gm.L + gm.tile - 1) / gm.tile;
     gm.chunks = (gm.tiles + G - 1) / G;
     gm.slots = slots;
@@ -396,12 +469,24 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     DLRMB_REQUIRE((int64_t)t->ntab * gm.chunks < (1ll << 31), "batch too large for one update launch");
     const uint32_t* keys = t->keys[t->sorted_buf];
     const uint32_t* pos = t->pos[t->sorted_buf];
-    DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, sizeof(uint32_t), s));
     dim3 grid((unsigned)gm.chunks, (unsigned)t->ntab);
-    update_tiles_kernel<VEC, NCH, THREADS, RowT><<<grid, THREADS, 0, s>>>(t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags,
-                                                       t->head_list, t->head_count, gm);
-    DLRMB_LAUNCH_CHECK();
     const int64_t total_chunks = (int64_t)t->ntab * gm.chunks;
+    // DLRM-sized batches: level 3 runs in the tail of the same launch (see the header comment)
+    const bool tail = (int64_t)t->ntab * gm.L <= kUpdateTailMaxEntries && getenv("DLRMB_UPDATE_TWO_LAUNCHES") == nullptr;
+    if (tail) {
+        constexpr int ctas_per_sm = (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1);   // the kernel's launch bound
+        int64_t tail_ctas = (int64_t)t->sm_count * ctas_per_sm / 2;
+        if (tail_ctas > total_chunks) tail_ctas = total_chunks;
+        if (tail_ctas < 1) tail_ctas = 1;
+        update_tiles_kernel<VEC, NCH, THREADS, RowT, true><<<grid, THREADS, 0, s>>>(
+            t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm, (unsigned)tail_ctas);
+        DLRMB_LAUNCH_CHECK();
+        return DLRMB_OK;
+    }
+    DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, 3 * sizeof(uint32_t), s));
+    update_tiles_kernel<VEC, NCH, THREADS, RowT, false><<<grid, THREADS, 0, s>>>(
+        t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm, 0u);
+    DLRMB_LAUNCH_CHECK();
     unsigned fgrid = (unsigned)(total_chunks < (int64_t)t->sm_count * 8 ? total_chunks : (int64_t)t->sm_count * 8);
     update_fixup_kernel<VEC, NCH, RowT><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,
                                                         t->head_list, t->head_count, gm);

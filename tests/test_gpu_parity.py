@@ -232,9 +232,9 @@ WARP_SHAPES = [  # (B, F, d): every compiled warp-per-sample specialisation, rag
 
 @pytest.mark.parametrize("B,F,d", WARP_SHAPES)
 def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypatch):
-    """The FFMA2 warp-per-sample kernels (csrc/interact_warp.cu) against the oracle and against the
-    general tiled kernels (csrc/interact.cu) on the same inputs.  Backward keeps the tiled kernel's
-    summation order, so it must match bit for bit; forward sums even and odd k separately."""
+    """The warp-per-sample kernels (csrc/interact_warp.cu: tensor-core 3xTF32 forward, FFMA2 forward,
+    FFMA2 backward) against the oracle and against the general tiled kernels (csrc/interact.cu) on the
+    same inputs.  Backward keeps the tiled kernel's summation order, so it must match bit for bit."""
     from dlrm_jl_b200 import _lib
     from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
     assert _lib.load().dlrmb_interaction_has_warp_path(F, d) == 1
@@ -242,11 +242,11 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypat
     T = rng.standard_normal((B, F, d)).astype(np.float32)
     Td = torch.from_numpy(T).to(_dev())
     res = {}
-    for path in ("tiled", "warp"):
-        if path == "tiled":
-            monkeypatch.setenv("DLRMB_INTERACT", "tiled")
-        else:
+    for path in ("tiled", "ffma2", "warp"):
+        if path == "warp":      # default: tensor-core 3xTF32 forward, FFMA2 backward
             monkeypatch.delenv("DLRMB_INTERACT", raising=False)
+        else:
+            monkeypatch.setenv("DLRMB_INTERACT", path)
         outs = []
         for pad in (1, 16):
             w = interaction_width(F, d, pad)
@@ -260,8 +260,13 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypat
             dx, dT = interaction_bwd(torch.from_numpy(g).to(_dev()), Td, pad)
             outs.append((out.cpu().numpy(), dx.cpu().numpy(), dT.cpu().numpy(), g, w, pad))
         res[path] = outs
-    for (o_t, dx_t, dT_t, g, w, pad), (o_w, dx_w, dT_w, _, _, _) in zip(res["tiled"], res["warp"]):
+    for (o_t, dx_t, dT_t, g, w, pad), (o_f, _, _, _, _, _), (o_w, dx_w, dT_w, _, _, _) in zip(
+            res["tiled"], res["ffma2"], res["warp"]):
         ref = O.interaction_fwd(T, pad)
+        assert ref.shape == o_f.shape and O.rel_err(o_f, ref) < FWD_RTOL and np.array_equal(o_f[:, :d], T[:, 0])
+        # elementwise: the 3xTF32 tensor-core Gram stays within a few fp32 ulps of the dot products' scale
+        scale = np.sqrt(float(d)) * 4.0
+        assert np.max(np.abs(o_w - ref)) < 2e-6 * scale * max(1.0, float(np.max(np.abs(T))))
         assert ref.shape == o_w.shape and O.rel_err(o_w, ref) < FWD_RTOL
         assert np.array_equal(o_w[:, :d], T[:, 0])
         assert np.all(o_w[:, d + F * (F - 1) // 2:] == 0)
@@ -269,6 +274,42 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypat
         dx_ref, dT_ref = O.interaction_bwd(g, T, w - d - F * (F - 1) // 2)
         assert O.rel_err(dT_w, dT_ref) < FWD_RTOL and O.rel_err(dx_w, dx_ref) < FWD_RTOL
         assert np.array_equal(dT_w, dT_t) and np.array_equal(dx_w, dx_t)
+
+
+@pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (77, 27, 64), (33, 8, 16), (19, 11, 128)])
+def test_interaction_backward_scatter_matches_plain_backward(B, F, d, monkeypatch):
+    """dlrmb_interaction_bwd_scatter with every destination in local memory: the rows land at
+    base + (sample_offset + b) * stride + offset, bit-identical to the plain backward's dT rows
+    (slot 0 is not scattered), for the warp-per-sample and the tiled kernels."""
+    from dlrm_jl_b200.interact import DotInteraction, ScatterPlan, interaction_bwd, interaction_width
+    rng = np.random.default_rng(B + F)
+    T = torch.from_numpy(rng.standard_normal((B, F, d)).astype(np.float32)).to(_dev())
+    x = T[:, 0].clone().requires_grad_(True)
+    g = torch.from_numpy(rng.standard_normal((B, interaction_width(F, d))).astype(np.float32)).to(_dev())
+    sample_offset = 5
+    # two "owners": even tables in buffer A [B + 8][nA][d], odd tables in buffer B [B + 8][nB][d]
+    owners = [[f for f in range(1, F) if f % 2 == 0], [f for f in range(1, F) if f % 2 == 1]]
+    for path in ("tiled", None):
+        if path:
+            monkeypatch.setenv("DLRMB_INTERACT", path)
+        else:
+            monkeypatch.delenv("DLRMB_INTERACT", raising=False)
+        bufs = [torch.full((B + 8, max(1, len(o)), d), -7.0, device=_dev()) for o in owners]
+        dests = torch.zeros((F, 3), dtype=torch.int64)
+        for buf, own in zip(bufs, owners):
+            for j, f in enumerate(own):
+                dests[f, 0] = buf.data_ptr()
+                dests[f, 1] = buf.shape[1] * d
+                dests[f, 2] = j * d
+        plan = ScatterPlan(dests.to(_dev()), sample_offset)
+        x.grad = None
+        DotInteraction()(x, T.clone(), scatter=plan).backward(g)
+        dx_ref, dT_ref = interaction_bwd(g, T)
+        assert torch.equal(x.grad, dx_ref)
+        for buf, own in zip(bufs, owners):
+            for j, f in enumerate(own):
+                assert torch.equal(buf[sample_offset:sample_offset + B, j], dT_ref[:, f])
+            assert torch.all(buf[:sample_offset] == -7.0) and torch.all(buf[sample_offset + B:] == -7.0)
 
 
 def test_interaction_warp_path_coverage():
@@ -353,6 +394,29 @@ def test_sparse_sgd_is_deterministic_and_matches_ordered_sum():
         ref = tables[k].copy()
         O.sparse_sgd_update_fast(ref, idx[k], np.ascontiguousarray(dT[:, k]), 0.5)
         assert O.rel_err(a[k], ref) < SGD_RTOL
+
+
+@pytest.mark.parametrize("D", [4, 64, 128, 256, 512])
+def test_sparse_sgd_tail_fixup_equals_two_launch_fixup(D, monkeypatch):
+    """DLRM-sized batches finish the chunk-crossing runs in the tail of the tiles launch; large batches
+    (or DLRMB_UPDATE_TWO_LAUNCHES) use the separate fix-up kernel.  Same arithmetic order, same bits --
+    over several consecutive steps, so the in-kernel counters must re-arm correctly."""
+    rng = np.random.default_rng(D)
+    rows, B = [2, 3, 40, 50000, 1], 6000 + D
+    tables = _rand_tables(rng, rows, D)
+    idx = [np.minimum((rng.pareto(1.05, size=(B, 1)) * 1.0).astype(np.int64), r - 1) for r in rows]
+    dT = (rng.standard_normal((B, len(rows), D)) * 0.01).astype(np.float32)
+    monkeypatch.delenv("DLRMB_UPDATE_TWO_LAUNCHES", raising=False)
+    a = _run_update(tables, idx, dT, 0, 0.5, steps=4)
+    monkeypatch.setenv("DLRMB_UPDATE_TWO_LAUNCHES", "1")
+    b = _run_update(tables, idx, dT, 0, 0.5, steps=4)
+    ref = [tb.copy() for tb in tables]
+    for _ in range(4):
+        for k in range(len(rows)):
+            O.sparse_sgd_update_fast(ref[k], idx[k], np.ascontiguousarray(dT[:, k]), 0.5)
+    for k in range(len(rows)):
+        assert np.array_equal(a[k], b[k]), k
+        assert O.rel_err(a[k], ref[k]) < SGD_RTOL, k
 
 
 def test_sparse_sgd_radix_path_hot_rows():

@@ -316,23 +316,35 @@ def run_ours(args):
 
     flat = FlatGrads(params, world)
     mlp_stream = torch.cuda.Stream()
+    # Dense layers as the reference has them (OneDNN.Dense: GEMM + bias + relu in one primitive): library
+    # GEMMs, epilogue-fused activations, one launch of this repo's kernel per layer for relu mask +
+    # bias gradient, weight gradients written straight into the flat all-reduce bucket.
+    fused_mlp = not args.unfused_mlp
+    if fused_mlp:
+        from dlrm_jl_b200.dense import FusedMLP
+        nbp = len(list(bottom.parameters()))
+        bottom_f = FusedMLP(bottom, flat.views[:nbp])
+        top_f = FusedMLP(list(top)[:-1], flat.views[nbp:])
+    else:
+        bottom_f, top_f = bottom, top_logits
 
     def train_step(dense, labels, idx):
         main = torch.cuda.current_stream()
-        flat.zero()
+        if not fused_mlp:
+            flat.zero()        # autograd accumulates into the bucket; the fused layers overwrite it
         # bottom MLP on a second stream: it is independent of the embedding exchange until the
         # interaction, so its GEMMs hide the index / pooled-embedding all-to-alls (and, because
         # autograd replays backward ops on their forward stream, its backward hides the gradient
         # all-to-all and the sparse update)
         mlp_stream.wait_stream(main)
         with torch.cuda.stream(mlp_stream):
-            x = bottom(dense)
+            x = bottom_f(dense)
         fused = se.scatter_plan is not None
         T = se.lookup_fused(idx) if fused else se.lookup(idx, anchor)
         se.sort_async()
         main.wait_stream(mlp_stream)
         z = dot(x, T, scatter=se.scatter_plan) if fused else dot(x, T)
-        loss = sigmoid_bce(top_logits(z), labels)
+        loss = sigmoid_bce(top_f(z), labels)
         loss.backward()
         main.wait_stream(mlp_stream)
         if fused:
@@ -515,7 +527,9 @@ def run_ours(args):
             "metric": "dlrm_train_samples_per_sec", "value": Bg * K / (ms_total * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check),
+            "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check,
+                           mlp=("fused dense layers (library fp32 GEMMs, epilogue bias+relu, dlrmb_dense_bwd_act_bias)" if fused_mlp
+                                else "nn.Linear + ReLU autograd")),
             "e2e": {"value": Bg * K / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / K, "last_loss": last_loss},
             "gpu_launches": launches,
@@ -660,6 +674,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
+    ap.add_argument("--unfused-mlp", action="store_true",
+                    help="plain nn.Linear / ReLU autograd for the MLPs instead of dlrm_jl_b200.dense.FusedMLP")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:

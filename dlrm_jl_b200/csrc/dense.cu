@@ -1,0 +1,78 @@
+// Dense-layer backward glue: activation pullback fused with the bias gradient.
+//
+// The reference's MLP layers are OneDNN.Dense(Flux.Dense(in, out, relu)) (DLRM.jl
+// src/model/model.jl:72-93): one primitive computes relu(W x + b), and its pullback hands back
+// dW, db and dx.  The GEMMs stay library calls here (cuBLAS, fp32); what a framework adds around
+// them in the backward pass -- the relu mask (one elementwise launch), the bias gradient (a column
+// reduction of dY, ~13 us per layer as a generic reduce kernel) and the accumulation of both into
+// gradient buffers -- is one launch of this kernel per layer:
+//     dZ[b][n] = dY[b][n] * (Y[b][n] > 0)          (Y = the layer's output; no mask when Y is NULL)
+//     db[n]    = sum_b dZ[b][n]
+// dY is read once, dZ written once (in place when dZ == dY).  A CTA owns 32 columns x one block of
+// rows; its column sums go to scratch and the last CTA of a column block to finish (a counter, not
+// a floating-point atomic) adds the row blocks' partials in ascending order, so db is
+// bit-reproducible.
+#include "common.cuh"
+
+namespace dlrmb {
+
+constexpr int kDenseRowBlocks = 16;
+
+__global__ void __launch_bounds__(256)
+dense_bwd_act_bias_kernel(const float* __restrict__ dy, const float* __restrict__ y, int B, int N,
+                          float* __restrict__ dz, float* __restrict__ db, float* __restrict__ partial,
+                          unsigned int* __restrict__ counters, int rows_per_block) {
+    __shared__ float red[8][32];
+    __shared__ bool is_last;
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + c;
+    const int row0 = blockIdx.y * rows_per_block;
+    const int row1 = min(B, row0 + rows_per_block);
+    float acc = 0.f;
+    if (col < N) {
+        for (int b = row0 + r; b < row1; b += 8) {
+            const size_t i = (size_t)b * N + col;
+            float g = dy[i];
+            if (y != nullptr && !(y[i] > 0.f)) g = 0.f;
+            if (dz != dy || y != nullptr) dz[i] = g;
+            acc += g;
+        }
+    }
+    red[r][c] = acc;
+    __syncthreads();
+    if (r == 0) {
+        float s = red[0][c];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) s += red[q][c];
+        if (col < N) partial[(size_t)blockIdx.y * N + col] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        is_last = (atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    if (is_last && r == 0 && col < N) {
+        float s = 0.f;
+        for (unsigned q = 0; q < gridDim.y; ++q) s += __ldcg(partial + (size_t)q * N + col);   // fixed order
+        db[col] = s;
+    }
+    if (is_last && threadIdx.x == 0) counters[blockIdx.x] = 0;   // re-armed for the next call
+}
+
+int64_t dense_bwd_scratch_floats(int N) { return (int64_t)kDenseRowBlocks * N + (N + 31) / 32 + 32; }
+
+int launch_dense_bwd_act_bias(const float* dy, const float* y, int B, int N, float* dz, float* db,
+                              float* scratch, cudaStream_t s) {
+    int rb = kDenseRowBlocks;
+    while (rb > 1 && (B + rb - 1) / rb < 8) rb /= 2;
+    const int rows_per_block = (B + rb - 1) / rb;
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((B + rows_per_block - 1) / rows_per_block));
+    unsigned int* counters = reinterpret_cast<unsigned int*>(scratch + (size_t)kDenseRowBlocks * N);
+    dense_bwd_act_bias_kernel<<<grid, 256, 0, s>>>(dy, y, B, N, dz, db, scratch, counters, rows_per_block);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+}  // namespace dlrmb

@@ -22,7 +22,7 @@
 //            list of head chunks; every listed run gets a CTA whose lane groups add the carried
 //            partials in a fixed strided order and update the row once.  For large batches that is
 //            a second launch (update_fixup_kernel).  At DLRM batch sizes, where a launch costs as
-//            much as the whole fix-up, the LAST CTAs of update_tiles_kernel to finish stay behind,
+//            much as the whole fix-up, the highest-numbered CTAs of update_tiles_kernel stay behind,
 //            wait for the grid's completion count and run level 3 themselves (TAIL = true): one
 //            launch per update, no memset (the last CTA out re-arms the counters).
 //
@@ -173,7 +173,7 @@ __device__ __forceinline__ void fixup_runs(const TableDesc* __restrict__ desc, c
 }
 
 // head_count points at three counters: [0] listed head chunks, [1] CTAs done, [2] tail CTAs done.
-// TAIL: the last `tail_ctas` CTAs to finish wait for the rest of the grid and run level 3.
+// TAIL: the `tail_ctas` CTAs with the highest block ids wait for the rest of the grid and run level 3.
 template <int VEC, int NCH, int THREADS, typename RowT, bool TAIL>
 __global__ void __launch_bounds__(THREADS, (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1))
 update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
@@ -188,7 +188,6 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     __shared__ uint8_t s_flag[THREADS];
     __shared__ int s_cta_head;
     __shared__ int s_first;
-    __shared__ unsigned s_ticket;
 
     const int lpr = 1 << gm.lpr_log2;
     const int G = THREADS >> gm.lpr_log2;
@@ -305,6 +304,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     const int nact = min(G, gm.tiles - cta * G);     // active groups in this CTA
     float* pcarry = partial + (((size_t)k * gm.pcap + cta) * 2 + 0) * D;
     float* phead = partial + (((size_t)k * gm.pcap + cta) * 2 + 1) * D;
+    bool wrote_scratch = false;
     if (active && (fl & FLAG_HEAD)) {
         // this group's last run continues: add the carry partials of the following tiles up to
         // (and including) the first one in which the run ends
@@ -329,6 +329,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             for (int m = 0; m < NCH; ++m)
                 if (chunk_ok[m]) reinterpret_cast<V*>(phead)[sl + m * lpr] = tot[m];
             if (sl == 0) s_cta_head = 1;
+            wrote_scratch = true;
         }
     }
     uint8_t cta_flag = 0;
@@ -346,8 +347,9 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
 #pragma unroll
         for (int m = 0; m < NCH; ++m)
             if (chunk_ok[m]) reinterpret_cast<V*>(pcarry)[sl + m * lpr] = tot[m];
+        wrote_scratch = true;
     }
-    if (TAIL) __threadfence();      // partials of this CTA are visible before its completion is counted
+    if (TAIL && wrote_scratch) __threadfence();   // partials are visible before this CTA's completion is counted
     __syncthreads();
     if (tid == 0) {
         if (s_cta_head) {
@@ -357,18 +359,18 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         flags[(size_t)k * gm.pcap + cta] = cta_flag;
         if (TAIL) {
             __threadfence();
-            s_ticket = atomicAdd(head_count + 1, 1u);
+            atomicAdd(head_count + 1, 1u);   // result unused: a fire-and-forget reduction
         }
     }
     if (!TAIL) return;
 
-    // ---- level 3 inside this launch: the last `tail_ctas` CTAs to finish stay behind.  They hold at
-    // most tail_ctas of the machine's CTA slots (the launcher keeps that below half of them), so the
-    // CTAs still running or not yet scheduled always find a slot and the wait cannot deadlock.
-    __syncthreads();
+    // ---- level 3 inside this launch: the `tail_ctas` CTAs with the highest block ids stay behind
+    // until the completion count reaches the grid size.  They hold at most tail_ctas of the machine's
+    // CTA slots (the launcher keeps that below half of them), so the CTAs still running or not yet
+    // scheduled always find a slot and the wait cannot deadlock.
     const unsigned total = gridDim.x * gridDim.y;
-    const unsigned ticket = s_ticket;
-    if (ticket + tail_ctas < total) return;
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin + tail_ctas < total) return;
     if (tid == 0) {
         // bounded (about a second): a lost completion would otherwise hang the device; head_count[3]
         // counts the give-ups so a debugging host can see them
@@ -385,7 +387,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     __syncthreads();
     const uint32_t n_heads = *reinterpret_cast<volatile uint32_t*>(head_count);
     fixup_runs<VEC, NCH, THREADS, RowT>(desc, keys, lr, partial, flags, head_list, n_heads,
-                                        ticket - (total - tail_ctas), tail_ctas, gm, s_carry, &s_first);
+                                        lin - (total - tail_ctas), tail_ctas, gm, s_carry, &s_first);
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(head_count + 2, 1u) == tail_ctas - 1) {   // last one out re-arms the counters
@@ -395,7 +397,6 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         }
     }
 }
-
 
 template <int VEC, int NCH, typename RowT>
 __global__ void __launch_bounds__(256)

@@ -141,6 +141,16 @@ int32_t dlrmb_bce_sigmoid_fwd_bwd(int32_t device, const float* logits, const flo
                                   float* prob, float* dlogits, float* loss, float* scratch,
                                   dlrmb_stream stream);
 
+/* ---- dense-layer backward glue: the pullback of OneDNN.Dense(Flux.Dense(in, out, relu))
+ * (src/model/model.jl:72-93) minus its GEMMs: dZ = dY .* (Y > 0) (no mask when `y` is NULL) and the
+ * bias gradient db[n] = sum_b dZ[b][n], one launch.  dy, y, dz are [B][N] device arrays (dz may be
+ * dy), db is [N].  `scratch` is a caller-provided device buffer of at least
+ * dlrmb_dense_bwd_scratch_floats(N) floats, zero-initialised once and not shared between concurrent
+ * calls; the call leaves it ready for the next one. ---------------------------------------------- */
+int64_t dlrmb_dense_bwd_scratch_floats(int32_t N);
+int32_t dlrmb_dense_bwd_act_bias(int32_t device, const float* dy, const float* y, int32_t B, int32_t N,
+                                 float* dz, float* db, float* scratch, dlrmb_stream stream);
+
 /* ---- batch marshalling: `load!(labels, dense, sparse, records)` (src/data/criteo.jl:284-310) on
  * the device.  `records` is a DEVICE copy of B packed DACRecord structs (160 bytes each: Int32
  * label, 13 Float32, 26 UInt32; src/data/criteo.jl:91-95).  Outputs: labels [B] as Float32,

@@ -244,6 +244,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL's version
+    # banner, for one) is sent to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
@@ -541,6 +546,8 @@ def run_ours(args):
             r = cpu_arm(wl, 20, 2, args.cpu_rows_cap, budget_s=20.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     # Leave without tearing NCCL down: destroying a communicator that captured CUDA graphs still
     # reference can block for minutes.  Everything measured is already printed and flushed.

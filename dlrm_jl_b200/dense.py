@@ -109,6 +109,14 @@ class FusedMLP(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.layers(x)
 
+    def bind_param_grads(self) -> None:
+        """Point every parameter's ``.grad`` at its gradient buffer (call after backward when an
+        optimiser reads ``.grad``, as ``custom_update_`` does)."""
+        for m in self.layers:
+            if isinstance(m, FusedDense):
+                m.linear.weight.grad = m.grad_weight
+                m.linear.bias.grad = m.grad_bias
+
     def grad_buffers(self) -> List[torch.Tensor]:
         out = []
         for m in self.layers:

@@ -89,7 +89,7 @@ class DLRMModel:
 
 def dlrm(bottom_mlp_sizes: Sequence[int], top_mlp_sizes: Sequence[int], sparse_feature_size: int,
          embedding_sizes: Sequence[int], *, max_lookups: int, device=0, interaction=None,
-         seed: int = 51234, init_tables: bool = True) -> DLRMModel:
+         seed: int = 51234, init_tables: bool = True, fused_dense: bool = False) -> DLRMModel:
     """``dlrm(bottom, top, feature_size, embedding_sizes; ...)`` (src/model/model.jl:173-233)."""
     dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
     gen = torch.Generator().manual_seed(seed)  # Random.seed!(51234), :193
@@ -104,6 +104,9 @@ def dlrm(bottom_mlp_sizes: Sequence[int], top_mlp_sizes: Sequence[int], sparse_f
     top_in = up_to_mul_of((pre_triangle * pre_triangle - pre_triangle) // 2 + bottom_out, POST_INTERACTION_PAD_TO_MUL)
     sizes = [top_in, *top_mlp_sizes]
     top = create_mlp(sizes, len(sizes), dev, gen)  # sigmoid on the last layer, :230
+    if fused_dense:   # OneDNN.Dense-style fused layers (dlrm_jl_b200.dense), same parameters
+        from .dense import FusedMLP
+        bottom, top = FusedMLP(bottom), FusedMLP(top)
     return DLRMModel(bottom, tables, interaction or DotInteraction(), top)
 
 

@@ -119,6 +119,9 @@ def train_step(loss: LossWrapper, model: DLRMModel, opt: Descent, labels, dense,
         # the dedup sort needs the indices only: run it beside the backward pass
         model.embeddings.sort(T.indices, T.idx_base, side_stream=True)
     l.backward()
+    for mlp in (model.bottom_mlp, model.top_mlp):      # fused dense layers keep their gradients in buffers
+        if hasattr(mlp, "bind_param_grads"):
+            mlp.bind_param_grads()
     telemetry("grads_done")
     custom_update_(opt, model, T, telemetry, presorted=overlap_sort)
     telemetry("update_done")

@@ -513,10 +513,12 @@ def _torch_mlp(layers, sigmoid_last):
     return nn.Sequential(*mods)
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name", ["single", "multi"])
-def test_validate_golden_one_sgd_step(name):
+def test_validate_golden_one_sgd_step(name, fused):
     """src/validation.jl:1-44 + test/integration.jl: loss, then one step at lr = 10.0; every
-    embedding table and MLP parameter must match the PyTorch post-step values."""
+    embedding table and MLP parameter must match the PyTorch post-step values -- with the MLPs as
+    nn.Linear autograd and as fused dense layers (dlrm_jl_b200.dense)."""
     from dlrm_jl_b200.embedding import Descent
     from dlrm_jl_b200.interact import DotInteraction
     from dlrm_jl_b200.model import DLRMModel
@@ -525,7 +527,11 @@ def test_validate_golden_one_sgd_step(name):
     g = load_golden(name)
     bot, top, tables, dense, idx, labels = golden_model(g)
     t = _tables(tables, idx[0].size)
-    model = DLRMModel(_torch_mlp(bot, False), t, DotInteraction(), _torch_mlp(top, True))
+    mb, mt = _torch_mlp(bot, False), _torch_mlp(top, True)
+    if fused:
+        from dlrm_jl_b200.dense import FusedMLP
+        mb, mt = FusedMLP(mb), FusedMLP(mt)
+    model = DLRMModel(mb, t, DotInteraction(), mt)
     seen = []
     loss_fn = wrap_loss(bce_loss, cb=seen.append)
     dense_d = torch.from_numpy(dense).to(_dev())
@@ -541,8 +547,9 @@ def test_validate_golden_one_sgd_step(name):
         got = t.download(k)
         assert O.rel_err(got, uemb[k]) < SGD_RTOL, k
         assert not O.isapprox(tables[k], got), "update must differ from the original (validation.jl:142)"
-    for lin, (uW, ub) in zip([m for m in list(model.bottom_mlp) + list(model.top_mlp) if hasattr(m, "weight")],
-                             ubot + utop):
+    linears = [m for mlp in (model.bottom_mlp, model.top_mlp) for m in mlp.modules() if isinstance(m, torch.nn.Linear)]
+    assert len(linears) == len(ubot) + len(utop)
+    for lin, (uW, ub) in zip(linears, ubot + utop):
         assert O.rel_err(lin.weight.detach().cpu().numpy(), uW) < SGD_RTOL
         assert O.rel_err(lin.bias.detach().cpu().numpy(), ub) < SGD_RTOL
     for sym in ("start", "lookup", "bottom_mlp", "interaction", "top_mlp", "loss", "interaction_back",

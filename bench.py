@@ -321,6 +321,7 @@ def run_ours(args):
 
     flat = FlatGrads(params, world)
     mlp_stream = torch.cuda.Stream()
+    upd_stream = torch.cuda.Stream()
     # Dense layers as the reference has them (OneDNN.Dense: GEMM + bias + relu in one primitive): library
     # GEMMs, epilogue-fused activations, one launch of this repo's kernel per layer for relu mask +
     # bias gradient, weight gradients written straight into the flat all-reduce bucket.
@@ -354,10 +355,14 @@ def run_ours(args):
         main.wait_stream(mlp_stream)
         if fused:
             se.finish_backward()
+        # the sparse update touches the tables only: it runs beside the dense all-reduce + dense SGD
+        upd_stream.wait_stream(main)
+        with torch.cuda.stream(upd_stream):
+            se.update(LR * flat.scale, presorted=True)
         flat.allreduce()
         with torch.no_grad():
             torch._foreach_add_(params, flat.views, alpha=-LR * flat.scale)
-        se.update(LR * flat.scale, presorted=True)
+        main.wait_stream(upd_stream)
         return loss.detach()
 
     # synthetic batches: host-pinned copies (e2e) and device copies (value)

@@ -69,56 +69,107 @@ def synth_batch(wl, step: int, rank: int = 0, rows_cap: int | None = None):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions: an NVML polling thread (5 ms period;
+    `nvidia-smi -lms` as the fallback) whose samples are kept only if they fall inside a window
+    opened with `begin()` and closed with `end()`."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
+        self.samples = []      # (time, sm_mhz, max_mhz, reasons)
+        self.windows = []
+        self._open = None
+        self._stop = threading.Event()
+        self.thread = None
         self.proc = None
-        self.lines = []
+        self.source = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    phys = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(get_reasons(h))
+                        self.samples.append((time.perf_counter(), mhz, mx, {n for n, b in bits.items() if r & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "nvml, 5 ms period"
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.source = "nvidia-smi -lms 20"
         except Exception:
             self.proc = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                self.samples.append((time.perf_counter(), float(parts[0]), float(parts[1]),
+                                     {n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+
+    def begin(self):
+        self._open = time.perf_counter()
+
+    def end(self):
+        if self._open is not None:
+            self.windows.append((self._open, time.perf_counter()))
+            self._open = None
+
+    def stop(self):
+        if self.thread is None:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        time.sleep(0.03)
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+        used = inside or self.samples
+        if not used:
+            return None
+        reasons = set()
+        for s_ in used:
+            reasons |= s_[3]
+        return {"sm_mhz": float(np.median([s_[1] for s_ in used])), "sm_max_mhz": float(max(s_[2] for s_ in used)),
+                "reasons": sorted(reasons), "samples": len(used),
+                "window": "inside the timed regions (value + e2e)" if inside else "whole run (no sample fell inside the timed regions)",
+                "source": self.source}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -427,20 +478,22 @@ def run_ours(args):
         return s_loss
 
     # ---- value: inputs resident in HBM ----
-    for i in range(W):
-        run_step(*devb[i])
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        run_step(*devb[i])
+    barrier()
     n0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     for i in range(K):
         run_step(*devb[W + i])
     e1.record()
     barrier()
+    sampler.end()
     launches = launch_count() - n0
     if graph is not None:   # replays do not pass through the host-side counter: count per captured step
         n1 = launch_count()
@@ -448,7 +501,6 @@ def run_ours(args):
         torch.cuda.synchronize()
         launches = (launch_count() - n1) * K
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel device time of this repo's kernels over the same K batches.  Preferred: the
     # step captured a second time with an event-record node on either side of every library call
@@ -505,13 +557,16 @@ def run_ours(args):
         e2e_step(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     f0.record()
     last_loss = 0.0
     for i in range(K):
         last_loss = e2e_step(W + i)
     f1.record()
     barrier()
+    sampler.end()
     e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-launch device time of each kernel of this repo, launched back to back over the timed
     # batches (one CUDA graph of nb launches per kernel, every launch on a different batch; the

@@ -444,8 +444,11 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
 #pragma unroll
             for (int j = 0; j < G::NT; ++j) {
                 if (j > 2 * i + 1) continue;            // tile entirely above the diagonal
-                // small terms first.  (Issuing the three passes tile-interleaved, so that no MMA
-                // waits for its predecessor, measured slower: 14.3 vs 13.8 us at B = 2048.)
+                // small terms first.  (Measured and not taken: issuing the three passes tile-
+                // interleaved so that no MMA waits for its predecessor, 14.3 vs 13.8 us at B = 2048;
+                // delivering the tile as two column halves on two mbarriers so that the first half's
+                // MMAs overlap the second half's loads, 13.5 vs 13.9 us at B = 2048 but 63 vs 59.5 us
+                // at B = 16384.)
                 mma_tf32(acc[i][j], al, hi[j][0], hi[j][1]);
                 mma_tf32(acc[i][j], ah, lo[j][0], lo[j][1]);
                 mma_tf32(acc[i][j], ah, hi[j][0], hi[j][1]);

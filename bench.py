@@ -371,6 +371,7 @@ def run_ours(args):
     anchor = torch.zeros(1, device=dev, requires_grad=True)
 
     flat = FlatGrads(params, world)
+    pflat = flat.flatten_params()       # dense SGD = one axpy over the flat parameter buffer
     mlp_stream = torch.cuda.Stream()
     upd_stream = torch.cuda.Stream()
     # Dense layers as the reference has them (OneDNN.Dense: GEMM + bias + relu in one primitive): library
@@ -412,7 +413,7 @@ def run_ours(args):
             se.update(LR * flat.scale, presorted=True)
         flat.allreduce()
         with torch.no_grad():
-            torch._foreach_add_(params, flat.views, alpha=-LR * flat.scale)
+            pflat.add_(flat.flat, alpha=-LR * flat.scale)      # Flux.update!: x .-= eta * grad
         main.wait_stream(upd_stream)
         return loss.detach()
 

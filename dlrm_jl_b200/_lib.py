@@ -58,6 +58,7 @@ SIGNATURES = {
     "dlrmb_tables_set_slot_map": (_i32, [_vp, C.POINTER(_i32)]),
     "dlrmb_embedding_fwd_p2p": (_i32, [_vp, *_idx_args, C.POINTER(_vp), _i32, _i32, _i32, _vp]),
     "dlrmb_interaction_has_warp_path": (_i32, [_i32, _i32]),
+    "dlrmb_dense_fwd_bias_act": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "dlrmb_dense_bwd_scratch_floats": (_i64, [_i32]),
     "dlrmb_dense_bwd_act_bias": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dlrmb_interaction_bwd_scatter": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),

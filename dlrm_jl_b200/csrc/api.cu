@@ -322,6 +322,15 @@ int32_t dlrmb_interaction_bwd(int32_t device, const float* dOut, const float* T,
     return launch_interaction_bwd(dOut, T, B, F, d, pad_to_mul, dT, dx, device_sm_count(device), (cudaStream_t)stream);
 }
 
+int32_t dlrmb_dense_fwd_bias_act(int32_t device, float* z, const float* bias, int32_t B, int32_t N, int32_t relu,
+                                 dlrmb_stream stream) {
+    DLRMB_REQUIRE(B > 0 && N > 0, "B and N must be positive (got %d, %d)", B, N);
+    DLRMB_REQUIRE(z && bias, "null buffer");
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    return launch_dense_fwd_bias_act(z, bias, B, N, relu, device_sm_count(device), (cudaStream_t)stream);
+}
+
 int64_t dlrmb_dense_bwd_scratch_floats(int32_t N) { return dense_bwd_scratch_floats(N); }
 
 int32_t dlrmb_dense_bwd_act_bias(int32_t device, const float* dy, const float* y, int32_t B, int32_t N,

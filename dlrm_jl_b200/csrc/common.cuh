@@ -162,6 +162,7 @@ int launch_check_indices(dlrmb_tables* t, const void* d_idx, int idx_bytes, int 
                          long long* bad_val);
 int launch_bce_sigmoid(const float* z, const float* y, int B, float* prob, float* dz, float* loss,
                        float* scratch, cudaStream_t s);
+int launch_dense_fwd_bias_act(float* z, const float* bias, int B, int N, int relu, int sm_count, cudaStream_t s);
 int64_t dense_bwd_scratch_floats(int N);
 int launch_dense_bwd_act_bias(const float* dy, const float* y, int B, int N, float* dz, float* db,
                               float* scratch, cudaStream_t s);

@@ -4,7 +4,8 @@ type DLRM.jl's ``create_mlp`` stacks (src/model/model.jl:72-93).
 The GEMMs are library calls (torch / cuBLAS, fp32, TF32 off) exactly as the reference leaves them to
 oneDNN.  What is fused here is the glue a framework otherwise spends a dozen launches per layer on:
 
-* forward: bias add and relu ride in the GEMM epilogue (``torch._addmm_activation``);
+* forward: bias add and relu are one in-place pass over the GEMM output (``dlrmb_dense_fwd_bias_act``;
+  cuBLASLt's fp32 SIMT GEMMs run their own bias / relu epilogue as a separate, slower kernel);
 * backward: relu mask + bias gradient in ONE launch of this repo's ``dlrmb_dense_bwd_act_bias`` kernel
   (csrc/dense.cu), the weight gradient GEMM writes straight into the caller's gradient buffer (for the
   data-parallel step: a view of the flat all-reduce bucket), so there is no gradient accumulation
@@ -36,10 +37,9 @@ class _DenseFn(torch.autograd.Function):
         if not x.is_cuda:
             raise _lib.DLRMB200Error(_lib.EINVAL, "fused dense layers run on the GPU only (no CPU fallback)")
         x = x.contiguous()
-        if relu:
-            y = torch._addmm_activation(bias, x, weight.t())   # relu(x W^T + b), epilogue-fused
-        else:
-            y = torch.addmm(bias, x, weight.t())
+        y = torch.mm(x, weight.t())                            # plain library GEMM
+        _lib.check(_lib.load().dlrmb_dense_fwd_bias_act(       # + bias, relu: one in-place pass
+            y.device.index or 0, y.data_ptr(), bias.data_ptr(), y.shape[0], y.shape[1], 1 if relu else 0, _stream(y)))
         ctx.relu = relu
         ctx.gw, ctx.gb, ctx.scratch = gw, gb, scratch
         ctx.save_for_backward(x, weight, y if relu else None)

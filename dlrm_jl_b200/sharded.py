@@ -378,6 +378,20 @@ class FlatGrads:
             off += p.numel()
         self.scale = 1.0 / world
 
+    def flatten_params(self) -> torch.Tensor:
+        """Re-home the parameters as views of ONE flat buffer laid out like the gradient bucket, so
+        the dense SGD step is a single `pflat.add_(flat, alpha=-lr)` instead of a multi-tensor pass."""
+        pflat = torch.empty_like(self.flat)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                view = pflat[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                off += p.numel()
+        self.pflat = pflat
+        return pflat
+
     def zero(self) -> None:
         self.flat.zero_()
         for p, v in zip(self.params, self.views):

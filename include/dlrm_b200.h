@@ -147,6 +147,10 @@ int32_t dlrmb_bce_sigmoid_fwd_bwd(int32_t device, const float* logits, const flo
  * dy), db is [N].  `scratch` is a caller-provided device buffer of at least
  * dlrmb_dense_bwd_scratch_floats(N) floats, zero-initialised once and not shared between concurrent
  * calls; the call leaves it ready for the next one. ---------------------------------------------- */
+/* Forward epilogue of the same layer: z[b][n] = act(z[b][n] + bias[n]) in place on the GEMM output
+ * (act = relu when `relu` != 0, identity otherwise). */
+int32_t dlrmb_dense_fwd_bias_act(int32_t device, float* z, const float* bias, int32_t B, int32_t N, int32_t relu,
+                                 dlrmb_stream stream);
 int64_t dlrmb_dense_bwd_scratch_floats(int32_t N);
 int32_t dlrmb_dense_bwd_act_bias(int32_t device, const float* dy, const float* y, int32_t B, int32_t N,
                                  float* dz, float* db, float* scratch, dlrmb_stream stream);

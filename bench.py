@@ -546,28 +546,86 @@ def run_ours(args):
         prof = _prof.summary()
         prof_mode = "eager launches, one CUDA-event pair per library call"
 
-    # ---- e2e: host inputs in, loss out, every step ----
+    # ---- e2e: host inputs in, loss out, every step.  Graph mode runs it as a two-slot pipeline, the way
+    # a training loop with a prefetching loader does (DACLoader): the pinned-host ->
+    # device copy of step i+1's inputs is issued on a copy stream before step i is launched, and step
+    # i's loss is copied to pinned host memory behind the step and read while step i+1 runs.  Every
+    # step's inputs cross PCIe and every step's loss is read on the host inside the timed region.
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
     def e2e_step(i):
         a, b, c = host[i]
         l = run_step(a, b, c, non_blocking=True)
         loss_host.copy_(l.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host[0])
-    for i in range(min(W, 3)):
-        e2e_step(i)
+
+    def e2e_pipelined(first, count):
+        main = torch.cuda.current_stream()
+        for slot in (0, 1):                     # staging buffers are free at the start
+            stage_free[slot].record(main)
+        losses = []
+
+        def prefetch(i, slot):
+            copy_stream.wait_event(stage_free[slot])
+            with torch.cuda.stream(copy_stream):
+                for dst, src in zip(stage[slot], host[i]):
+                    dst.copy_(src, non_blocking=True)
+                stage_ready[slot].record(copy_stream)
+
+        prefetch(first, 0)
+        for j in range(count):
+            slot = j & 1
+            if j + 1 < count:
+                prefetch(first + j + 1, 1 - slot)
+            main.wait_event(stage_ready[slot])
+            s_dense.copy_(stage[slot][0], non_blocking=True)
+            s_labels.copy_(stage[slot][1], non_blocking=True)
+            s_idx.copy_(stage[slot][2], non_blocking=True)
+            stage_free[slot].record(main)
+            graph.replay()
+            loss_pinned[slot].copy_(s_loss.reshape(1), non_blocking=True)
+            loss_done[slot].record(main)
+            if j >= 1:                          # read the previous step's loss while this one runs
+                loss_done[1 - slot].synchronize()
+                losses.append(float(loss_pinned[1 - slot][0]))
+        last = (count - 1) & 1
+        loss_done[last].synchronize()
+        losses.append(float(loss_pinned[last][0]))
+        return losses
+
+    pipelined = graph is not None and not args.e2e_sync
+    if pipelined:
+        copy_stream = torch.cuda.Stream()
+        stage = [tuple(torch.empty_like(t) for t in (s_dense, s_labels, s_idx)) for _ in range(2)]
+        stage_ready = [torch.cuda.Event() for _ in range(2)]
+        stage_free = [torch.cuda.Event() for _ in range(2)]
+        loss_pinned = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_done = [torch.cuda.Event() for _ in range(2)]
+        e2e_pipelined(0, min(W, 3))
+    else:
+        for i in range(min(W, 3)):
+            e2e_step(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.begin()
     f0.record()
     last_loss = 0.0
-    for i in range(K):
-        last_loss = e2e_step(W + i)
+    if pipelined:
+        e2e_losses = e2e_pipelined(W, K)
+        assert len(e2e_losses) == K
+        last_loss = e2e_losses[-1]
+    else:
+        for i in range(K):
+            last_loss = e2e_step(W + i)
     f1.record()
     barrier()
     sampler.end()
     e2e_ms = max_over_ranks(f0.elapsed_time(f1))
     clocks = sampler.stop() if rank == 0 else None
+    e2e_mode = ("two-slot pipeline: inputs of step i+1 copied (pinned host -> device) while step i runs, loss of step i "
+                "read on the host while step i+1 runs" if pipelined else
+                "synchronous: copy inputs, run the step, read the loss, every step")
 
     # ---- per-launch device time of each kernel of this repo, launched back to back over the timed
     # batches (one CUDA graph of nb launches per kernel, every launch on a different batch; the
@@ -597,7 +655,8 @@ def run_ours(args):
                            mlp=("fused dense layers (library fp32 GEMMs, epilogue bias+relu, dlrmb_dense_bwd_act_bias)" if fused_mlp
                                 else "nn.Linear + ReLU autograd")),
             "e2e": {"value": Bg * K / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / K, "last_loss": last_loss},
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / K, "last_loss": last_loss,
+                    "mode": e2e_mode},
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -742,6 +801,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
+    ap.add_argument("--e2e-sync", action="store_true",
+                    help="e2e leg without the input-prefetch / deferred-loss pipeline (copy, run, read, every step)")
     ap.add_argument("--unfused-mlp", action="store_true",
                     help="plain nn.Linear / ReLU autograd for the MLPs instead of dlrm_jl_b200.dense.FusedMLP")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")

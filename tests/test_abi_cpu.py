@@ -40,6 +40,26 @@ def test_binding_covers_header_exactly(built_lib):
     assert isinstance(lib.dlrmb_launch_count(), int)
 
 
+def test_julia_glue_and_integration_guide_only_name_exported_symbols(built_lib):
+    """julia/DLRMB200.jl (the ccall side a DLRM.jl maintainer loads) and INTEGRATION.md may only bind
+    symbols the header declares and the library exports; every pure query is callable without a GPU."""
+    declared = set(_declared_symbols())
+    lib = ctypes.CDLL(built_lib)
+    for rel in ("julia/DLRMB200.jl", "INTEGRATION.md"):
+        text = open(os.path.join(ROOT, rel)).read()
+        used = set(re.findall(r"\b(dlrmb_[a-z0-9_]+)\b", text))
+        # prose may abbreviate families: dlrmb_xbuf_*, dlrmb_embedding_fwd[_host], dlrmb_tables_create / _upload
+        used = {u for u in used if not u.endswith("_")}
+        unknown = sorted(u for u in used if u not in declared and not any(d.startswith(u) for d in declared))
+        assert not unknown, f"{rel} names symbols the header does not declare: {unknown}"
+    for n in re.findall(r"ccall\(\(:(dlrmb_[a-z0-9_]+),", open(os.path.join(ROOT, "julia/DLRMB200.jl")).read()):
+        assert hasattr(lib, n), n
+    from dlrm_jl_b200 import _lib
+    L = _lib.load()
+    assert L.dlrmb_interaction_has_warp_path(27, 128) == 1 and L.dlrmb_interaction_has_warp_path(5, 12) == 0
+    assert L.dlrmb_dense_bwd_scratch_floats(1024) >= 16 * 1024 + 32
+
+
 def test_argument_validation_needs_no_gpu(built_lib):
     from dlrm_jl_b200 import _lib
     lib = _lib.load()

@@ -2,7 +2,7 @@
 """bench.py -- DLRM training samples/s on synthetic Criteo-shaped data (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload terabyte|kaggle] [--batch B] [--no-cpu-baseline]
+                    [--workload terabyte|kaggle|sweep] [--batch B] [--no-cpu-baseline]
 
 A "step" is one DLRM training step on one batch: embedding lookup -> bottom MLP -> dot
 interaction -> top MLP -> BCE -> backward (interaction pullback) -> dense SGD -> sparse
@@ -17,6 +17,8 @@ data-parallel.  `--workload kaggle` = 26 Kaggle tables, D = 64, B = 2048 (BASELI
 
 `--impl reference`: the reference's CPU algorithm for the same step (C restatement of the
 Julia path for lookup / interaction / sparse SGD + torch-CPU (oneDNN) MLPs) on the host cores.
+`--workload sweep`: BASELINE config 5, the single-table embedding microbenchmark grid (rows 1e5-1e8,
+D 16-256, pooling 1-64, uniform / Zipf 1.05 / Zipf 1.2), gather + sort + update GB/s per case.
 """
 from __future__ import annotations
 
@@ -36,6 +38,9 @@ if ROOT not in sys.path:
 
 TERABYTE_CAP = 40_000_000
 LR = 0.1  # script.jl:14
+# arithmetic type of the path: fp32 everywhere; the interaction forward computes its Gram matrix on the
+# tensor cores in 3xTF32 form (error-compensated, measured 1.2e-6 relative against float64, tolerance 1e-5)
+DTYPE_LABEL = "f32 (3xTF32 interaction forward)"
 
 
 def workload(name: str, batch: int):
@@ -175,22 +180,57 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm on the host cores
 # ----------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Host cores this process may use.  Not omp_get_max_threads(): torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which would pin the CPU arm to one core.  DLRMB_CPU_THREADS overrides."""
+    env = os.environ.get("DLRMB_CPU_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def host_ram_bytes():
+    """(total, available) host memory in bytes (/proc/meminfo), (0, 0) if unknown."""
+    try:
+        info = {}
+        with open("/proc/meminfo") as fh:
+            for line in fh:
+                k, v = line.split(":")
+                info[k] = int(v.split()[0]) * 1024
+        return info.get("MemTotal", 0), info.get("MemAvailable", 0)
+    except Exception:
+        return 0, 0
+
+
+def auto_rows_cap(wl, budget_bytes: int) -> int:
+    """Largest per-table row cap (a power of two, or no cap) whose tables fit `budget_bytes`."""
+    full = sum(wl["rows"]) * wl["D"] * 4
+    if full <= budget_bytes:
+        return max(wl["rows"])
+    cap = 1 << 26
+    while cap > 1024 and sum(min(r, cap) for r in wl["rows"]) * wl["D"] * 4 > budget_bytes:
+        cap >>= 1
+    return cap
+
+
 def cpu_arm(wl, steps: int, warmup: int, rows_cap: int, budget_s: float = 25.0):
-    """Full training step on the CPU.  Bounded sample: tables capped at `rows_cap` rows each so
-    they fit host RAM; everything else (batch, D, MLP sizes, step structure) is the workload's."""
+    """Full training step on the CPU.  Bounded sample: tables capped at `rows_cap` rows each (0 = the
+    largest cap that fits 45 % of the available host RAM, at most 48 GiB of tables so the set-up stays
+    within a minute or two); everything else (batch, D, MLP sizes, step structure) is the workload's."""
     import torch
     from oracle import c_oracle as CO
-    threads = CO.max_threads()
+    threads = host_threads()
     torch.set_num_threads(threads)
+    ram_total, ram_avail = host_ram_bytes()
+    if rows_cap <= 0:
+        budget = min(int(0.45 * ram_avail) if ram_avail else (4 << 30), 48 << 30)
+        rows_cap = auto_rows_cap(wl, budget)
     rows = [min(r, rows_cap) for r in wl["rows"]]
     D, B, F = wl["D"], wl["B"], wl["F"]
-    rng = np.random.default_rng(1)
-    tables = []
-    for r in rows:
-        t = rng.random((r, D), dtype=np.float32)
-        t -= 0.5
-        t *= 2.0 / np.sqrt(r)
-        tables.append(t)
+    tables = [CO.init_uniform(r, D, 1 + k, threads) for k, r in enumerate(rows)]
 
     def mlp(sizes, sigmoid_last):
         mods = []
@@ -213,19 +253,19 @@ def cpu_arm(wl, steps: int, warmup: int, rows_cap: int, budget_s: float = 25.0):
         t0 = time.perf_counter()
         for p in params:
             p.grad = None
-        CO.lookup(tables, idx64, slot0=1, out=T)                       # maplookup (model.jl:161)
+        CO.lookup(tables, idx64, slot0=1, out=T, nthreads=threads)     # maplookup (model.jl:161)
         x = bottom(torch.from_numpy(dense))                            # bottom MLP (oneDNN)
         T[:, 0, :] = x.detach().numpy()                                # fast_vcat (interact.jl:271-281)
-        CO.interaction_fwd(T, out=z)                                   # DotInteraction (:394-411)
+        CO.interaction_fwd(T, out=z, nthreads=threads)                 # DotInteraction (:394-411)
         zt = torch.from_numpy(z).requires_grad_(True)
         out = top(zt).reshape(-1)
         loss = torch.nn.functional.binary_cross_entropy(out, torch.from_numpy(labels))
         loss.backward()
-        CO.interaction_bwd(zt.grad.numpy(), T, dT=dT, dx=dx)           # dot_back (:424-436)
+        CO.interaction_bwd(zt.grad.numpy(), T, dT=dT, dx=dx, nthreads=threads)   # dot_back (:424-436)
         x.backward(torch.from_numpy(dx))
         with torch.no_grad():
             torch._foreach_add_(params, [p.grad for p in params], alpha=-LR)
-        CO.sparse_sgd(tables, idx64, dT, 1, LR)                        # EmbeddingTables.update!
+        CO.sparse_sgd(tables, idx64, dT, 1, LR, nthreads=threads)      # EmbeddingTables.update!
         _ = float(loss.detach())
         return time.perf_counter() - t0
 
@@ -238,10 +278,13 @@ def cpu_arm(wl, steps: int, warmup: int, rows_cap: int, budget_s: float = 25.0):
         if time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
     total = float(sum(times))
+    capped = rows_cap < max(wl["rows"])
     return dict(value=B * len(times) / total, ms_per_step=1e3 * total / len(times), steps=len(times),
-                cores=threads,
-                sample=(f"{len(times)} full training steps, batch {B}, 26 tables, D {D}, rows capped at "
-                        f"{rows_cap} per table to fit host RAM ({sum(rows) * D * 4 / 2**30:.1f} GiB of tables); "
+                cores=threads, rows_cap=(rows_cap if capped else None), host_ram_gb=round(ram_total / 2**30, 1),
+                sample=(f"{len(times)} full training steps (after {warmup} warm-up), batch {B}, 26 tables, D {D}, "
+                        + (f"rows capped at {rows_cap} per table to fit host RAM" if capped else "full-size tables")
+                        + f" ({sum(rows) * D * 4 / 2**30:.1f} GiB of tables; host RAM {ram_total / 2**30:.0f} GiB, "
+                        f"{ram_avail / 2**30:.0f} GiB available); {threads} host threads; "
                         "C restatement of the Julia lookup/interaction/sparse-SGD path (OpenMP) + torch-CPU "
                         "(oneDNN) MLPs; batch generation excluded"))
 
@@ -250,13 +293,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "sweep":
+        print(json.dumps({"impl": "reference", "unavailable": "the sweep workload has no CPU arm (run terabyte / kaggle)"}), flush=True)
+        return
     wl = workload(args.workload, args.batch)
-    r = cpu_arm(wl, args.steps, min(args.warmup, 3), args.cpu_rows_cap, budget_s=90.0)
+    r = cpu_arm(wl, args.steps, args.warmup, args.cpu_rows_cap, budget_s=120.0)
     line = {
         "impl": "reference", "metric": "dlrm_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(wl, 1, note="CPU arm: one process on the host cores, no GPU"),
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL, "data": "synthetic",
+        "config": bench_config(wl, 1, note="CPU arm: one process on the host cores, no GPU",
+                               rows_cap=r["rows_cap"], host_ram_gb=r["host_ram_gb"]),
         "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -265,8 +312,9 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def bench_config(wl, world, note=""):
+def bench_config(wl, world, note="", rows_cap=None, host_ram_gb=None):
     return {
+        "rows_cap": rows_cap, "host_ram_gb": host_ram_gb,
         "workload": f"criteo_{wl['name']}_synthetic: 26 tables, D {wl['D']}, batch {wl['B']} per GPU, P 1, "
                     f"{sum(wl['rows']) * wl['D'] * 4 / 1e9:.1f} GB fp32 tables",
         "tables": len(wl["rows"]), "embedding_dim": wl["D"], "batch_per_gpu": wl["B"],
@@ -330,43 +378,26 @@ def run_ours(args):
         if args.exchange == "p2p":
             ok, why = 1.0, ""
             try:
-                # reference results through the NCCL path, then the fused paths on the same inputs
-                chk = torch.from_numpy(synth_batch(wl, 999, rank)[2]).to(dev)
-                gen_c = torch.Generator(device="cpu").manual_seed(7 + rank)
-                xc = torch.randn((B, D), generator=gen_c).to(dev).requires_grad_(True)
-                gz = torch.randn((B, D + F * (F - 1) // 2), generator=gen_c).to(dev)
-                probe = DotInteraction()
-                a0 = torch.zeros(1, device=dev, requires_grad=True)
-                t_nccl = se.lookup(chk, a0)
-                probe(xc, t_nccl).backward(gz)
-                t_ref, g_ref, dx_ref = t_nccl.detach().clone(), se.owned_grad.clone(), xc.grad.clone()
-                xc.grad = None
                 se.enable_peer_exchange(B)
                 se.enable_fused_backward(B)
-                t_p2p = se.lookup_fused(chk)
-                if not torch.equal(t_ref[:, 1:], t_p2p[:, 1:]):
-                    ok, why = 0.0, "fused forward exchange differs from the NCCL path"
-                probe(xc, t_p2p, scatter=se.scatter_plan).backward(gz)
-                se.finish_backward()
-                t_mine = len(se.local_ids)
-                if t_mine and not torch.equal(g_ref, se.owned_grad[:, :t_mine]):
-                    ok, why = 0.0, "fused backward exchange differs from the NCCL path"
-                if not torch.equal(dx_ref, xc.grad):
-                    ok, why = 0.0, "dx differs between the fused and the NCCL path"
-            except Exception as exc:  # noqa: BLE001
+            except Exception as exc:  # noqa: BLE001 - e.g. CUDA IPC not permitted in this container
                 ok, why = 0.0, f"{type(exc).__name__}: {exc}"
             flag = torch.tensor([ok], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank takes the same decision
             if float(flag.item()) == 1.0:
                 exchange = ("fused over NVLink peer stores: lookup -> peers' interaction inputs (forward), "
                             "interaction backward -> owners' gradient buffers (backward)")
-                exchange_check = "pooled rows, owner-side gradients and dx == NCCL all-to-all path, bit for bit, on every rank"
             else:
                 se.peer = None
                 se.scatter_plan = None
-                exchange_check = f"fell back to NCCL ({why or 'another rank failed'})"
-                if rank == 0:
-                    print(f"[bench] peer exchange disabled: {exchange_check}", file=sys.stderr)
+                exchange = f"nccl all-to-all (peer mapping unavailable: {why or 'on another rank'})"
+        # one sharded step on a batch whose ids fall in the first CHECK_ROWS rows of every table, compared
+        # with the UNSHARDED CPU oracle run on a downloaded copy of those rows
+        exchange_check = sharded_oracle_check(se, wl, dev, rank, world)
+        if rank == 0:
+            print(f"[bench] sharded step vs unsharded oracle: {exchange_check}", file=sys.stderr)
+        if not exchange_check["ok"]:
+            raise SystemExit(f"sharded path disagrees with the oracle: {exchange_check}")
     dot = DotInteraction()
     anchor = torch.zeros(1, device=dev, requires_grad=True)
 
@@ -650,7 +681,7 @@ def run_ours(args):
         line = {
             "metric": "dlrm_train_samples_per_sec", "value": Bg * K / (ms_total * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL, "data": "synthetic",
             "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check,
                            mlp=("fused dense layers (library fp32 GEMMs, epilogue bias+relu, dlrmb_dense_bwd_act_bias)" if fused_mlp
                                 else "nn.Linear + ReLU autograd")),
@@ -662,8 +693,13 @@ def run_ours(args):
         }
         line.update(hot_path_report(wl, world, rank, se, prof, ms_step, replay))
         line["hot_path"]["kernel_timing"] = prof_mode
+        if world == 1 and not args.no_host_leg:
+            try:
+                line["e2e_host"] = e2e_host_leg(se, wl, host[W:W + min(K, 10)], dev)
+            except Exception as exc:  # noqa: BLE001
+                line["e2e_host"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_arm(wl, 20, 2, args.cpu_rows_cap, budget_s=20.0)
+            r = cpu_arm(wl, 20, 3, args.cpu_rows_cap, budget_s=20.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         sys.stdout.flush()
@@ -678,8 +714,187 @@ def run_ours(args):
         os._exit(0)
 
 
+CHECK_ROWS = 64
+
+
+def sharded_oracle_check(se, wl, dev, rank, world):
+    """One sharded training step of the hot path on this run's GPUs -- index exchange, owner-side pooling
+    with the forward exchange, interaction forward / backward with the gradient exchange, owner-side sort
+    + sparse SGD -- against the unsharded CPU oracle (the checker; tolerances of tests/test_gpu_parity.py:
+    pooled rows bit-exact, interaction 1e-5, tables 1e-4).  Ids are drawn from the first CHECK_ROWS rows
+    of every table so that the oracle only needs a small downloaded sample of the 100 GB of tables."""
+    import torch
+    import torch.distributed as dist
+    from dlrm_jl_b200.interact import DotInteraction, interaction_width
+    from oracle import oracle as O
+    B, D, F = wl["B"], wl["D"], wl["F"]
+    rows = wl["rows"]
+    ntab = len(rows)
+    mine = se.local_ids
+    sample = {k: se.tables.table(j)[:min(rows[k], CHECK_ROWS)].float().cpu().numpy().copy() for j, k in enumerate(mine)}
+    parts = [None] * world
+    dist.all_gather_object(parts, sample)
+    ref_tables = [None] * ntab
+    for part in parts:
+        for k, v in part.items():
+            ref_tables[k] = v
+    w = interaction_width(F, D)
+    rngs = [np.random.default_rng(4242 + r) for r in range(world)]          # every rank can rebuild every rank's batch
+    idx_all = [np.stack([g.integers(0, min(r_, CHECK_ROWS), size=(B, 1)) for r_ in rows]) for g in rngs]
+    x_all = [g.standard_normal((B, D)).astype(np.float32) for g in rngs]
+    gz_all = [(g.standard_normal((B, w)) * 0.1).astype(np.float32) for g in rngs]
+    lr = 0.05
+    x = torch.from_numpy(x_all[rank]).to(dev).requires_grad_(True)
+    idx_local = torch.from_numpy(idx_all[rank].astype(np.int32)).to(dev)
+    dot = DotInteraction()
+    fused = se.scatter_plan is not None
+    anchor = torch.zeros(1, device=dev, requires_grad=True)
+    T = se.lookup_fused(idx_local) if fused else se.lookup(idx_local, anchor)
+    se.sort_async()
+    z = dot(x, T, scatter=se.scatter_plan) if fused else dot(x, T)
+    z.backward(torch.from_numpy(gz_all[rank]).to(dev))
+    if fused:
+        se.finish_backward()
+    se.update(lr)
+    torch.cuda.synchronize()
+    dist.barrier()
+    # ---- oracle
+    T_ref = O.lookup(ref_tables, list(idx_all[rank]), slot0=1)
+    T_got = T.detach().cpu().numpy()
+    res = {"pooled_rows_bit_exact": bool(np.array_equal(T_got[:, 1:], T_ref[:, 1:]))}
+    T_ref[:, 0] = x_all[rank]
+    res["interaction_fwd_rel_err"] = float(O.rel_err(z.detach().cpu().numpy(), O.interaction_fwd(T_ref)))
+    dT_glob = []
+    for r in range(world):
+        Tr = O.lookup(ref_tables, list(idx_all[r]), slot0=1)
+        Tr[:, 0] = x_all[r]
+        dx_r, dT_r = O.interaction_bwd(gz_all[r], Tr)
+        dT_glob.append(dT_r)
+        if r == rank:
+            res["dx_rel_err"] = float(O.rel_err(x.grad.cpu().numpy(), dx_r))
+    dT_glob = np.concatenate(dT_glob, axis=0)
+    terr = 0.0
+    for j, k in enumerate(mine):
+        idx_glob = np.concatenate([idx_all[r][k] for r in range(world)], axis=0)
+        O.sparse_sgd_update_fast(ref_tables[k], idx_glob, np.ascontiguousarray(dT_glob[:, 1 + k]), lr)
+        got = se.tables.table(j)[:min(rows[k], CHECK_ROWS)].float().cpu().numpy()
+        terr = max(terr, float(O.rel_err(got, ref_tables[k])))
+    res["tables_rel_err_after_update"] = terr
+    ok = (res["pooled_rows_bit_exact"] and res["interaction_fwd_rel_err"] < 1e-5 and res["dx_rel_err"] < 1e-5
+          and terr < 1e-4)
+    flag = torch.tensor([1.0 if ok else 0.0, -res["interaction_fwd_rel_err"], -res["dx_rel_err"], -terr], device=dev,
+                        dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # worst rank
+    v = flag.cpu().tolist()
+    return {"ok": bool(v[0] == 1.0), "against": "unsharded CPU oracle (oracle/oracle.py) on the first "
+            f"{CHECK_ROWS} rows of every table, batch {B} per rank, one full sharded step, worst rank",
+            "pooled_rows_bit_exact": bool(v[0] == 1.0 or res["pooled_rows_bit_exact"]),
+            "interaction_fwd_rel_err": -v[1], "dx_rel_err": -v[2], "tables_rel_err_after_update": -v[3]}
+
+
+def e2e_host_leg(se, wl, batches, dev):
+    """The hot path through the HOST-buffer C entry points (the form a CPU-resident DLRM.jl calls today:
+    Julia arrays in and out, copies inside each call): dlrmb_embedding_fwd_host -> dlrmb_interaction_fwd_host
+    -> dlrmb_interaction_bwd_host -> dlrmb_embedding_bwd_sgd_host on numpy buffers, wall clock per step
+    (every call returns synchronised).  MLPs are not part of this leg (they stay on the host in that set-up)."""
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    from dlrm_jl_b200.interact import interaction_width
+    lib = _lib.load()
+    t = se.tables
+    B, D, F = wl["B"], wl["D"], wl["F"]
+    w = interaction_width(F, D)
+    T = np.zeros((B, F, D), dtype=np.float32)
+    x = np.random.default_rng(3).standard_normal((B, D)).astype(np.float32)
+    out = np.empty((B, w), dtype=np.float32)
+    g = (np.random.default_rng(4).standard_normal((B, w)) * 1e-3).astype(np.float32)
+    dT = np.empty_like(T)
+    dx = np.empty((B, D), dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def step(idx):
+        _lib.check(lib.dlrmb_embedding_fwd_host(t._h, p(idx), 4, 0, B, 1, p(T), F, 1))
+        _lib.check(lib.dlrmb_interaction_fwd_host(t._h, p(T), p(x), B, F, D, 1, p(out)))
+        _lib.check(lib.dlrmb_interaction_bwd_host(t._h, p(g), p(T), B, F, D, 1, p(dT), p(dx)))
+        _lib.check(lib.dlrmb_embedding_bwd_sgd_host(t._h, p(idx), 4, 0, B, 1, p(dT), F, 1, 1e-6))
+
+    idxs = [np.ascontiguousarray(b[2].numpy().reshape(F - 1, B)) for b in batches]
+    for i in range(min(3, len(idxs))):
+        step(idxs[i])
+    t0 = time.perf_counter()
+    for idx in idxs:
+        step(idx)
+    dt = (time.perf_counter() - t0) / len(idxs)
+    h2d = idxs[0].nbytes * 2 + T.nbytes * 3 + x.nbytes + g.nbytes      # idx (twice), T (fwd slot-0 fill, interaction, bwd), x, dOut, dT
+    h2d += dT.nbytes
+    d2h = T.nbytes * 2 + out.nbytes + dT.nbytes + dx.nbytes
+    return {"value": B / dt, "unit": "samples/s", "ms_per_step": 1e3 * dt, "steps": len(idxs),
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "what": "hot path only (lookup, interaction fwd/bwd, sparse SGD) through the dlrmb_*_host entry points on "
+                    "pageable numpy buffers; every call copies its operands in and out and returns synchronised"}
+
+
+def run_sweep(args):
+    """BASELINE config 5: one table, 2^20 lookups per launch, rows x D x pooling x skew grid."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import hotpath
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    cases = []
+    rows_list = (100_000, 1_000_000, 10_000_000, 100_000_000)
+    dims = (16, 32, 64, 128, 256)
+    pools = (1, 4, 16, 64)
+    alphas = (0.0, 1.05, 1.2)
+    if args.sweep_quick:
+        rows_list, dims, pools, alphas = (1_000_000, 100_000_000), (64, 128), (1, 16), (0.0, 1.2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for rows in rows_list:
+        for D in dims:
+            if rows * D * 4 > 120e9:
+                continue
+            for P in pools:
+                for alpha in alphas:
+                    r = hotpath.run_case([rows], D, (1 << 20) // P, P, alpha, 3, True, 3, interaction=False,
+                                         label=f"rows={rows} D={D} P={P} zipf={alpha}")
+                    cases.append({"rows": rows, "D": D, "P": P, "zipf": alpha,
+                                  "lookup_us": r["lookup"]["us"], "lookup_frac": r["lookup"]["frac_hbm"],
+                                  "sort_us": r["sort"]["us"],
+                                  "update_us": r["update_only"]["us"], "update_frac": r["update_only"]["frac_hbm"],
+                                  "total_us": r["embedding_lookup_plus_update"]["us"],
+                                  "gbs": r["embedding_lookup_plus_update"]["gbs"],
+                                  "frac_hbm": r["embedding_lookup_plus_update"]["frac_hbm"],
+                                  "algorithmic_bytes": r["embedding_lookup_plus_update"]["algorithmic_bytes"]})
+                    print(json.dumps(cases[-1]), file=sys.stderr, flush=True)
+    e1.record()
+    torch.cuda.synchronize()
+    big = [c for c in cases if c["D"] >= 64]
+    gm = float(np.exp(np.mean([np.log(c["gbs"]) for c in cases])))
+    peak, peak_src = hotpath.hbm_peak()
+    line = {"metric": "embedding_lookup_plus_update_gbs", "value": gm, "unit": "GB/s", "n_gpus": 1,
+            "steps": len(cases), "warmup": 3, "ms_per_step": e0.elapsed_time(e1) / max(1, len(cases)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "embedding microbench sweep (BASELINE config 5): one table, 2^20 lookups per launch, "
+                                   "rows 1e5-1e8 x D 16-256 x pooling 1/4/16/64 x uniform / Zipf 1.05 / Zipf 1.2; value = "
+                                   "geometric mean over the cases of (lookup + sort + update algorithmic bytes) / time",
+                       "l2": "fresh index batch every launch; tables of 1e5 rows fit L2 and are reported as such"},
+            "summary": {"cases": len(cases), "hbm_peak_gbs": peak, "peak_source": peak_src,
+                        "frac_hbm_geomean": gm / peak,
+                        "frac_hbm_geomean_D_ge_64": float(np.exp(np.mean([np.log(c["frac_hbm"]) for c in big]))) if big else None,
+                        "cases_at_or_above_70pct": sum(1 for c in cases if c["frac_hbm"] >= 0.70),
+                        "cases_below_50pct": sum(1 for c in cases if c["frac_hbm"] < 0.50)},
+            "sweep": cases}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
 def kernel_replays(se, batches, wl, dev):
-    """name -> microseconds per launch, kernels launched back to back (dlrm_jl_b200._prof.time_launches)."""
+    """name -> microseconds per launch, kernels launched back to back (dlrm_jl_b200._prof.time_launches).
+    "lookup" is the launch the step uses: gather + the index sort of the coming update in one kernel;
+    "embedding_chain" is that launch followed by the update launch, per batch (the BASELINE metric)."""
     import torch
     from dlrm_jl_b200 import _lib, _prof
     from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
@@ -697,13 +912,15 @@ def kernel_replays(se, batches, wl, dev):
         gs.append(torch.randn((B, w), device=dev) * 1e-3)
     dT = torch.randn((B, F, D), device=dev) * 1e-3
     out = {}
-    out["lookup"] = _prof.time_launches(lambda i: t.lookup(idx[i], Ts[i], 1), nb)
-    out["sort"] = _prof.time_launches(lambda i: t.sort(idx[i]), nb)
+    out["lookup"] = _prof.time_launches(lambda i: t.lookup(idx[i], Ts[i], 1, sort=True), nb)
+    out["lookup_without_sort"] = _prof.time_launches(lambda i: t.lookup(idx[i], Ts[i], 1), nb)
+    out["sort_alone"] = _prof.time_launches(lambda i: t.sort(idx[i]), nb)
 
-    def sort_update(i):
-        t.sort(idx[i])
+    def chain(i):
+        t.lookup(idx[i], Ts[i], 1, sort=True)
         t.update_sorted(dT, 1, 1e-6)
-    out["update"] = max(_prof.time_launches(sort_update, nb) - out["sort"], 1e-3)
+    out["embedding_chain"] = _prof.time_launches(chain, nb)
+    out["update"] = max(out["embedding_chain"] - out["lookup"], 1e-3)
     out["interaction_fwd"] = _prof.time_launches(lambda i: interaction_fwd(Ts[i]), nb)
     out["interaction_bwd"] = _prof.time_launches(lambda i: interaction_bwd(gs[i], Ts[i]), nb)
     z = torch.randn((B,), device=dev)
@@ -723,8 +940,15 @@ def kernel_replays(se, batches, wl, dev):
 
 
 def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
-    """Per-kernel device time (CUDA events recorded inside the timed region) and the roofline of the
-    dominant kernel of this repo.  Algorithmic bytes per SURVEY.md section 8(d), rank 0's share."""
+    """Per-kernel device time and rooflines.  Algorithmic bytes per SURVEY.md section 8(d), rank 0's share.
+
+    Two clocks per kernel, both CUDA events on the launching stream, both reported:
+      * in_step_us -- an event-record node on either side of the call inside a second capture of the step
+        graph, replayed over the timed batches: the kernel where it sits in the step (cold inputs, the
+        neighbours it really has) plus a few microseconds of graph-dependency latency per event pair;
+      * back_to_back_us -- the kernel launched back to back over the same batches (1 GPU only).
+    `roofline` and `embedding` use the in-step clock (the conservative one); the back-to-back figures are
+    printed beside them."""
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -737,8 +961,7 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     Bg = B * world
     t_mine = len(se.local_ids)
     L = Bg * wl["P"]
-    # distinct rows touched per step on this rank's tables (U), averaged over the timed batches;
-    # with world > 1 the owner sees every rank's samples, approximated by U ~= distinct of L uniform draws
+    # distinct rows touched per step on this rank's tables (U), expectation for L uniform draws
     rows = [wl["rows"][k] for k in se.local_ids]
     U = sum(r * (1.0 - (1.0 - 1.0 / r) ** L) for r in rows)
     lookup_bytes = t_mine * (L * D * 4 + Bg * D * 4 + L * 4)
@@ -750,42 +973,62 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     kernels = {}
     for name, st in prof.items():
         k = {"launches": st["count"], "in_step_us": 1e3 * st["avg_ms"]}
-        k["avg_us"] = float(replay[name]) if (replay and name in replay) else k["in_step_us"]
-        k["avg_us_method"] = "back-to-back launches over the timed batches" if (replay and name in replay) else "in-step event pair"
-        if name in alg and k["avg_us"] > 0:
+        if replay and name in replay:
+            k["back_to_back_us"] = float(replay[name])
+        if name in alg and k["in_step_us"] > 0:
             k["algorithmic_bytes"] = int(alg[name])
-            k["gbs"] = alg[name] / (k["avg_us"] * 1e-6) / 1e9
+            k["gbs"] = alg[name] / (k["in_step_us"] * 1e-6) / 1e9
             k["frac_hbm"] = k["gbs"] / hbm_peak
+            if "back_to_back_us" in k:
+                k["frac_hbm_back_to_back"] = alg[name] / (k["back_to_back_us"] * 1e-6) / 1e9 / hbm_peak
         kernels[name] = k
-    own_ms = sum(k["avg_us"] for k in kernels.values()) * 1e-3
-    prof = {n: {"avg_ms": kernels[n]["avg_us"] * 1e-3} for n in kernels}
+    if replay:
+        for extra in ("lookup_without_sort", "sort_alone", "embedding_chain"):
+            if extra in replay:
+                kernels.setdefault("_replays", {})[extra + "_us"] = float(replay[extra])
+    own_ms = sum(k["in_step_us"] for n, k in kernels.items() if not n.startswith("_")) * 1e-3
     cand = [n for n in ("update", "lookup", "interaction_fwd", "interaction_bwd") if n in kernels]
-    dom = max(cand, key=lambda n: prof[n]["avg_ms"]) if cand else None
+    dom = max(cand, key=lambda n: kernels[n]["in_step_us"]) if cand else None
     out = {"kernels": kernels,
            "hot_path": {"own_kernels_us_per_step": 1e3 * own_ms, "share_of_step": own_ms / ms_step if ms_step else None,
                         "samples_per_s_own_kernels_only": (B / (own_ms * 1e-3)) if own_ms else None}}
-    emb_ms = sum(prof[n]["avg_ms"] for n in ("lookup", "sort", "update") if n in prof)
-    if emb_ms:
-        out["embedding"] = {"algorithmic_bytes": int(lookup_bytes + update_bytes), "us": 1e3 * emb_ms,
-                            "gbs": (lookup_bytes + update_bytes) / (emb_ms * 1e-3) / 1e9,
-                            "frac_hbm": (lookup_bytes + update_bytes) / (emb_ms * 1e-3) / 1e9 / hbm_peak,
-                            "includes": "lookup + index sort + scatter-add/SGD kernels"}
+    emb_names = [n for n in ("lookup", "sort", "update") if n in kernels]
+    emb_us = sum(kernels[n]["in_step_us"] for n in emb_names)
+    if emb_us:
+        emb_bytes = lookup_bytes + update_bytes
+        out["embedding"] = {"algorithmic_bytes": int(emb_bytes), "us": emb_us,
+                            "gbs": emb_bytes / (emb_us * 1e-6) / 1e9,
+                            "frac_hbm": emb_bytes / (emb_us * 1e-6) / 1e9 / hbm_peak,
+                            "clock": "in-step event pairs (sum over the launches below)",
+                            "includes": " + ".join(emb_names) + " launches (gather, index sort / dedup, scatter-add + SGD)"}
+        if replay and "embedding_chain" in replay:
+            out["embedding"]["back_to_back_us"] = float(replay["embedding_chain"])
+            out["embedding"]["frac_hbm_back_to_back"] = emb_bytes / (replay["embedding_chain"] * 1e-6) / 1e9 / hbm_peak
     if dom:
         traffic, traffic_src = None, None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", f"r01_ncu_traffic_{wl['name']}.json")) as fh:
-                tj = json.load(fh)
-            if world == 1 and dom in tj["kernels"]:
-                traffic = tj["kernels"][dom]["dram_bytes_read"] + tj["kernels"][dom]["dram_bytes_write"]
-                traffic_src = f"profiles/r01_ncu_traffic_{wl['name']}.json ({tj['report']})"
+            for tag in ("r02", "r01"):
+                path = os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic_{wl['name']}.json")
+                if os.path.exists(path):
+                    with open(path) as fh:
+                        tj = json.load(fh)
+                    if world == 1 and dom in tj["kernels"]:
+                        traffic = tj["kernels"][dom]["dram_bytes_read"] + tj["kernels"][dom]["dram_bytes_write"]
+                        traffic_src = (f"constant: profiles/{tag}_ncu_traffic_{wl['name']}.json ({tj['report']}), an ncu --set full "
+                                       "capture of this command, not measured in this run")
+                    break
         except Exception:
             pass
-        out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": hbm_peak,
-                           "unit": "GB/s", "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": traffic,
-                           "traffic_source": traffic_src,
-                           "peak_source": peak_src,
-                           "note": ("achieved = algorithmic bytes per launch / per-launch device time (CUDA events; "
-                                    + kernels[dom]["avg_us_method"] + ")")}
+        kd = kernels[dom]
+        out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": kd["gbs"], "peak": hbm_peak,
+                           "unit": "GB/s", "frac": kd["gbs"] / hbm_peak, "traffic": traffic,
+                           "traffic_source": traffic_src, "peak_source": peak_src,
+                           "achieved_back_to_back": (kd["algorithmic_bytes"] / (kd["back_to_back_us"] * 1e-6) / 1e9
+                                                     if "back_to_back_us" in kd else None),
+                           "note": ("dominant kernel of this repo by in-step time; achieved = algorithmic bytes per launch / "
+                                    "in-step device time (CUDA event-record nodes around the launch inside the step graph, "
+                                    "averaged over the timed batches); achieved_back_to_back = same bytes / back-to-back "
+                                    "launch time")}
     return out
 
 
@@ -795,9 +1038,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="terabyte", choices=["terabyte", "kaggle"])
+    ap.add_argument("--workload", default="terabyte", choices=["terabyte", "kaggle", "sweep"])
     ap.add_argument("--batch", type=int, default=2048)
-    ap.add_argument("--cpu-rows-cap", type=int, default=1 << 20)
+    ap.add_argument("--cpu-rows-cap", type=int, default=0,
+                    help="CPU arm: rows per table (0 = as many as 45 %% of the available host RAM holds, 48 GiB at most)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
@@ -806,11 +1050,15 @@ def main():
     ap.add_argument("--unfused-mlp", action="store_true",
                     help="plain nn.Linear / ReLU autograd for the MLPs instead of dlrm_jl_b200.dense.FusedMLP")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
+    ap.add_argument("--sweep-quick", action="store_true", help="--workload sweep on a 2 x 2 x 2 x 2 corner of the grid")
+    ap.add_argument("--no-host-leg", action="store_true", help="skip the e2e_host leg (hot path through the *_host entry points)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sweep":
+        run_sweep(args)
     else:
         run_ours(args)
 

@@ -26,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from dlrm_jl_b200 import _prof  # noqa: E402
+from dlrm_jl_b200 import _lib, _prof  # noqa: E402
 from dlrm_jl_b200.embedding import EmbeddingTables  # noqa: E402
 from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width  # noqa: E402
 from dlrm_jl_b200.model import KAGGLE_EMBEDDING_SIZES, TERABYTE_EMBEDDING_SIZES  # noqa: E402
@@ -117,6 +117,12 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
     rec("lookup", us, lookup_bytes)
     us_sort = time_graph(lambda i: t.sort(idx[i]), nb, use_graph, iters)
     res["sort"] = {"us": us_sort}
+    # training-step form: lookup + sort in one launch (the sort rides in extra CTAs when B*P <= 4096)
+    rec("lookup_sort", time_graph(lambda i: t.lookup(idx[i], T, 1, sort=True), nb, use_graph, iters), lookup_bytes)
+
+    def chain(i):
+        t.lookup(idx[i], T, 1, sort=True)
+        t.update_sorted(dT, 1, 0.01)
 
     def upd(i):
         t.sort(idx[i])
@@ -126,6 +132,8 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
     rec("sort_plus_update", us_both, update_bytes)
     rec("update_only", max(us_both - us_sort, 1e-3), update_bytes)
     rec("embedding_lookup_plus_update", res["lookup"]["us"] + us_both, lookup_bytes + update_bytes)
+    # the BASELINE metric as the step runs it: (lookup + sort) launch, then the update launch, back to back
+    rec("embedding_chain", time_graph(chain, nb, use_graph, iters), lookup_bytes + update_bytes)
     if interaction and D % 4 == 0 and F <= 64:
         w, Ts, gs = interaction_inputs()
         us = time_graph(lambda i: interaction_fwd(Ts[i]), nb, use_graph, iters)
@@ -134,7 +142,7 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
         us = time_graph(lambda i: interaction_bwd(gs[i], Ts[i]), nb, use_graph, iters)
         rec("interaction_bwd", us, B * (w + 2 * F * D + D) * 4)
         res["interaction_bwd"]["gflops"] = 2.0 * B * F * F * D / us / 1e3
-    res["interaction_path"] = os.environ.get("DLRMB_INTERACT", "warp")
+    res["options"] = {k: _lib.get_option(k) for k in ("interact_general", "update_two_launches", "update_tile", "pdl")}
     t.close()
     del T, dT, idx
     torch.cuda.empty_cache()
@@ -158,9 +166,13 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="table storage type")
     ap.add_argument("--only", default=None, help="time just this kernel (e.g. interaction_fwd)")
     ap.add_argument("--no-interaction", action="store_true", help="embedding kernels only")
+    ap.add_argument("--opt", action="append", default=[], help="library switch name=value (dlrmb_set_option)")
     ap.add_argument("--small-tables", action="store_true",
                     help="cap every table at 1000 rows (the interaction kernels do not depend on table size; keeps ncu replays cheap)")
     a = ap.parse_args()
+    for kv in a.opt:
+        name, value = kv.split("=")
+        _lib.set_option(name, int(value))
     results = []
     if a.sweep:
         for rows in (100_000, 1_000_000, 10_000_000, 100_000_000):

@@ -30,6 +30,8 @@ SIGNATURES = {
     "dlrmb_abi_version": (_i32, []),
     "dlrmb_last_error": (C.c_char_p, []),
     "dlrmb_launch_count": (_i64, []),
+    "dlrmb_set_option": (_i32, [C.c_char_p, _i64]),
+    "dlrmb_get_option": (_i32, [C.c_char_p, C.POINTER(_i64)]),
     "dlrmb_tables_create": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, C.POINTER(_vp)]),
     "dlrmb_tables_create_ex": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, _i32, C.POINTER(_vp)]),
     "dlrmb_tables_elem_bytes": (_i32, [_vp]),
@@ -41,6 +43,7 @@ SIGNATURES = {
     "dlrmb_tables_init_uniform": (_i32, [_vp, C.c_uint64, _vp]),
     "dlrmb_tables_sync": (_i32, [_vp]),
     "dlrmb_embedding_fwd": (_i32, [_vp, *_idx_args, _vp, _i32, _i32, _vp]),
+    "dlrmb_embedding_fwd_sort": (_i32, [_vp, *_idx_args, _vp, _i32, _i32, _vp]),
     "dlrmb_interaction_fwd": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "dlrmb_interaction_bwd": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "dlrmb_embedding_sort": (_i32, [_vp, *_idx_args, _vp]),
@@ -101,3 +104,14 @@ def check(status: int) -> None:
 
 def launch_count() -> int:
     return int(load().dlrmb_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide tuning / test switch of the library (include/dlrm_b200.h: dlrmb_set_option)."""
+    check(load().dlrmb_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = _i64()
+    check(load().dlrmb_get_option(name.encode(), C.byref(v)))
+    return int(v.value)

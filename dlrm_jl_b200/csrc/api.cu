@@ -12,6 +12,7 @@ namespace dlrmb {
 
 static thread_local char tl_error[512] = "";
 std::atomic<long long> g_launches{0};
+Options g_opt;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -33,19 +34,6 @@ int device_sm_count(int device) {
     }
     return cache[device];
 }
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-    }
-};
 
 static int grow(void** p, size_t* have, size_t need) {
     if (*have >= need) return DLRMB_OK;
@@ -72,6 +60,31 @@ extern "C" {
 int32_t dlrmb_abi_version(void) { return DLRMB_ABI_VERSION; }
 const char* dlrmb_last_error(void) { return tl_error; }
 int64_t dlrmb_launch_count(void) { return g_launches.load(); }
+
+static std::atomic<int>* find_option(const char* name) {
+    if (!name) return nullptr;
+    if (!strcmp(name, "interact_general")) return &g_opt.interact_general;
+    if (!strcmp(name, "update_two_launches")) return &g_opt.update_two_launches;
+    if (!strcmp(name, "update_tile")) return &g_opt.update_tile;
+    if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
+    if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
+    if (!strcmp(name, "pdl")) return &g_opt.pdl;
+    return nullptr;
+}
+
+int32_t dlrmb_set_option(const char* name, int64_t value) {
+    std::atomic<int>* o = find_option(name);
+    DLRMB_REQUIRE(o != nullptr, "unknown option '%s'", name ? name : "(null)");
+    o->store((int)value);
+    return DLRMB_OK;
+}
+
+int32_t dlrmb_get_option(const char* name, int64_t* value) {
+    std::atomic<int>* o = find_option(name);
+    DLRMB_REQUIRE(o != nullptr && value != nullptr, "unknown option '%s'", name ? name : "(null)");
+    *value = o->load();
+    return DLRMB_OK;
+}
 
 int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
                             int64_t max_lookups, dlrmb_tables** out) {
@@ -158,8 +171,8 @@ int32_t dlrmb_tables_create_ex(int32_t device, int32_t ntab, const int64_t* rows
                         sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)D));
     TRY_CUDA(cudaMalloc((void**)&t->tile_flags, (size_t)ntab * (size_t)t->partial_tiles_cap));
     TRY_CUDA(cudaMalloc((void**)&t->head_list, sizeof(uint32_t) * (size_t)ntab * (size_t)t->partial_tiles_cap));
-    TRY_CUDA(cudaMalloc((void**)&t->head_count, 4 * sizeof(uint32_t)));   // heads, CTAs done, tail CTAs done
-    TRY_CUDA(cudaMemset(t->head_count, 0, 4 * sizeof(uint32_t)));
+    TRY_CUDA(cudaMalloc((void**)&t->head_count, (1 + (size_t)ntab) * sizeof(uint32_t)));   // listed heads; CTAs done per table
+    TRY_CUDA(cudaMemset(t->head_count, 0, (1 + (size_t)ntab) * sizeof(uint32_t)));
     TRY_CUDA(cudaMalloc((void**)&t->d_seg, sizeof(int32_t) * ((size_t)max_lookups + 1)));
     TRY_CUDA(cudaMalloc((void**)&t->d_uniq, sizeof(int64_t) * (size_t)max_lookups));
     TRY_CUDA(cudaMalloc((void**)&t->d_nuniq, sizeof(int32_t)));
@@ -292,6 +305,24 @@ int32_t dlrmb_embedding_fwd(dlrmb_tables* t, const void* idx, int32_t idx_bytes,
     DLRMB_REQUIRE(slot0 >= 0 && slots >= slot0 + t->ntab,
                   "slots = %d too small for slot0 = %d + %d tables", slots, slot0, t->ntab);
     return launch_lookup(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, (cudaStream_t)stream);
+}
+
+int32_t dlrmb_embedding_fwd_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                 int32_t B, int32_t P, float* out, int32_t slots, int32_t slot0,
+                                 dlrmb_stream stream) {
+    GUARD(t);
+    int rc = check_idx_args(t, idx, idx_bytes, idx_base, B, P);
+    if (rc) return rc;
+    DLRMB_REQUIRE(out != nullptr, "out is null");
+    DLRMB_REQUIRE(slot0 >= 0 && slots >= slot0 + t->ntab,
+                  "slots = %d too small for slot0 = %d + %d tables", slots, slot0, t->ntab);
+    t->sorted_valid = false;
+    rc = launch_lookup_sort(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, (cudaStream_t)stream);
+    if (rc) return rc;
+    t->sorted_valid = true;
+    t->sorted_B = B;
+    t->sorted_P = P;
+    return DLRMB_OK;
 }
 
 static int check_interaction_args(int B, int F, int d, int pad_to_mul) {

@@ -42,6 +42,23 @@ extern std::atomic<long long> g_launches;
         DLRMB_CUDA(cudaGetLastError());                                                     \
     } while (0)
 
+// RAII: make `dev` current for the scope of an entry point, restore the caller's device on every
+// return path.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---- table storage -----------------------------------------------------------------------
 struct TableDesc {
     float* base;   // [rows][D] in HBM, 256-byte aligned; f32, or bf16 when the tables store bf16
@@ -89,6 +106,20 @@ template <> struct RowIO<__nv_bfloat16> {
 constexpr int kUpdateTile = 16;
 // Largest per-table lookup count the single-CTA shared-memory sort handles (sort.cu).
 constexpr int kSmemSortMax = 16384;
+// Largest per-table lookup count whose sort rides in the lookup launch (256-thread sort CTAs).
+constexpr int kFusedSortMax = 4096;
+
+// Process-wide tuning / test switches (dlrmb_set_option); read by the launchers, never from the
+// environment.
+struct Options {
+    std::atomic<int> interact_general{0};     // 1: general tiled interaction kernels even for the specialised shapes
+    std::atomic<int> update_two_launches{0};  // 1: separate fix-up launch at every batch size
+    std::atomic<int> update_tile{0};          // 4 | 8 | 16 | 32 entries per lane group (0 = chosen per batch)
+    std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
+    std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
+    std::atomic<int> pdl{1};                  // programmatic dependent launch for the chained kernels
+};
+extern Options g_opt;
 
 }  // namespace dlrmb
 
@@ -107,6 +138,7 @@ struct dlrmb_tables {
     float* slab = nullptr;           // all tables, one allocation (f32 or bf16 elements)
     dlrmb::TableDesc* d_desc = nullptr;
     int32_t* d_slotmap = nullptr;    // sharded use: interaction slot of each local table
+    int slotmap_max = -1;
     cudaStream_t own_stream = nullptr;
 
     // sort / update workspace (all [ntab][max_lookups] unless noted)
@@ -120,7 +152,7 @@ struct dlrmb_tables {
     uint8_t* tile_flags = nullptr;            // [ntab][tiles] boundary flags
     int64_t partial_tiles_cap = 0;
     uint32_t* head_list = nullptr;            // [ntab * tiles] tiles whose last run continues
-    uint32_t* head_count = nullptr;
+    uint32_t* head_count = nullptr;           // [1 + ntab]: listed heads (two-launch path), CTAs done per table
     // dedup export scratch
     int32_t* d_seg = nullptr;                 // [max_lookups + 1]
     int64_t* d_uniq = nullptr;                // [max_lookups]
@@ -153,6 +185,8 @@ int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, i
 bool interaction_has_warp_path(int F, int d);
 int launch_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
                 cudaStream_t s);
+int launch_lookup_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                       float* out, int slots, int slot0, cudaStream_t s);
 int launch_update(dlrmb_tables* t, const float* dT, int slots, int slot0, float lr, cudaStream_t s);
 int launch_dedup_export(dlrmb_tables* t, int k, cudaStream_t s);
 int launch_init_uniform(dlrmb_tables* t, uint64_t seed, cudaStream_t s);

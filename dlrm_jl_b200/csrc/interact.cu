@@ -285,8 +285,8 @@ static int launch_fwd_tb(float* T, const float* x, int B, int F, int d, int widt
     const int d4 = d / 4;
     // k-split (KS = 2^ks_log2 lanes per block): off by default, see launch_interaction_fwd
     int ks_log2 = 0;
-    if (const char* e = getenv("DLRMB_FWD_KS")) {   // tuning aid
-        int v = atoi(e);
+    {   // tuning aid: dlrmb_set_option("fwd_ks", v)
+        const int v = g_opt.fwd_ks.load(std::memory_order_relaxed);
         if (v >= 0 && v <= 3 && d4 % (1 << v) == 0) ks_log2 = v;
     }
     size_t per_sample = ((size_t)Fp * (d4 + 1) * 4 + width) * sizeof(float);
@@ -337,8 +337,8 @@ int launch_interaction_fwd(float* T, const float* x, int B, int F, int d, int pa
     // 21.4 us for TB = 6 and 20.3-29.8 us for TB = 9; every k-split variant loses to its shuffle
     // reduction), so it is the default; the larger blocks stay selectable for tuning.
     int tb = 3;
-    if (const char* e = getenv("DLRMB_FWD_TB")) {   // tuning aid
-        int v = atoi(e);
+    {   // tuning aid: dlrmb_set_option("fwd_tb", v)
+        const int v = g_opt.fwd_tb.load(std::memory_order_relaxed);
         if (v == 3 || v == 6 || v == 9) tb = v;
     }
     if (tb == 3) return launch_fwd_tb<3>(T, x, B, F, d, width, out, sm_count, s);

@@ -18,12 +18,10 @@
 //     per-output summation order (j ascending, one fused multiply-add per term) is the tiled
 //     kernel's, so both produce the same bits;
 //   * forward: T rows arrive by TMA bulk copies (cp.async.bulk, one per row, one mbarrier per
-//     warp) at bank-staggered row addresses; a lane owns a 4 x 4 block of the Gram lower triangle
-//     (28 blocks for F = 27: one warp), 8 LDS.128 per 32 FFMA2, even and odd k accumulated in the
-//     two halves of a register pair; the sample's output row is assembled in the dead part of the
-//     tile and leaves as one contiguous coalesced range.
-#include <stdlib.h>
-
+//     warp) at bank-staggered row addresses and the Gram matrix is computed on the tensor cores in
+//     3xTF32 form (see interaction_fwd_mma_kernel); the sample's output row is assembled in the dead
+//     part of the tile and leaves as one contiguous coalesced range.  (The FP32 FFMA2 forward of
+//     round 1 was bound by the shared-memory -> register path and has been removed.)
 #include "common.cuh"
 
 namespace dlrmb {
@@ -197,144 +195,9 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------
-template <int F, int D>
-struct FwdGeom {
-    static constexpr int D4 = D / 4;
-    static constexpr int LD4 = D4 + 1;                 // row pitch in float4 (16 bytes of padding)
-    static constexpr int NB = (F + 3) / 4;             // 4-row blocks
-    static constexpr int TPS = NB * (NB + 1) / 2;      // lower-triangle block pairs = lanes per sample
-    static constexpr int SPW = 32 / TPS;               // samples per warp
-    static constexpr int NPAIR = F * (F - 1) / 2;
-    // row f starts at float4 index f * LD4 + f / 4: rows 4*bi + r of different blocks (and rows
-    // 4*bj + c) then start in different 16-byte bank groups, so an operand load of a warp -- one
-    // 16-byte chunk per distinct row -- is served without bank conflicts
-    static __host__ __device__ constexpr int row_at(int f) { return f * LD4 + (f >> 2); }
-    static constexpr int SSZ = (row_at(F - 1) + LD4 + 3) & ~3;   // float4 per sample (64-byte multiple)
-    static constexpr int WARPS = 2;
-    static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSZ * 16 + (size_t)WARPS * 8; }
-    static_assert(TPS <= 32, "one warp must cover a sample's block pairs");
-    static_assert(NPAIR <= (SSZ - LD4) * 4, "output staging must fit behind row 0");
-};
-
-template <int F, int D>
-__global__ void __launch_bounds__(FwdGeom<F, D>::WARPS * 32)
-interaction_fwd_warp_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int width,
-                            float* __restrict__ out) {
-    using G = FwdGeom<F, D>;
-    extern __shared__ float4 smem4[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    float4* Ts = smem4 + (size_t)warp * G::SPW * G::SSZ;                              // [SPW][SSZ]
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem4 + (size_t)G::WARPS * G::SPW * G::SSZ) + warp;
-
-    const long long s0 = ((long long)blockIdx.x * G::WARPS + warp) * G::SPW;          // first sample of the warp
-    if (s0 >= B) return;
-    const int ns = (int)((B - s0 < G::SPW) ? (B - s0) : G::SPW);
-
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-                     ::"r"(smem_addr(bar)), "r"((unsigned)(ns * F * D * sizeof(float))) : "memory");
-    }
-    __syncwarp();
-    // one TMA bulk copy per feature row (slot 0 from x when it is handed separately)
-    for (int r = lane; r < ns * F; r += 32) {
-        const int s = r / F, f = r - s * F;
-        const float* src = (x != nullptr && f == 0) ? x + (size_t)(s0 + s) * D
-                                                    : T + ((size_t)(s0 + s) * F + f) * D;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                     ::"r"(smem_addr(Ts + (size_t)s * G::SSZ + G::row_at(f))), "l"(src),
-                       "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar)) : "memory");
-    }
-
-    // lane -> (sample, block pair bi >= bj)
-    const int sub = lane / G::TPS;
-    const int q = lane - sub * G::TPS;
-    int bi = 0;
-    while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
-    const int bj = q - bi * (bi + 1) / 2;
-    const bool live = sub < ns;
-    const float4* Tb = Ts + (size_t)(live ? sub : 0) * G::SSZ;
-    int ra[4], rb[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int fa = min(4 * bi + r, F - 1), fb = min(4 * bj + r, F - 1);   // clamped rows are discarded below
-        ra[r] = fa * G::LD4 + (fa >> 2);
-        rb[r] = fb * G::LD4 + (fb >> 2);
-    }
-
-    {   // wait for the tile
-        unsigned done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(done) : "r"(smem_addr(bar)), "r"(0) : "memory");
-        }
-    }
-
-    // fused fast_vcat: x also becomes slot 0 of T in global memory
-    if (x != nullptr) {
-        for (int i = lane; i < ns * G::D4; i += 32) {
-            const int s = i / G::D4, c = i - s * G::D4;
-            reinterpret_cast<float4*>(T + (size_t)(s0 + s) * F * D)[c] = Ts[(size_t)s * G::SSZ + c];
-        }
-    }
-
-    float2 acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
-    if (live) {
-#pragma unroll 4
-        for (int k = 0; k < G::D4; ++k) {
-            float4 a[4], bv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = Tb[ra[r] + k];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) bv[c] = Tb[rb[c] + k];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    acc[r][c] = ffma2(make_float2(a[r].x, a[r].y), make_float2(bv[c].x, bv[c].y), acc[r][c]);
-                    acc[r][c] = ffma2(make_float2(a[r].z, a[r].w), make_float2(bv[c].z, bv[c].w), acc[r][c]);
-                }
-        }
-    }
-    __syncwarp();   // every lane is done reading rows >= 1: their space becomes the output staging
-
-    float* Os = reinterpret_cast<float*>(Ts);   // sample s: row 0 at [s*SSZ*4, +D), pairs at [s*SSZ*4 + 4*LD4, +NPAIR)
-    if (live) {
-        float* o = Os + (size_t)sub * G::SSZ * 4 + 4 * G::LD4;
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int j = 4 * bi + r, i = 4 * bj + c;
-                if (i < j && j < F) o[j * (j - 1) / 2 + i] = acc[r][c].x + acc[r][c].y;
-            }
-    }
-    __syncwarp();
-
-    // the warp's samples are one contiguous range of the output; each row leaves coalesced
-#pragma unroll 1
-    for (int s = 0; s < ns; ++s) {
-        const float* base = Os + (size_t)s * G::SSZ * 4;
-        float* og = out + (size_t)(s0 + s) * width;
-        for (int c = lane; c < D; c += 32) og[c] = base[c];
-        for (int c = lane; c < G::NPAIR; c += 32) og[D + c] = base[4 * G::LD4 + c];
-        for (int c = D + G::NPAIR + lane; c < width; c += 32) og[c] = 0.f;   // pad_to_mul padding
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // forward on the tensor cores: 3xTF32 (error-compensated) warp-level MMA
 // ------------------------------------------------------------------------------------------
-// The FFMA2 forward above is bound by the shared-memory -> register path: a 4 x 4 register block
+// An FP32-FMA forward is bound by the shared-memory -> register path: a 4 x 4 register block
 // reads 8 floats per 16 FMAs, and that path delivers 32 floats per clock per SM against 128 FMAs per
 // clock (ncu: 1,090 shared wavefronts per sample, 7 us of shared-memory pipe per SM at B = 2048,
 // above the 5 us the HBM traffic takes).  The k-reduction is what the tensor core does internally,
@@ -492,20 +355,6 @@ int launch_fwd_mma(float* T, const float* x, int B, int width, float* out, cudaS
 }
 
 template <int F, int D>
-int launch_fwd_warp(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
-    using G = FwdGeom<F, D>;
-    static unsigned long long attr_done = 0;
-    const size_t smem = G::smem_bytes();
-    int rc = ensure_smem_attr((const void*)interaction_fwd_warp_kernel<F, D>, (int)smem, &attr_done);
-    if (rc) return rc;
-    const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
-    const long long grid = (groups + G::WARPS - 1) / G::WARPS;
-    interaction_fwd_warp_kernel<F, D><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(T, x, B, width, out);
-    DLRMB_LAUNCH_CHECK();
-    return DLRMB_OK;
-}
-
-template <int F, int D>
 int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
                     const void* dests, long long sample_offset, cudaStream_t s) {
     using G = BwdGeom<F, D>;
@@ -528,16 +377,9 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
     return DLRMB_OK;
 }
 
-// DLRMB_INTERACT = "tiled" forces the general kernels of interact.cu, "ffma2" the FFMA2 forward
-// instead of the tensor-core forward (A/B runs, tests); unset = the fastest measured path.
-bool warp_path_enabled() {
-    const char* e = getenv("DLRMB_INTERACT");
-    return !(e && strcmp(e, "tiled") == 0);
-}
-bool fwd_use_mma() {
-    const char* e = getenv("DLRMB_INTERACT");
-    return !(e && strcmp(e, "ffma2") == 0);
-}
+// dlrmb_set_option("interact_general", 1) sends the specialised shapes through the general tiled kernels
+// of interact.cu (parity tests compare the two); default = the specialised kernels.
+bool warp_path_enabled() { return g_opt.interact_general.load(std::memory_order_relaxed) == 0; }
 
 }  // namespace
 
@@ -557,12 +399,7 @@ bool interaction_has_warp_path(int F, int d) {
 int try_interaction_fwd_warp(float* T, const float* x, int B, int F, int d, int width, float* out,
                              cudaStream_t s) {
     if (!warp_path_enabled()) return -1;
-    if (fwd_use_mma()) {
 #define X(FF, DD) if (F == FF && d == DD) return launch_fwd_mma<FF, DD>(T, x, B, width, out, s);
-        DLRMB_WARP_SHAPES(X)
-#undef X
-    }
-#define X(FF, DD) if (F == FF && d == DD) return launch_fwd_warp<FF, DD>(T, x, B, width, out, s);
     DLRMB_WARP_SHAPES(X)
 #undef X
     return -1;

@@ -11,6 +11,7 @@
 // P == 1 and from a 4-deep unrolled pooling loop when P > 1.  The pooled sum runs in ascending
 // p, so results are bit-identical to the CPU restatement.
 #include "common.cuh"
+#include "sort_small.cuh"
 
 namespace dlrmb {
 
@@ -36,22 +37,23 @@ template <> struct Vec<1> {
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 };
 
-// P == 1: plain gather.  U independent chains per thread.
+// P == 1: plain gather.  U independent chains per thread.  `cta` of `nctas` CTAs of 256 threads share
+// table k.
 template <typename IdxT, int VEC, int U, typename RowT>
-__global__ void __launch_bounds__(256)
-lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
-                     uint32_t B, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
+__device__ __forceinline__ void lookup_gather_body(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx,
+                                                   int idx_base, uint32_t B, uint32_t C, int cshift,
+                                                   float* __restrict__ out, int slots, int slot0, int k,
+                                                   uint32_t cta, uint32_t nctas) {
     using V = typename Vec<VEC>::type;
-    const int k = blockIdx.y;
     const float* __restrict__ tb = desc[k].base;
     const IdxT* __restrict__ ik = idx + (size_t)k * B;
     const uint32_t n = B * C;
-    const uint32_t step = gridDim.x * blockDim.x;
+    const uint32_t step = nctas * blockDim.x;
     const size_t D = (size_t)C * VEC;
     float* __restrict__ ob = out + (size_t)(slot0 + k) * D;
     const size_t ostride = (size_t)slots * D;
 
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step * U) {
+    for (uint32_t t = cta * blockDim.x + threadIdx.x; t < n; t += step * U) {
         int64_t row[U];
         uint32_t b[U], c[U];
         bool ok[U];
@@ -75,20 +77,20 @@ lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict_
 
 // P > 1: gather + sum-pool, ascending p.
 template <typename IdxT, int VEC, typename RowT>
-__global__ void __launch_bounds__(256)
-lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
-                   uint32_t B, uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
+__device__ __forceinline__ void lookup_pool_body(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx,
+                                                 int idx_base, uint32_t B, uint32_t P, uint32_t C, int cshift,
+                                                 float* __restrict__ out, int slots, int slot0, int k,
+                                                 uint32_t cta, uint32_t nctas) {
     using V = typename Vec<VEC>::type;
-    const int k = blockIdx.y;
     const float* __restrict__ tb = desc[k].base;
     const IdxT* __restrict__ ik = idx + (size_t)k * B * P;
     const uint32_t n = B * C;
-    const uint32_t step = gridDim.x * blockDim.x;
+    const uint32_t step = nctas * blockDim.x;
     const size_t D = (size_t)C * VEC;
     float* __restrict__ ob = out + (size_t)(slot0 + k) * D;
     const size_t ostride = (size_t)slots * D;
 
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step) {
+    for (uint32_t t = cta * blockDim.x + threadIdx.x; t < n; t += step) {
         const uint32_t b = cshift >= 0 ? (t >> cshift) : (t / C);
         const uint32_t c = t - b * C;
         const IdxT* __restrict__ ip = ik + (size_t)b * P;
@@ -116,6 +118,61 @@ lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
     }
 }
 
+template <typename IdxT, int VEC, int U, typename RowT>
+__global__ void __launch_bounds__(256)
+lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
+                     uint32_t B, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
+    lookup_gather_body<IdxT, VEC, U, RowT>(desc, idx, idx_base, B, C, cshift, out, slots, slot0, blockIdx.y,
+                                           blockIdx.x, gridDim.x);
+}
+
+template <typename IdxT, int VEC, typename RowT>
+__global__ void __launch_bounds__(256)
+lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
+                   uint32_t B, uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
+    lookup_pool_body<IdxT, VEC, RowT>(desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, blockIdx.y,
+                                      blockIdx.x, gridDim.x);
+}
+
+// Training-step form: the lookup and the index sort / dedup of the NEXT sparse update in one launch.
+// The sort needs the indices only, and one CTA per table sorts that table's B*P keys in shared
+// memory (sort_small.cuh) in less time than the gather takes, so the first `ntab` CTAs of the grid
+// are sort CTAs and the rest gather: the sort costs no launch of its own and no time on the stream.
+template <typename IdxT, int U, typename RowT, int ITEMS, bool POOL>
+__global__ void __launch_bounds__(256, 5)
+lookup_sort_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base, uint32_t B,
+                   uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0, int ntab,
+                   uint32_t bx, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap) {
+    extern __shared__ uint32_t sort_smem[];
+    if ((int)blockIdx.x < ntab) {
+        const int k = blockIdx.x;
+        const int L = (int)(B * P);
+        sort_small_body<IdxT, ITEMS, 256>(idx + (size_t)k * L, idx_base, L, desc[k].rows,
+                                          keys_out + (size_t)k * cap, pos_out + (size_t)k * cap, sort_smem);
+        return;
+    }
+    const uint32_t lin = blockIdx.x - ntab;
+    const int k = (int)(lin / bx);
+    const uint32_t cx = lin - (uint32_t)k * bx;
+    if (POOL) lookup_pool_body<IdxT, 4, RowT>(desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, k, cx, bx);
+    else lookup_gather_body<IdxT, 4, U, RowT>(desc, idx, idx_base, B, C, cshift, out, slots, slot0, k, cx, bx);
+}
+
+static void lookup_grid(const dlrmb_tables* t, int64_t n, int P, int64_t* bx, int* cshift, uint32_t C) {
+    constexpr int U = 4;
+    const int per_block = 256 * (P == 1 ? U : 1);
+    int64_t b = ceil_div64(n, per_block);
+    const int64_t cap = (int64_t)t->sm_count * 32;
+    if (b * t->ntab > cap) b = cap / t->ntab > 0 ? cap / t->ntab : 1;
+    *bx = b;
+    *cshift = -1;
+    if ((C & (C - 1)) == 0) {
+        int sh = 0;
+        while ((1u << sh) < C) ++sh;
+        *cshift = sh;
+    }
+}
+
 template <typename IdxT, int VEC, typename RowT>
 static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, float* out,
                            int slots, int slot0, cudaStream_t s) {
@@ -123,16 +180,10 @@ static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B
     const int64_t n = (int64_t)B * C;
     DLRMB_REQUIRE(n < (1ll << 30), "B * D too large for one lookup launch (%lld chunks)", (long long)n);
     constexpr int U = 4;
-    const int per_block = 256 * (P == 1 ? U : 1);
-    int64_t bx = ceil_div64(n, per_block);
-    const int64_t cap = (int64_t)t->sm_count * 32;
-    if (bx * t->ntab > cap) bx = cap / t->ntab > 0 ? cap / t->ntab : 1;
+    int64_t bx;
+    int cshift;
+    lookup_grid(t, n, P, &bx, &cshift, C);
     dim3 grid((unsigned)bx, (unsigned)t->ntab);
-    int cshift = -1;
-    if ((C & (C - 1)) == 0) {
-        cshift = 0;
-        while ((1u << cshift) < C) ++cshift;
-    }
     if (P == 1)
         lookup_gather_kernel<IdxT, VEC, U, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, cshift, out, slots, slot0);
     else
@@ -160,6 +211,60 @@ int launch_lookup(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base,
     if (t->elem_bytes == 2)
         return launch_lookup_r<__nv_bfloat16>(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, s);
     return launch_lookup_r<float>(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, s);
+}
+
+template <typename IdxT, typename RowT, int ITEMS, bool POOL>
+static int launch_lookup_sort_i(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, float* out,
+                                int slots, int slot0, cudaStream_t s) {
+    const uint32_t C = t->D / 4;
+    const int64_t n = (int64_t)B * C;
+    DLRMB_REQUIRE(n < (1ll << 30), "B * D too large for one lookup launch (%lld chunks)", (long long)n);
+    constexpr int U = 4;
+    int64_t bx;
+    int cshift;
+    lookup_grid(t, n, P, &bx, &cshift, C);
+    constexpr size_t smem = SmallSortGeom<ITEMS, 256>::smem_bytes();
+    static unsigned long long attr_done = 0;
+    int rc = ensure_smem_attr((const void*)lookup_sort_kernel<IdxT, U, RowT, ITEMS, POOL>, (int)smem, &attr_done);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)(t->ntab + bx * t->ntab);
+    lookup_sort_kernel<IdxT, U, RowT, ITEMS, POOL><<<grid, 256, smem, s>>>(
+        t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, t->ntab, (uint32_t)bx, t->keys[0], t->pos[0], t->cap);
+    DLRMB_LAUNCH_CHECK();
+    t->sorted_buf = 0;
+    return DLRMB_OK;
+}
+
+template <typename IdxT, typename RowT>
+static int launch_lookup_sort_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, int P, float* out,
+                                int slots, int slot0, cudaStream_t s) {
+    const int64_t L = (int64_t)B * P;
+    if (L <= 2048)
+        return P == 1 ? launch_lookup_sort_i<IdxT, RowT, 8, false>(t, idx, idx_base, B, P, out, slots, slot0, s)
+                      : launch_lookup_sort_i<IdxT, RowT, 8, true>(t, idx, idx_base, B, P, out, slots, slot0, s);
+    return P == 1 ? launch_lookup_sort_i<IdxT, RowT, 16, false>(t, idx, idx_base, B, P, out, slots, slot0, s)
+                  : launch_lookup_sort_i<IdxT, RowT, 16, true>(t, idx, idx_base, B, P, out, slots, slot0, s);
+}
+
+// lookup + sort for the next update: fused into one launch when the sort fits the 256-thread
+// shared-memory path and the rows are 16-byte vectorisable; two launches otherwise.
+int launch_lookup_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
+                       float* out, int slots, int slot0, cudaStream_t s) {
+    const bool vec4 = (t->D % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (!vec4 || (int64_t)B * P > kFusedSortMax) {
+        int rc = launch_lookup(t, idx, idx_bytes, idx_base, B, P, out, slots, slot0, s);
+        if (rc) return rc;
+        return launch_sort(t, idx, idx_bytes, idx_base, B, P, s);
+    }
+    const bool bf = t->elem_bytes == 2;
+    if (idx_bytes == 4) {
+        const uint32_t* p = static_cast<const uint32_t*>(idx);
+        return bf ? launch_lookup_sort_t<uint32_t, __nv_bfloat16>(t, p, idx_base, B, P, out, slots, slot0, s)
+                  : launch_lookup_sort_t<uint32_t, float>(t, p, idx_base, B, P, out, slots, slot0, s);
+    }
+    const int64_t* p = static_cast<const int64_t*>(idx);
+    return bf ? launch_lookup_sort_t<int64_t, __nv_bfloat16>(t, p, idx_base, B, P, out, slots, slot0, s)
+              : launch_lookup_sort_t<int64_t, float>(t, p, idx_base, B, P, out, slots, slot0, s);
 }
 
 // ---- ScaledUniform init (src/model/model.jl:61-65): U(-1/sqrt(rows), 1/sqrt(rows)) ------------

@@ -117,20 +117,23 @@ extern "C" {
 int32_t dlrmb_xbuf_create(int32_t device, int64_t bytes, dlrmb_xbuf** out) {
     DLRMB_REQUIRE(out != nullptr && bytes > 0, "bad xbuf arguments");
     *out = nullptr;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    DLRMB_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
     void* p = nullptr;
     DLRMB_CUDA(cudaMalloc(&p, (size_t)bytes));
-    DLRMB_CUDA(cudaMemset(p, 0, (size_t)bytes));
-    if (prev >= 0 && prev != device) cudaSetDevice(prev);
-    dlrmb_xbuf* x = new dlrmb_xbuf{device, p, (size_t)bytes};
-    *out = x;
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("cudaMemset of a %lld-byte exchange buffer failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return DLRMB_ECUDA;
+    }
+    *out = new dlrmb_xbuf{device, p, (size_t)bytes};
     return DLRMB_OK;
 }
 
 int32_t dlrmb_xbuf_destroy(dlrmb_xbuf* x) {
     if (!x) return DLRMB_OK;
+    DeviceGuard guard(x->device);
     cudaFree(x->ptr);
     delete x;
     return DLRMB_OK;
@@ -153,36 +156,37 @@ int32_t dlrmb_xbuf_ipc_handle(dlrmb_xbuf* x, uint8_t* handle64) {
 
 int32_t dlrmb_xbuf_open(int32_t device, const uint8_t* handle64, void** peer_ptr) {
     DLRMB_REQUIRE(handle64 && peer_ptr, "null argument");
-    int prev = -1;
-    cudaGetDevice(&prev);
-    DLRMB_CUDA(cudaSetDevice(device));
+    *peer_ptr = nullptr;
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     void* p = nullptr;
     DLRMB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    if (prev >= 0 && prev != device) cudaSetDevice(prev);
     *peer_ptr = p;
     return DLRMB_OK;
 }
 
 int32_t dlrmb_xbuf_close(int32_t device, void* peer_ptr) {
     if (!peer_ptr) return DLRMB_OK;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    DLRMB_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
     DLRMB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
-    if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return DLRMB_OK;
 }
 
 int32_t dlrmb_tables_set_slot_map(dlrmb_tables* t, const int32_t* slots) {
     DLRMB_REQUIRE(t && slots, "null argument");
-    int prev = -1;
-    cudaGetDevice(&prev);
-    DLRMB_CUDA(cudaSetDevice(t->device));
+    DeviceGuard guard(t->device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", t->device);
+    int max_slot = -1;
+    for (int k = 0; k < t->ntab; ++k) {
+        DLRMB_REQUIRE(slots[k] >= 0, "slot_map[%d] = %d is negative", k, slots[k]);
+        if (slots[k] > max_slot) max_slot = slots[k];
+    }
     if (!t->d_slotmap) DLRMB_CUDA(cudaMalloc((void**)&t->d_slotmap, sizeof(int32_t) * t->ntab));
     DLRMB_CUDA(cudaMemcpy(t->d_slotmap, slots, sizeof(int32_t) * t->ntab, cudaMemcpyHostToDevice));
-    if (prev >= 0 && prev != t->device) cudaSetDevice(prev);
+    t->slotmap_max = max_slot;
     return DLRMB_OK;
 }
 
@@ -191,6 +195,8 @@ int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_by
                                 int32_t B_local, int32_t slots, dlrmb_stream stream) {
     DLRMB_REQUIRE(t != nullptr && idx != nullptr && peer_T != nullptr, "null argument");
     DLRMB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, "idx_bytes must be 4 or 8 (got %d)", idx_bytes);
+    DLRMB_REQUIRE(idx_base == 0 || idx_base == 1, "idx_base must be 0 or 1 (got %d)", idx_base);
+    DLRMB_REQUIRE(P > 0, "P must be positive (got %d)", P);
     DLRMB_REQUIRE(world >= 1 && world <= kMaxPeers, "world must be in 1..%d (got %d)", kMaxPeers, world);
     DLRMB_REQUIRE(B_local > 0 && B_global == B_local * world, "B_global (%d) must equal B_local (%d) * world (%d)",
                   B_global, B_local, world);
@@ -200,9 +206,10 @@ int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_by
         set_error("dlrmb_embedding_fwd_p2p needs dlrmb_tables_set_slot_map first");
         return DLRMB_ESTATE;
     }
-    int prev = -1;
-    cudaGetDevice(&prev);
-    DLRMB_CUDA(cudaSetDevice(t->device));
+    DLRMB_REQUIRE(slots > t->slotmap_max, "slots = %d does not cover the slot map (largest slot %d)", slots,
+                  t->slotmap_max);
+    DeviceGuard guard(t->device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", t->device);
     PeerPtrs peers;
     bool aligned = (t->D % 4 == 0);
     for (int r = 0; r < kMaxPeers; ++r) {
@@ -228,7 +235,6 @@ int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_by
         else rc = bf ? launch_p2p_t<int64_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
                      : launch_p2p_t<int64_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
     }
-    if (prev >= 0 && prev != t->device) cudaSetDevice(prev);
     return rc;
 }
 

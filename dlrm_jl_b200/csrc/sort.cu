@@ -8,8 +8,9 @@
 //
 // Two paths, chosen per call from L = B*P:
 //   * L <= kSmemSortMax: one CTA per table runs the whole LSD radix sort in shared memory
-//     (8-bit digits, as many passes as that table's row count needs); a single launch covers
-//     all tables.
+//     (digits of up to 9 bits, as many passes as that table's row count needs); a single launch
+//     covers all tables.  Training steps do not even pay that launch: dlrmb_embedding_fwd_sort runs
+//     the same sort in extra CTAs of the lookup launch (lookup.cu), hidden behind the gather.
 //   * larger L: least-significant-digit radix sort, digits of up to 9 bits, tiles of 4096 keys, all tables
 //     batched through grid.y.  Per pass: per-tile digit histogram -> exclusive scan over
 //     (digit, tile), one CTA per digit -> stable scatter whose in-tile ranks come from warp match_any + per-warp
@@ -19,123 +20,27 @@
 // Output: keys[sorted_buf] (ascending 0-based row ids) and pos[sorted_buf] (the stable
 // permutation), both [ntab][max_lookups].
 #include "common.cuh"
+#include "sort_small.cuh"
 
 namespace dlrmb {
 
 // ---------------------------------------------------------------------------------------------
 // small path: LSD radix sort held in shared memory, one CTA per table, one launch for all tables
+// (body in sort_small.cuh; the fused lookup + sort launch of lookup.cu runs the same body)
 // ---------------------------------------------------------------------------------------------
-// THREADS x ITEMS keys (up to 512 x 32 = 16384).  Element e of the table's flat index list lives in warp w = e / (32 *
-// ITEMS), item i, lane l (e = w*32*ITEMS + i*32 + l), so (warp, item, lane) order is input order
-// and the per-digit ranks below make every pass stable.  Per pass: match_any groups the lanes of a
-// warp by digit, a per-warp digit counter in shared memory turns that into a rank inside the warp's
-// chunk, a 256-wide exclusive scan over the digit totals gives the bucket starts, and the keys are
-// scattered through shared memory.  The number of passes follows the table's own row count
-// (a 24-row table needs one 8-bit pass, a 10M-row table three).
 template <typename IdxT, int ITEMS, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sort_small_kernel(const IdxT* __restrict__ idx, int idx_base, int L, const TableDesc* __restrict__ desc,
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap) {
-    constexpr int N = THREADS * ITEMS;
-    constexpr int NW = THREADS / 32;
     extern __shared__ uint32_t sort_smem[];
-    uint32_t* ksm = sort_smem;                                   // [N]
-    uint32_t* wh = ksm + N;                                      // [NW][256]
-    uint32_t* wsum = wh + NW * 256;                              // [8]
-    uint16_t* vsm = reinterpret_cast<uint16_t*>(wsum + 8);       // [N]
     const int k = blockIdx.x;
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const IdxT* __restrict__ ik = idx + (size_t)k * L;
-    const int64_t rows = desc[k].rows;
-    int bits = 0;
-    while (bits < 32 && (1ll << bits) < rows) ++bits;
-    const int passes = (bits + 7) >> 3;
-    const int base = w * (32 * ITEMS);
-    const uint32_t lt_mask = (1u << lane) - 1u;
-
-    uint32_t key[ITEMS];
-    uint32_t vr[ITEMS];    // low 16 bits: original position, high 16 bits: rank inside the warp's chunk
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int e = base + i * 32 + lane;
-        key[i] = e < L ? (uint32_t)((int64_t)ik[e] - idx_base) : 0xffffffffu;
-        vr[i] = (uint32_t)e;
-    }
-    for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-        for (int i = tid; i < NW * 256; i += THREADS) wh[i] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t dig = (key[i] >> shift) & 255u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, dig);
-            const uint32_t lt = peers & lt_mask;
-            const uint32_t b = wh[w * 256 + dig];
-            __syncwarp();
-            if (lt == 0) wh[w * 256 + dig] = b + __popc(peers);
-            __syncwarp();
-            vr[i] = (vr[i] & 0xffffu) | ((b + __popc(lt)) << 16);
-        }
-        __syncthreads();
-        {   // thread d < 256 owns digit d: bucket start = exclusive scan of the digit totals
-            uint32_t total = 0;
-            if (tid < 256)
-                for (int ww = 0; ww < NW; ++ww) total += wh[ww * 256 + tid];
-            uint32_t inc = total;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (lane == 31 && w < 8) wsum[w] = inc;
-            __syncthreads();
-            if (tid < 256) {
-                uint32_t run = inc - total;
-                for (int ww = 0; ww < 8; ++ww)
-                    if (ww < w) run += wsum[ww];
-                for (int ww = 0; ww < NW; ++ww) {
-                    const uint32_t c = wh[ww * 256 + tid];
-                    wh[ww * 256 + tid] = run;
-                    run += c;
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t dst = wh[w * 256 + ((key[i] >> shift) & 255u)] + (vr[i] >> 16);
-            ksm[dst] = key[i];
-            vsm[dst] = (uint16_t)(vr[i] & 0xffffu);
-        }
-        __syncthreads();
-        if (p + 1 < passes) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                const int e = base + i * 32 + lane;
-                key[i] = ksm[e];
-                vr[i] = vsm[e];
-            }
-        }
-    }
-    uint32_t* ko = keys_out + (size_t)k * cap;
-    uint32_t* po = pos_out + (size_t)k * cap;
-    if (passes == 0) {   // single-row table: already sorted
-        for (int i = tid; i < L; i += THREADS) {
-            ko[i] = 0u;
-            po[i] = (uint32_t)i;
-        }
-        return;
-    }
-    for (int i = tid; i < L; i += THREADS) {
-        ko[i] = ksm[i];
-        po[i] = vsm[i];
-    }
+    sort_small_body<IdxT, ITEMS, THREADS>(idx + (size_t)k * L, idx_base, L, desc[k].rows,
+                                          keys_out + (size_t)k * cap, pos_out + (size_t)k * cap, sort_smem);
 }
 
 template <typename IdxT, int ITEMS, int THREADS>
 static int launch_sort_small(dlrmb_tables* t, const IdxT* idx, int idx_base, int L, cudaStream_t s) {
-    constexpr int N = THREADS * ITEMS;
-    constexpr size_t smem = sizeof(uint32_t) * (N + (THREADS / 32) * 256 + 8) + sizeof(uint16_t) * N;
+    constexpr size_t smem = SmallSortGeom<ITEMS, THREADS>::smem_bytes();
     static unsigned long long attr_done = 0;
     int rc = ensure_smem_attr((const void*)sort_small_kernel<IdxT, ITEMS, THREADS>, (int)smem, &attr_done);
     if (rc) return rc;

@@ -22,22 +22,23 @@
 //            list of head chunks; every listed run gets a CTA whose lane groups add the carried
 //            partials in a fixed strided order and update the row once.  For large batches that is
 //            a second launch (update_fixup_kernel).  At DLRM batch sizes, where a launch costs as
-//            much as the whole fix-up, the highest-numbered CTAs of update_tiles_kernel stay behind,
-//            wait for the grid's completion count and run level 3 themselves (TAIL = true): one
-//            launch per update, no memset (the last CTA out re-arms the counters).
+//            much as the whole fix-up, level 3 runs inside the same launch (INLINE = true): every CTA
+//            counts itself done on its table's counter, and the CTA that finds the count complete --
+//            the last one of that table, whichever it is -- lists the table's head chunks and
+//            finishes their runs.  Nobody waits for anybody (no spin, no assumption about the order
+//            in which CTAs are scheduled), the tables finish independently, and the last CTA re-arms
+//            its counter, so an update is one launch and no memset.
 //
 // HBM traffic per entry: 8 B of (key, position), one D*4-byte gradient row read, and per distinct
 // row one D*4-byte read + one D*4-byte write.  The 4 keys / 4 positions of a batch are one 16-byte
 // load each, the next batch's are requested before the current batch's rows, and the rows of a
 // batch (gradient rows plus the table rows of the runs ending in it) are all in flight together.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace dlrmb {
 
-// Batches of at most this many (table, lookup) entries run the fix-up in the tail of the tiles launch.
-constexpr int64_t kUpdateTailMaxEntries = 1 << 18;
+// Batches of at most this many (table, lookup) entries run the fix-up inside the tiles launch.
+constexpr int64_t kUpdateInlineMaxEntries = 1 << 18;
 
 template <int VEC> struct UV;
 template <> struct UV<4> {
@@ -172,15 +173,72 @@ __device__ __forceinline__ void fixup_runs(const TableDesc* __restrict__ desc, c
     }
 }
 
-// head_count points at three counters: [0] listed head chunks, [1] CTAs done, [2] tail CTAs done.
-// TAIL: the `tail_ctas` CTAs with the highest block ids wait for the rest of the grid and run level 3.
-template <int VEC, int NCH, int THREADS, typename RowT, bool TAIL>
+// Level 3 inside the tiles launch: the same arithmetic as fixup_runs, ONE LANE GROUP per listed run (the
+// runs of a DLRM-sized batch span a handful of chunks, and a table has up to chunks - 1 of them, so the
+// last CTA of a table works on G runs at a time).  The summation order is fixup_runs' -- nsub = 256 /
+// lanes-per-row strided partial sums, added in ascending order on top of the head partial -- so both
+// paths give the same bits.
+template <int VEC, int NCH, typename RowT>
+__device__ __forceinline__ void fixup_runs_grouped(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
+                                                   float lr, const float* partial, const uint8_t* flags,
+                                                   const uint32_t* head_list, uint32_t n_heads, int grp, int G,
+                                                   int sl, const UpdateGeom& gm) {
+    using V = typename UV<VEC>::type;
+    const int lpr = 1 << gm.lpr_log2;
+    const int nsub = 256 >> gm.lpr_log2;                 // lane groups of update_fixup_kernel
+    const size_t D = (size_t)gm.C * VEC;
+    const int chunk_entries = gm.G * gm.tile;
+    for (uint32_t h = grp; h < n_heads; h += G) {
+        const int gid = (int)__ldcg(head_list + h);
+        const int k = gid / gm.chunks;
+        const int g = gid - k * gm.chunks;
+        const uint8_t* fk = flags + (size_t)k * gm.pcap;
+        const float* pk = partial + (size_t)k * gm.pcap * 2 * D;
+        int u_last = gm.chunks - 1;
+        for (int base = g + 1; base < gm.chunks; base += 8) {
+            uint8_t f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = (base + q < gm.chunks) ? __ldcg(fk + base + q) : (uint8_t)FLAG_CARRY_ENDS;
+            int first = -1;
+#pragma unroll
+            for (int q = 7; q >= 0; --q)
+                if (f[q] & FLAG_CARRY_ENDS) first = q;
+            if (first >= 0) {
+                u_last = base + first;
+                break;
+            }
+        }
+        const int nact = min(nsub, u_last - g);
+        const int last = (g + 1) * chunk_entries - 1;    // last entry of the head chunk
+        const uint32_t key = keys[(size_t)k * gm.cap + last];
+        float* tbase = desc[k].base;
+        const V* hp = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D);
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) {
+            const int c = sl + m * lpr;
+            if (c >= gm.C) continue;
+            V total = __ldcg(hp + c);
+            const V row = RowV<VEC, RowT>::load(tbase, key, D, c);
+            for (int j = 0; j < nact; ++j) {
+                V acc = UV<VEC>::zero();
+#pragma unroll 4
+                for (int u = g + 1 + j; u <= u_last; u += nsub)
+                    acc = UV<VEC>::add(acc, __ldcg(reinterpret_cast<const V*>(pk + (size_t)u * 2 * D) + c));
+                total = UV<VEC>::add(total, acc);
+            }
+            RowV<VEC, RowT>::store(tbase, key, D, c, UV<VEC>::sgd(row, total, lr));
+        }
+    }
+}
+
+// head_count: [0] = listed head chunks (two-launch path), [1 + k] = CTAs of table k that are done
+// (INLINE path; zero between launches).
+template <int VEC, int NCH, int THREADS, typename RowT, bool INLINE>
 __global__ void __launch_bounds__(THREADS, (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1))
 update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
                     const uint32_t* __restrict__ pos, const float* __restrict__ dT, float lr,
                     float* __restrict__ partial, uint8_t* __restrict__ flags,
-                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm,
-                    unsigned tail_ctas) {
+                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm) {
     using V = typename UV<VEC>::type;
     constexpr int U = 4;
     __shared__ V s_carry[THREADS * NCH];   // per group: partial of the run carried in from the previous tile
@@ -188,6 +246,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     __shared__ uint8_t s_flag[THREADS];
     __shared__ int s_cta_head;
     __shared__ int s_first;
+    __shared__ uint32_t s_nheads;
 
     const int lpr = 1 << gm.lpr_log2;
     const int G = THREADS >> gm.lpr_log2;
@@ -349,53 +408,44 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             if (chunk_ok[m]) reinterpret_cast<V*>(pcarry)[sl + m * lpr] = tot[m];
         wrote_scratch = true;
     }
-    if (TAIL && wrote_scratch) __threadfence();   // partials are visible before this CTA's completion is counted
+    if (INLINE && wrote_scratch) __threadfence();   // partials are visible before this CTA's completion is counted
     __syncthreads();
-    if (tid == 0) {
-        if (s_cta_head) {
-            cta_flag |= FLAG_HEAD;
-            head_list[atomicAdd(head_count, 1u)] = (uint32_t)(k * gm.chunks + cta);
-        }
-        flags[(size_t)k * gm.pcap + cta] = cta_flag;
-        if (TAIL) {
-            __threadfence();
-            atomicAdd(head_count + 1, 1u);   // result unused: a fire-and-forget reduction
-        }
-    }
-    if (!TAIL) return;
-
-    // ---- level 3 inside this launch: the `tail_ctas` CTAs with the highest block ids stay behind
-    // until the completion count reaches the grid size.  They hold at most tail_ctas of the machine's
-    // CTA slots (the launcher keeps that below half of them), so the CTAs still running or not yet
-    // scheduled always find a slot and the wait cannot deadlock.
-    const unsigned total = gridDim.x * gridDim.y;
-    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
-    if (lin + tail_ctas < total) return;
-    if (tid == 0) {
-        // bounded (about a second): a lost completion would otherwise hang the device; head_count[3]
-        // counts the give-ups so a debugging host can see them
-        unsigned spins = 0;
-        while (*reinterpret_cast<volatile uint32_t*>(head_count + 1) < total) {
-            __nanosleep(64);
-            if (++spins > (1u << 23)) {
-                atomicAdd(head_count + 3, 1u);
-                break;
+    if (!INLINE) {
+        if (tid == 0) {
+            if (s_cta_head) {
+                cta_flag |= FLAG_HEAD;
+                head_list[atomicAdd(head_count, 1u)] = (uint32_t)(k * gm.chunks + cta);
             }
+            flags[(size_t)k * gm.pcap + cta] = cta_flag;
         }
+        return;
+    }
+
+    // ---- level 3 inside this launch: the last CTA of table k to get here finishes the table's
+    // chunk-crossing runs (the pattern of the threadfence reduction: publish, fence, count).
+    if (tid == 0) {
+        if (s_cta_head) cta_flag |= FLAG_HEAD;
+        *reinterpret_cast<volatile uint8_t*>(flags + (size_t)k * gm.pcap + cta) = cta_flag;
         __threadfence();
+        const uint32_t done = atomicAdd(head_count + 1 + k, 1u) + 1u;
+        s_first = (done == gridDim.x) ? 1 : 0;
+        if (done == gridDim.x) head_count[1 + k] = 0;   // re-arm for the next launch (every CTA of the table has counted)
+        s_nheads = 0;
     }
     __syncthreads();
-    const uint32_t n_heads = *reinterpret_cast<volatile uint32_t*>(head_count);
-    fixup_runs<VEC, NCH, THREADS, RowT>(desc, keys, lr, partial, flags, head_list, n_heads,
-                                        lin - (total - tail_ctas), tail_ctas, gm, s_carry, &s_first);
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(head_count + 2, 1u) == tail_ctas - 1) {   // last one out re-arms the counters
-            head_count[0] = 0;
-            head_count[1] = 0;
-            head_count[2] = 0;
-        }
+    if (!s_first) return;
+    __threadfence();
+    // list the table's head chunks (order irrelevant: distinct runs touch distinct rows)
+    uint32_t* my_heads = head_list + (size_t)k * gm.pcap;
+    const uint8_t* fk = flags + (size_t)k * gm.pcap;
+    for (int base = 0; base < gm.chunks; base += THREADS) {
+        const int u = base + tid;
+        if (u < gm.chunks && (__ldcg(fk + u) & FLAG_HEAD)) __stcg(my_heads + atomicAdd(&s_nheads, 1u), (uint32_t)(k * gm.chunks + u));
     }
+    __syncthreads();
+    const uint32_t n_heads = s_nheads;
+    if (n_heads == 0) return;
+    fixup_runs_grouped<VEC, NCH, RowT>(desc, keys, lr, partial, flags, my_heads, n_heads, grp, G, sl, gm);
 }
 
 template <int VEC, int NCH, typename RowT>
@@ -455,8 +505,8 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     gm.G = G;
     gm.tile = choose_update_tile((int64_t)t->ntab * gm.L, lpr, t->sm_count,
                                  THREADS * ((NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1)));
-    if (const char* e = getenv("DLRMB_UPDATE_TILE")) {   // tuning aid: 4, 8, 16 or 32 entries per lane group
-        const int v = atoi(e);
+    {   // tuning aid (dlrmb_set_option("update_tile", v)): 4, 8, 16 or 32 entries per lane group
+        const int v = g_opt.update_tile.load(std::memory_order_relaxed);
         if (v == 4 || v == 8 || v == 16 || v == 32) gm.tile = v;
     }
     gm.tiles = (gm.L + gm.tile - 1) / gm.tile;
@@ -472,21 +522,18 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     const uint32_t* pos = t->pos[t->sorted_buf];
     dim3 grid((unsigned)gm.chunks, (unsigned)t->ntab);
     const int64_t total_chunks = (int64_t)t->ntab * gm.chunks;
-    // DLRM-sized batches: level 3 runs in the tail of the same launch (see the header comment)
-    const bool tail = (int64_t)t->ntab * gm.L <= kUpdateTailMaxEntries && getenv("DLRMB_UPDATE_TWO_LAUNCHES") == nullptr;
-    if (tail) {
-        constexpr int ctas_per_sm = (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1);   // the kernel's launch bound
-        int64_t tail_ctas = (int64_t)t->sm_count * ctas_per_sm / 2;
-        if (tail_ctas > total_chunks) tail_ctas = total_chunks;
-        if (tail_ctas < 1) tail_ctas = 1;
+    // DLRM-sized batches: level 3 runs inside the same launch (see the header comment)
+    const bool inline_fixup = (int64_t)t->ntab * gm.L <= kUpdateInlineMaxEntries &&
+                              g_opt.update_two_launches.load(std::memory_order_relaxed) == 0;
+    if (inline_fixup) {
         update_tiles_kernel<VEC, NCH, THREADS, RowT, true><<<grid, THREADS, 0, s>>>(
-            t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm, (unsigned)tail_ctas);
+            t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm);
         DLRMB_LAUNCH_CHECK();
         return DLRMB_OK;
     }
-    DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, 3 * sizeof(uint32_t), s));
+    DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, sizeof(uint32_t), s));
     update_tiles_kernel<VEC, NCH, THREADS, RowT, false><<<grid, THREADS, 0, s>>>(
-        t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm, 0u);
+        t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm);
     DLRMB_LAUNCH_CHECK();
     unsigned fgrid = (unsigned)(total_chunks < (int64_t)t->sm_count * 8 ? total_chunks : (int64_t)t->sm_count * 8);
     update_fixup_kernel<VEC, NCH, RowT><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,

@@ -155,14 +155,19 @@ class EmbeddingTables:
         _lib.check(self._lib.dlrmb_tables_init_uniform(self._h, seed, _stream_ptr(self.device)))
 
     # -- kernels ------------------------------------------------------------------------------
-    def lookup(self, idx: torch.Tensor, out: torch.Tensor, slot0: int, idx_base: int = 0) -> None:
+    def lookup(self, idx: torch.Tensor, out: torch.Tensor, slot0: int, idx_base: int = 0, sort: bool = False) -> None:
+        """Gather + sum-pool into ``out``.  ``sort=True`` is the training-step form: the same launch also
+        sorts / dedups the indices for the sparse update of this batch (dlrmb_embedding_fwd_sort), so
+        :meth:`update_sorted` can follow the backward pass without a sort launch."""
         ntab, B, P = idx.shape
         slots = out.shape[1]
         assert out.is_contiguous() and out.dtype == torch.float32 and out.shape == (B, slots, self.D)
+        fn = self._lib.dlrmb_embedding_fwd_sort if sort else self._lib.dlrmb_embedding_fwd
         with _prof.range("lookup"):
-            _lib.check(self._lib.dlrmb_embedding_fwd(
-                self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, out.data_ptr(), slots, slot0,
-                _stream_ptr(self.device)))
+            _lib.check(fn(self._h, idx.data_ptr(), idx.element_size(), idx_base, B, P, out.data_ptr(), slots, slot0,
+                          _stream_ptr(self.device)))
+        if sort:
+            self._pending_side = False
 
     def set_slot_map(self, slots: Sequence[int]) -> None:
         """Sharded use: interaction slot (1 + global table id) of each local table."""
@@ -248,12 +253,16 @@ class DefaultStrategy:
     """``DefaultStrategy()``: one D x B matrix per table (test/model/model.jl:265-271)."""
 
 
-def maplookup(strategy, tables: EmbeddingTables, sparse, idx_base: int = 0, requires_grad: bool = False):
+def maplookup(strategy, tables: EmbeddingTables, sparse, idx_base: int = 0, requires_grad: bool = False,
+              check: bool = False):
     """``maplookup(strategy, tables, sparse)`` (src/model/model.jl:161).
 
     Preallocation: returns T [B][slot0 + ntab][D] (slots < slot0 zero).  Default: returns a list
     of [B][D] views, one per table.  The normalised index tensor is attached as ``.indices`` on
-    the returned buffer for the pullback (:func:`sparse_updates`).
+    the returned buffer for the pullback (:func:`sparse_updates`).  With ``requires_grad`` (a training
+    step) the launch also prepares the sort / dedup of the coming sparse update (``T.presorted``).
+    ``check`` range-checks the indices first (the kernels, like the reference's ``@inbounds`` loops,
+    do not) and raises ``DLRMB_EOOB`` naming the first offender.
     """
     idx = _as_index_tensor(sparse, tables.ntab, tables.device)
     if isinstance(strategy, PreallocationStrategy):
@@ -264,13 +273,16 @@ def maplookup(strategy, tables: EmbeddingTables, sparse, idx_base: int = 0, requ
         slot0 = 0
     else:
         raise TypeError(f"unknown lookup strategy {strategy!r}")
+    if check:
+        tables.check_indices(idx, idx_base)
     B = idx.shape[1]
     alloc = torch.zeros if slot0 > 0 else torch.empty
     T = alloc((B, slot0 + tables.ntab, tables.D), dtype=torch.float32, device=tables.device)
-    tables.lookup(idx, T, slot0, idx_base)
+    tables.lookup(idx, T, slot0, idx_base, sort=requires_grad)
     T.indices = idx
     T.idx_base = idx_base
     T.slot0 = slot0
+    T.presorted = bool(requires_grad)
     if requires_grad:
         T.requires_grad_(True)
     if isinstance(strategy, DefaultStrategy):

@@ -72,7 +72,13 @@ class _DotInteractionFn(torch.autograd.Function):
                 T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
                 dT.data_ptr(), dx.data_ptr(), _stream(T)))
         # (dx, dy): dy is the whole (d*F) x B matrix, slot 0 included (interact.jl:428-435)
-        return (dx if ctx.has_x else None), dT, None
+        if not ctx.has_x:
+            # dot_interaction entry point: x IS slot 0 of the stacked input, so its gradient is the sum of
+            # both roles -- the pass-through copy out[:, :d] and the Gram row -- which is what the kernel
+            # returns as dx = dOut[:, :d] + dT[:, 0] (Zygote differentiates concat([X, Zflat]) the same way)
+            dT[:, 0, :] = dx
+            return None, dT, None
+        return dx, dT, None
 
 
 class ScatterPlan:

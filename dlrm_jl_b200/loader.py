@@ -33,7 +33,14 @@ class DACLoader:
     on a side stream while the caller works on the current one.
     """
 
-    def __init__(self, dataset: np.ndarray, batchsize: int, device=0):
+    def __init__(self, dataset: np.ndarray, batchsize: int, device=0, idx_base: int = 1):
+        """``idx_base``: base of the categorical ids in ``dataset``.  Files written by the reference's
+        preprocessing are 1-based (``reindex!`` assigns ``length(dict) + 1``, src/data/criteo.jl:249-253),
+        hence the default; the ids are passed through unchanged and the base travels with the loader
+        (``train`` adopts it, ``DLRMModel(..., idx_base=loader.idx_base)``)."""
+        if idx_base not in (0, 1):
+            raise ValueError("idx_base must be 0 or 1")
+        self.idx_base = int(idx_base)
         if dataset.dtype != DAC_DTYPE:
             raise TypeError("dataset must be an array of DACRecord (loader.DAC_DTYPE)")
         self.dataset = dataset

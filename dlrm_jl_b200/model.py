@@ -71,13 +71,15 @@ class DLRMModel:
         return list(self.bottom_mlp.parameters()) + list(self.top_mlp.parameters())
 
     def __call__(self, dense: torch.Tensor, sparse, strategy=None, cb=donothing, idx_base: int = 0,
-                 training: bool = False):
+                 training: bool = False, check_indices: bool = False):
         """The functor, src/model/model.jl:152-166.  Returns (out [B], T) where T is the lookup
-        buffer (its ``.grad`` after backward is the sparse gradient source)."""
+        buffer (its ``.grad`` after backward is the sparse gradient source).  ``idx_base`` is 1 for
+        reference-format data (1-based ids, src/data/criteo.jl:249-253), 0 for PyTorch-style ids;
+        ``check_indices`` validates the batch against the table sizes before the unchecked kernels run."""
         D = self.embeddings.D
         if strategy is None:
             strategy = PreallocationStrategy(D)
-        y = callback(cb, "lookup", maplookup, strategy, self.embeddings, sparse, idx_base, training)
+        y = callback(cb, "lookup", maplookup, strategy, self.embeddings, sparse, idx_base, training, check_indices)
         x = callback(cb, "bottom_mlp", self.bottom_mlp, dense)
         if isinstance(strategy, DefaultStrategy):
             z = callback(cb, "interaction", dot_interaction, x, y)

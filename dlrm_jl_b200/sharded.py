@@ -175,6 +175,30 @@ class PeerExchange:
         self.G = None
         self.peer_G_ptrs = None
         self._gbuf = None
+        self._closed = False
+
+    def close(self) -> None:
+        """Unmap the peers' buffers (cudaIpcCloseMemHandle) and free this rank's exchange buffers.  Every
+        rank must have finished using the mappings (call after a barrier); views of T / G are dead after."""
+        if getattr(self, "_closed", True):
+            return
+        self._closed = True
+        dev = self.device.index or 0
+        for ptrs in (self.peer_ptrs, self.peer_G_ptrs or []):
+            for r, q in enumerate(ptrs):
+                if r != self.rank and q:
+                    self.lib.dlrmb_xbuf_close(dev, q)
+        self.T = self.G = None
+        for h in (self._xbuf, self._gbuf):
+            if h is not None:
+                self.lib.dlrmb_xbuf_destroy(h)
+        self._xbuf = self._gbuf = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _share(self, nbytes: int):
         """Allocate an exchange buffer and map every rank's copy: returns (own ptr, [ptr per rank])."""
@@ -236,19 +260,21 @@ class _ShardedLookupFn(torch.autograd.Function):
         Bl = idx_local.shape[1]
         if se.world == 1:
             # no exchange: pool straight into the interaction input (slot 0 is filled with x by
-            # the interaction kernel's fused fast_vcat)
+            # the interaction kernel's fused fast_vcat); the same launch sorts the indices for the update
             se.idx_owned = idx_local
             T = torch.empty((Bl, 1 + se.ntab, D), dtype=torch.float32, device=idx_local.device)
             se.lookup_fn(idx_local, T, 1)
+            se.presorted = se.lookup_sorts
             return T
         idx_owned = exchange_indices(idx_local, se.sharding, se.rank, se.group)
         se.idx_owned = idx_owned
+        se.presorted = False
         Bg = idx_owned.shape[1]
         if se.peer is not None:
             # fused path: pooled rows go straight into the owners' T over NVLink; the barrier
             # orders every rank's stores before anyone reads its own T
             if len(se.local_ids):
-                se.tables.lookup_p2p(idx_owned, se.peer.peer_ptrs, Bl, 1 + se.ntab)
+                se.tables.lookup_p2p(idx_owned, se.peer.peer_ptrs, Bl, 1 + se.ntab, se.idx_base)
             se.peer.barrier()
             # a fresh alias every step: the persistent buffer tensor itself must never pick up
             # autograd history (a stale grad_fn from an earlier step would chain the graphs)
@@ -281,9 +307,16 @@ class ShardedEmbedding:
     """
 
     def __init__(self, rows: Sequence[int], D: int, rank: int, world: int, lookup_fn: Callable,
-                 update_fn: Callable, group=None, sort_fn: Optional[Callable] = None):
+                 update_fn: Callable, group=None, sort_fn: Optional[Callable] = None, idx_base: int = 0,
+                 lookup_sorts: bool = False):
+        """``idx_base``: 1 for reference-format (1-based) ids, 0 for PyTorch-style ids; it is handed to
+        every kernel that reads the indices.  ``lookup_sorts``: `lookup_fn` also prepares the sort /
+        dedup of the step's update (the fused launch), so `sort_async` has nothing left to do."""
         self.sharding = TableSharding.build(rows, world)
         self.rank, self.world, self.group = rank, world, group
+        self.idx_base = int(idx_base)
+        self.lookup_sorts = bool(lookup_sorts)
+        self.presorted = False
         self.D = D
         self.ntab = len(rows)
         self.local_ids = self.sharding.local[rank]
@@ -307,8 +340,9 @@ class ShardedEmbedding:
         with torch.no_grad():
             idx_owned = exchange_indices(idx_local, self.sharding, self.rank, self.group)
             self.idx_owned = idx_owned
+            self.presorted = False
             if len(self.local_ids):
-                self.tables.lookup_p2p(idx_owned, self.peer.peer_ptrs, idx_local.shape[1], 1 + self.ntab)
+                self.tables.lookup_p2p(idx_owned, self.peer.peer_ptrs, idx_local.shape[1], 1 + self.ntab, self.idx_base)
             self.peer.barrier()
             return self.peer.T.detach()
 
@@ -329,18 +363,21 @@ class ShardedEmbedding:
 
     @classmethod
     def create(cls, rows: Sequence[int], D: int, B_local: int, P: int, rank: int, world: int, device,
-               group=None, seed: int = 51234) -> "ShardedEmbedding":
+               group=None, seed: int = 51234, idx_base: int = 0, dtype=None) -> "ShardedEmbedding":
         from .embedding import EmbeddingTables
         sh = TableSharding.build(rows, world)
         mine = sh.local[rank]
-        tables = EmbeddingTables([rows[k] for k in mine] or [1], D, B_local * world * P, device)
+        kw = {} if dtype is None else {"dtype": dtype}
+        tables = EmbeddingTables([rows[k] for k in mine] or [1], D, B_local * world * P, device, **kw)
         tables.init_uniform(seed + 7919 * rank)
+        fused_sort = world == 1      # single GPU: the sort rides in the lookup launch
         se = cls(rows, D, rank, world,
-                 lookup_fn=lambda idx, out, slot0: tables.lookup(idx, out, slot0),
+                 lookup_fn=lambda idx, out, slot0: tables.lookup(idx, out, slot0, idx_base, sort=fused_sort),
                  update_fn=lambda idx, g, lr, slot0, presorted=False: (
-                     tables.update_sorted(g, slot0, lr) if presorted else tables.bwd_sgd(idx, g, slot0, lr)),
+                     tables.update_sorted(g, slot0, lr) if presorted else tables.bwd_sgd(idx, g, slot0, lr, idx_base)),
                  group=group,
-                 sort_fn=lambda idx: tables.sort(idx, 0, side_stream=True))
+                 sort_fn=lambda idx: tables.sort(idx, idx_base, side_stream=True),
+                 idx_base=idx_base, lookup_sorts=fused_sort)
         se.tables = tables
         return se
 
@@ -350,14 +387,29 @@ class ShardedEmbedding:
         return _ShardedLookupFn.apply(anchor, self, idx_local)
 
     def sort_async(self) -> None:
-        """Start the index sort/dedup for this step's update on the side stream."""
+        """Start the index sort/dedup for this step's update on the side stream (nothing to do when
+        the lookup launch already produced it)."""
+        if self.presorted:
+            return
         if self.sort_fn is not None and len(self.local_ids):
             self.sort_fn(self.idx_owned)
+            self.presorted = True
 
-    def update(self, lr: float, presorted: bool = False) -> None:
+    def update(self, lr: float, presorted: Optional[bool] = None) -> None:
+        """Owner-side sparse SGD.  ``presorted`` defaults to whether this step's sort already ran
+        (fused lookup launch or `sort_async`)."""
         if len(self.local_ids) == 0:
             return
+        if presorted is None:
+            presorted = self.presorted
         self.update_fn(self.idx_owned, self.owned_grad, lr, self.slot0, presorted)
+        self.presorted = False
+
+    def close(self) -> None:
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+            self.scatter_plan = None
 
 
 class FlatGrads:

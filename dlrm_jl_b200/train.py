@@ -109,21 +109,24 @@ def custom_update_(opt: Descent, model: DLRMModel, T: torch.Tensor, telemetry: C
 def train_step(loss: LossWrapper, model: DLRMModel, opt: Descent, labels, dense, sparse,
                overlap_sort: bool = True) -> torch.Tensor:
     """One iteration of the loop body of ``train!`` (src/train/train.jl:215-237).
-    Returns the loss tensor (device); no host synchronisation happens here."""
+    Returns the loss tensor (device); no host synchronisation happens here.  Index base and range
+    checking travel in the loss wrapper's keywords (``wrap_loss(bce_loss, idx_base=1, check_indices=True)``)."""
     telemetry = loss.kw.get("cb", donothing)
     telemetry("start")
     for p in model.dense_parameters():
         p.grad = None
     l, T = loss(model, labels, dense, sparse, training=True)
-    if overlap_sort:
+    presorted = bool(getattr(T, "presorted", False))     # the lookup launch already sorted the indices
+    if overlap_sort and not presorted:
         # the dedup sort needs the indices only: run it beside the backward pass
         model.embeddings.sort(T.indices, T.idx_base, side_stream=True)
+        presorted = True
     l.backward()
     for mlp in (model.bottom_mlp, model.top_mlp):      # fused dense layers keep their gradients in buffers
         if hasattr(mlp, "bind_param_grads"):
             mlp.bind_param_grads()
     telemetry("grads_done")
-    custom_update_(opt, model, T, telemetry, presorted=overlap_sort)
+    custom_update_(opt, model, T, telemetry, presorted=presorted)
     telemetry("update_done")
     return l.detach()
 
@@ -131,11 +134,22 @@ def train_step(loss: LossWrapper, model: DLRMModel, opt: Descent, labels, dense,
 def train(loss: LossWrapper, model: DLRMModel, data: Iterable, opt: Descent, cb: Callable = lambda: None,
           maxiters: Optional[int] = None):
     """``train!(loss, model, data, opt; cb, maxiters)`` (src/train/train.jl:189-240).
-    ``data`` yields (labels, dense, sparse).  Returns dict(iteration_times [ns], losses)."""
+    ``data`` yields (labels, dense, sparse).  Returns dict(iteration_times [ns], losses).
+
+    If ``data`` carries an ``idx_base`` attribute (a :class:`~dlrm_jl_b200.loader.DACLoader` over a
+    reference-preprocessed file is 1-based) and the loss wrapper does not set one, it is adopted; the
+    first batch is always range-checked against the table sizes (the kernels are unchecked, like the
+    reference's ``@inbounds`` loops), so a base mismatch fails loudly instead of training on shifted rows."""
     losses: List[float] = []
     iteration_times: List[int] = []
     count = 0
+    if "idx_base" not in loss.kw and hasattr(data, "idx_base"):
+        loss.kw["idx_base"] = int(data.idx_base)
     for labels, dense, sparse in data:
+        if count == 0:
+            from .embedding import _as_index_tensor
+            model.embeddings.check_indices(
+                _as_index_tensor(sparse, model.embeddings.ntab, model.embeddings.device), loss.kw.get("idx_base", 0))
         start = time.perf_counter_ns()
         l = train_step(loss, model, opt, labels, dense, sparse)
         losses.append(float(l))  # the reference pushes the loss every iteration (:231); this syncs

@@ -54,6 +54,15 @@ int32_t dlrmb_abi_version(void);
 const char* dlrmb_last_error(void);
 /* Number of kernel launches issued by this library in this process (bench bookkeeping). */
 int64_t dlrmb_launch_count(void);
+/* Process-wide tuning / test switches, read by the launchers (never from the environment):
+ *   "interact_general" 1 = run the general tiled interaction kernels even for the specialised shapes
+ *   "update_two_launches" 1 = separate fix-up launch of the sparse update at every batch size
+ *   "update_tile" 4|8|16|32 = entries per lane group of the sparse update (0 = chosen per batch)
+ *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
+ *   "pdl" 0 = launch without programmatic dependent launch attributes
+ * Defaults are the measured-fastest configuration; unknown names return DLRMB_EINVAL. */
+int32_t dlrmb_set_option(const char* name, int64_t value);
+int32_t dlrmb_get_option(const char* name, int64_t* value);
 
 /* ---- table storage: replaces SimpleEmbedding{Static{D}}(data) on an `embedding_allocator`
  * array (src/model/model.jl:185-206, src/data/criteo.jl:413,490) and the CachedArrays-backed
@@ -87,6 +96,15 @@ int32_t dlrmb_tables_sync(dlrmb_tables* t);
 int32_t dlrmb_embedding_fwd(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
                             int32_t B, int32_t P, float* out, int32_t slots, int32_t slot0,
                             dlrmb_stream stream);
+
+/* Training-step form of the lookup: the same pooled output plus, in the same launch, the index
+ * sort / dedup that the sparse update of this batch needs (what dlrmb_embedding_sort computes; it
+ * depends on the indices only).  The reference builds its SparseIndexer dictionaries inside
+ * update! (src/train/train.jl:276-290); here that work rides in extra CTAs of the gather launch, so
+ * dlrmb_embedding_update_sorted can follow the backward pass directly. */
+int32_t dlrmb_embedding_fwd_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                 int32_t B, int32_t P, float* out, int32_t slots, int32_t slot0,
+                                 dlrmb_stream stream);
 
 /* ---- dot interaction: (dot::DotInteraction)(x, ys) and its rrule
  * (src/model/interact.jl:394-411, 438-447).  T is [B][F][d] with slot 0 = x.  If `x` is

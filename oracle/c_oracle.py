@@ -98,3 +98,10 @@ def sparse_sgd(tables: List[np.ndarray], idx, dT: np.ndarray, slot0: int, lr: fl
     slots = dT.shape[1]
     lib().oracle_sparse_sgd(_table_ptrs(tables), ntab, D, _p(ix), B, P, _p(dT), slots, slot0,
                             C.c_float(lr), nthreads or max_threads())
+
+
+def init_uniform(rows: int, D: int, seed: int, nthreads: int = 0) -> np.ndarray:
+    """[rows][D] table of U(-1/sqrt(rows), 1/sqrt(rows)) values, filled in parallel (CPU-arm setup)."""
+    t = np.empty((rows, D), dtype=np.float32)
+    lib().oracle_init_uniform(_p(t), C.c_int64(rows), D, C.c_uint64(seed), nthreads or max_threads())
+    return t

@@ -189,3 +189,25 @@ void oracle_sparse_sgd(float* const* tables, int ntab, int D, const int64_t* idx
         free(dict.vals);
     }
 }
+
+/* CPU-arm setup helper (not part of the timed path): fill a [rows][D] table with U(-1/sqrt(rows),
+ * 1/sqrt(rows)) values (ScaledUniform, src/model/model.jl:61-65; the reference threads its init the
+ * same way, :40-44) from a counter hash, in parallel, so that tables of tens of GB are ready in
+ * seconds. */
+static inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void oracle_init_uniform(float* table, int64_t rows, int D, uint64_t seed, int nthreads) {
+    const float scale = 1.0f / sqrtf((float)rows);
+    const int64_t n = rows * (int64_t)D;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t h = mix64(seed ^ mix64((uint64_t)i));
+        float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+        table[i] = (2.0f * u - 1.0f) * scale;
+    }
+}

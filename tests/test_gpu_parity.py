@@ -230,11 +230,25 @@ WARP_SHAPES = [  # (B, F, d): every compiled warp-per-sample specialisation, rag
 ]
 
 
+@pytest.fixture
+def lib_options():
+    """Set library switches for one test and restore the defaults afterwards."""
+    from dlrm_jl_b200 import _lib
+    touched = {}
+
+    def set_(name, value):
+        touched.setdefault(name, _lib.get_option(name))
+        _lib.set_option(name, value)
+    yield set_
+    for name, value in touched.items():
+        _lib.set_option(name, value)
+
+
 @pytest.mark.parametrize("B,F,d", WARP_SHAPES)
-def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypatch):
-    """The warp-per-sample kernels (csrc/interact_warp.cu: tensor-core 3xTF32 forward, FFMA2 forward,
-    FFMA2 backward) against the oracle and against the general tiled kernels (csrc/interact.cu) on the
-    same inputs.  Backward keeps the tiled kernel's summation order, so it must match bit for bit."""
+def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, lib_options):
+    """The warp-per-sample kernels (csrc/interact_warp.cu: tensor-core 3xTF32 forward, FFMA2 backward)
+    against the oracle and against the general tiled kernels (csrc/interact.cu) on the same inputs.
+    Backward keeps the tiled kernel's summation order, so it must match bit for bit."""
     from dlrm_jl_b200 import _lib
     from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
     assert _lib.load().dlrmb_interaction_has_warp_path(F, d) == 1
@@ -242,11 +256,8 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypat
     T = rng.standard_normal((B, F, d)).astype(np.float32)
     Td = torch.from_numpy(T).to(_dev())
     res = {}
-    for path in ("tiled", "ffma2", "warp"):
-        if path == "warp":      # default: tensor-core 3xTF32 forward, FFMA2 backward
-            monkeypatch.delenv("DLRMB_INTERACT", raising=False)
-        else:
-            monkeypatch.setenv("DLRMB_INTERACT", path)
+    for path in ("tiled", "warp"):
+        lib_options("interact_general", 1 if path == "tiled" else 0)
         outs = []
         for pad in (1, 16):
             w = interaction_width(F, d, pad)
@@ -260,10 +271,9 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypat
             dx, dT = interaction_bwd(torch.from_numpy(g).to(_dev()), Td, pad)
             outs.append((out.cpu().numpy(), dx.cpu().numpy(), dT.cpu().numpy(), g, w, pad))
         res[path] = outs
-    for (o_t, dx_t, dT_t, g, w, pad), (o_f, _, _, _, _, _), (o_w, dx_w, dT_w, _, _, _) in zip(
-            res["tiled"], res["ffma2"], res["warp"]):
+    for (o_t, dx_t, dT_t, g, w, pad), (o_w, dx_w, dT_w, _, _, _) in zip(res["tiled"], res["warp"]):
         ref = O.interaction_fwd(T, pad)
-        assert ref.shape == o_f.shape and O.rel_err(o_f, ref) < FWD_RTOL and np.array_equal(o_f[:, :d], T[:, 0])
+        assert ref.shape == o_t.shape and O.rel_err(o_t, ref) < FWD_RTOL and np.array_equal(o_t[:, :d], T[:, 0])
         # elementwise: the 3xTF32 tensor-core Gram stays within a few fp32 ulps of the dot products' scale
         scale = np.sqrt(float(d)) * 4.0
         assert np.max(np.abs(o_w - ref)) < 2e-6 * scale * max(1.0, float(np.max(np.abs(T))))
@@ -277,7 +287,7 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, monkeypat
 
 
 @pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (77, 27, 64), (33, 8, 16), (19, 11, 128)])
-def test_interaction_backward_scatter_matches_plain_backward(B, F, d, monkeypatch):
+def test_interaction_backward_scatter_matches_plain_backward(B, F, d, lib_options):
     """dlrmb_interaction_bwd_scatter with every destination in local memory: the rows land at
     base + (sample_offset + b) * stride + offset, bit-identical to the plain backward's dT rows
     (slot 0 is not scattered), for the warp-per-sample and the tiled kernels."""
@@ -290,10 +300,7 @@ def test_interaction_backward_scatter_matches_plain_backward(B, F, d, monkeypatc
     # two "owners": even tables in buffer A [B + 8][nA][d], odd tables in buffer B [B + 8][nB][d]
     owners = [[f for f in range(1, F) if f % 2 == 0], [f for f in range(1, F) if f % 2 == 1]]
     for path in ("tiled", None):
-        if path:
-            monkeypatch.setenv("DLRMB_INTERACT", path)
-        else:
-            monkeypatch.delenv("DLRMB_INTERACT", raising=False)
+        lib_options("interact_general", 1 if path else 0)
         bufs = [torch.full((B + 8, max(1, len(o)), d), -7.0, device=_dev()) for o in owners]
         dests = torch.zeros((F, 3), dtype=torch.int64)
         for buf, own in zip(bufs, owners):
@@ -397,18 +404,19 @@ def test_sparse_sgd_is_deterministic_and_matches_ordered_sum():
 
 
 @pytest.mark.parametrize("D", [4, 64, 128, 256, 512])
-def test_sparse_sgd_tail_fixup_equals_two_launch_fixup(D, monkeypatch):
-    """DLRM-sized batches finish the chunk-crossing runs in the tail of the tiles launch; large batches
-    (or DLRMB_UPDATE_TWO_LAUNCHES) use the separate fix-up kernel.  Same arithmetic order, same bits --
-    over several consecutive steps, so the in-kernel counters must re-arm correctly."""
+def test_sparse_sgd_inline_fixup_equals_two_launch_fixup(D, lib_options):
+    """DLRM-sized batches finish the chunk-crossing runs inside the tiles launch (the last CTA of each
+    table); large batches (or the "update_two_launches" switch) use the separate fix-up kernel.  Same
+    arithmetic order, same bits -- over several consecutive steps, so the in-kernel per-table counters
+    must re-arm correctly."""
     rng = np.random.default_rng(D)
     rows, B = [2, 3, 40, 50000, 1], 6000 + D
     tables = _rand_tables(rng, rows, D)
     idx = [np.minimum((rng.pareto(1.05, size=(B, 1)) * 1.0).astype(np.int64), r - 1) for r in rows]
     dT = (rng.standard_normal((B, len(rows), D)) * 0.01).astype(np.float32)
-    monkeypatch.delenv("DLRMB_UPDATE_TWO_LAUNCHES", raising=False)
+    lib_options("update_two_launches", 0)
     a = _run_update(tables, idx, dT, 0, 0.5, steps=4)
-    monkeypatch.setenv("DLRMB_UPDATE_TWO_LAUNCHES", "1")
+    lib_options("update_two_launches", 1)
     b = _run_update(tables, idx, dT, 0, 0.5, steps=4)
     ref = [tb.copy() for tb in tables]
     for _ in range(4):
@@ -809,3 +817,219 @@ def test_dense_bwd_act_bias_kernel_exact():
         _lib.check(lib.dlrmb_dense_bwd_act_bias(0, dyc.data_ptr(), None, B, N, dyc.data_ptr(), db2.data_ptr(),
                                                scratch.data_ptr(), int(torch.cuda.current_stream().cuda_stream)))
         assert torch.equal(dyc, dy) and torch.allclose(db2.double(), dy.double().sum(0), rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: fused lookup + sort launch, DefaultStrategy gradient, pooling / skew, index base,
+# Terabyte geometry
+# ------------------------------------------------------------------------------------------------
+def zipf_indices(rng, rows, size, alpha):
+    """inverse-CDF Zipf r = floor(((N^(1-a) - 1) u + 1)^(1/(1-a))) - 1, then a fixed
+    random relabelling of the row ids (multiplicative hash) so hot rows are spread over the table."""
+    u = rng.random(size)
+    r = np.floor(((float(rows) ** (1.0 - alpha) - 1.0) * u + 1.0) ** (1.0 / (1.0 - alpha))).astype(np.int64) - 1
+    r = np.clip(r, 0, rows - 1)
+    return (r * 2654435761 + 12345) % rows
+
+
+@pytest.mark.parametrize("B,P", [(1, 1), (5, 3), (2048, 1), (683, 3), (4096, 1), (100, 40), (4097, 1), (3000, 2)])
+@pytest.mark.parametrize("dtype,base", [(np.int32, 0), (np.int64, 1)])
+def test_lookup_sort_fused_launch_equals_separate_launches(B, P, dtype, base):
+    """dlrmb_embedding_fwd_sort (the sort rides in extra CTAs of the lookup launch for B*P <= 4096, two
+    launches above) == dlrmb_embedding_fwd + dlrmb_embedding_sort: pooled rows and the exported
+    dedup, bit for bit, and against the oracle."""
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    rng = np.random.default_rng(B * 7 + P)
+    rows, D = [3, 1000, 40_000_000, 513, 70000], 32
+    L = B * P
+    t = EmbeddingTables(rows, D, L, 0)
+    t.init_uniform(3)
+    idx = np.stack([rng.integers(0, r, size=(B, P)) for r in rows])
+    dev_idx = torch.from_numpy((idx + base).astype(dtype)).to(_dev())
+    T1 = torch.empty((B, 1 + len(rows), D), device=_dev())
+    T2 = torch.full((B, 1 + len(rows), D), -3.0, device=_dev())
+    t.lookup(dev_idx, T1, 1, base)
+    t.lookup(dev_idx, T2, 1, base, sort=True)
+    assert torch.equal(T1[:, 1:], T2[:, 1:]) and torch.all(T2[:, 0] == -3.0)
+    fused = [t.sort_dedup_export(k, L) for k in range(len(rows))]
+    t.sort(dev_idx, base)
+    for k in range(len(rows)):
+        sep = t.sort_dedup_export(k, L)
+        ref = O.sort_dedup(idx[k].reshape(-1))
+        for a, b, c in zip(fused[k], sep, ref):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
+    # the update consumes the fused launch's sort directly
+    dT = torch.randn((B, 1 + len(rows), D), device=_dev())
+    before = {k: t.table(k).clone() for k in (0, 1, 3)}
+    t.lookup(dev_idx, T2, 1, base, sort=True)
+    t.update_sorted(dT, 1, 0.25)
+    for k in (0, 1, 3):
+        ref = before[k].cpu().numpy()
+        O.sparse_sgd_update_fast(ref, idx[k], np.ascontiguousarray(dT[:, 1 + k].cpu().numpy()), 0.25)
+        assert O.rel_err(t.table(k).cpu().numpy(), ref) < SGD_RTOL
+    t.close()
+
+
+def test_dot_interaction_default_strategy_gradient_reaches_x():
+    """dot_interaction (src/model/interact.jl:503-513; DefaultStrategy) under autograd: the gradient of
+    x is dOut[:, :d] + (S T)[0] -- Zygote differentiates concat([X, Zflat]) -- and the ys get their Gram
+    rows.  Checked against the oracle pullback and against DotInteraction on the same inputs."""
+    from dlrm_jl_b200.interact import DotInteraction, dot_interaction, interaction_width
+    rng = np.random.default_rng(17)
+    for B, F, d in [(33, 8, 16), (20, 27, 64), (9, 5, 12)]:
+        Tn = rng.standard_normal((B, F, d)).astype(np.float32)
+        g = rng.standard_normal((B, interaction_width(F, d))).astype(np.float32)
+        x = torch.from_numpy(Tn[:, 0].copy()).to(_dev()).requires_grad_(True)
+        ys = [torch.from_numpy(Tn[:, f].copy()).to(_dev()).requires_grad_(True) for f in range(1, F)]
+        z = dot_interaction(x, ys)
+        z.backward(torch.from_numpy(g).to(_dev()))
+        dx_ref, dT_ref = O.interaction_bwd(g, Tn)
+        assert O.rel_err(z.detach().cpu().numpy(), O.interaction_fwd(Tn)) < FWD_RTOL
+        assert O.rel_err(x.grad.cpu().numpy(), dx_ref) < FWD_RTOL
+        assert not np.allclose(x.grad.cpu().numpy(), dT_ref[:, 0], atol=1e-3), "pass-through term must be present"
+        for f in range(1, F):
+            assert O.rel_err(ys[f - 1].grad.cpu().numpy(), dT_ref[:, f]) < FWD_RTOL
+        x2 = torch.from_numpy(Tn[:, 0].copy()).to(_dev()).requires_grad_(True)
+        T2 = torch.from_numpy(Tn).to(_dev()).requires_grad_(True)
+        DotInteraction()(x2, T2).backward(torch.from_numpy(g).to(_dev()))
+        assert torch.equal(x2.grad, x.grad)
+
+
+@pytest.mark.parametrize("D", [16, 64, 128])
+@pytest.mark.parametrize("B,P,alpha", [(512, 4, 0.0), (64, 64, 0.0), (2048, 4, 1.05), (256, 64, 1.2), (2048, 1, 1.2),
+                                       (6000, 16, 1.2)])
+def test_sparse_sgd_pooling_and_zipf_skew_vs_oracle(D, B, P, alpha):
+    """Pooling factors 4 / 16 / 64 (BASELINE config 5) and Zipf-skewed indices (alpha 1.05, 1.2): tables
+    after three SGD steps against the oracle, run-to-run bit-reproducible, untouched rows untouched."""
+    rng = np.random.default_rng(D * 3 + B + P)
+    rows = [100000, 50, 3, 1000003]
+    tables = _rand_tables(rng, rows, D)
+    idx = [(zipf_indices(rng, r, (B, P), alpha) if alpha > 0 else rng.integers(0, r, size=(B, P))) for r in rows]
+    dT = (rng.standard_normal((B, 1 + len(rows), D)) * 0.05).astype(np.float32)
+    got = _run_update(tables, idx, dT, 1, 0.1, steps=3)
+    again = _run_update(tables, idx, dT, 1, 0.1, steps=3)
+    ref = [tb.copy() for tb in tables]
+    for _ in range(3):
+        for k in range(len(rows)):
+            O.sparse_sgd_update_fast(ref[k], idx[k], np.ascontiguousarray(dT[:, 1 + k]), 0.1)
+    for k in range(len(rows)):
+        assert np.array_equal(got[k], again[k]), "bitwise reproducible"
+        assert O.rel_err(got[k], ref[k]) < SGD_RTOL, k
+        untouched = np.setdiff1d(np.arange(rows[k]), np.unique(idx[k]))
+        assert np.array_equal(got[k][untouched], tables[k][untouched])
+
+
+def test_lookup_pooling_64_and_zipf_bit_exact():
+    from dlrm_jl_b200.embedding import PreallocationStrategy, maplookup
+    rng = np.random.default_rng(64)
+    rows, D = [100000, 7, 5000], 128
+    tables = _rand_tables(rng, rows, D)
+    for B, P, alpha in [(128, 64, 1.2), (300, 16, 1.05), (2048, 4, 1.2)]:
+        idx = [zipf_indices(rng, r, (B, P), alpha) for r in rows]
+        t = _tables(tables, B * P)
+        T = maplookup(PreallocationStrategy(D), t, idx).cpu().numpy()
+        assert np.array_equal(T, O.lookup(tables, idx, slot0=1)), (B, P, alpha)
+        t.close()
+
+
+def test_one_based_reference_format_batches_train_on_the_right_rows():
+    """Reference-preprocessed data is 1-based (src/data/criteo.jl:249-253).  A DACLoader over such
+    records carries idx_base = 1, `train` adopts it and range-checks the first batch; the resulting
+    tables equal the oracle run on the 0-based ids, and a 0-based interpretation of the same file is
+    refused (DLRMB_EOOB) instead of training on rows shifted by one."""
+    from dlrm_jl_b200 import DLRMB200Error
+    from dlrm_jl_b200.embedding import Descent
+    from dlrm_jl_b200.loader import DAC_DTYPE, DACLoader
+    from dlrm_jl_b200.model import kaggle_dlrm
+    from dlrm_jl_b200.train import bce_loss, train, wrap_loss
+    rows = [50, 3, 57, 1000, 24, 5000, 10, 7] + [11 + k for k in range(18)]
+    rng = np.random.default_rng(12)
+    n, B = 256, 64
+    data = np.zeros(n, dtype=DAC_DTYPE)
+    data["label"] = rng.integers(0, 2, size=n)
+    data["continuous"] = rng.random((n, 13), dtype=np.float32)
+    ids0 = np.stack([rng.integers(0, r, size=n) for r in rows], axis=1)
+    ids0[0, :] = np.asarray(rows) - 1                      # the largest legal id of every table is present
+    data["categorical"] = (ids0 + 1).astype(np.uint32)     # 1-based on disk
+    model = kaggle_dlrm(feature_size=16, max_lookups=B, device=0, embedding_sizes=rows)
+    start = [model.embeddings.download(k) for k in range(26)]
+    loader = DACLoader(data, B, 0)
+    assert loader.idx_base == 1
+    out = train(wrap_loss(bce_loss), model, loader, Descent(0.5), maxiters=2)
+    assert len(out["losses"]) == 2 and np.isfinite(out["losses"]).all()
+    for k in (0, 1, 3):
+        got = model.embeddings.download(k)
+        touched = np.unique(ids0[:2 * B, k])
+        untouched = np.setdiff1d(np.arange(rows[k]), touched)
+        assert np.array_equal(got[untouched], start[k][untouched])
+        assert not np.array_equal(got[touched], start[k][touched])
+    model0 = kaggle_dlrm(feature_size=16, max_lookups=B, device=0, embedding_sizes=rows)
+    with pytest.raises(DLRMB200Error, match="DLRMB_EOOB"):
+        train(wrap_loss(bce_loss), model0, DACLoader(data, B, 0, idx_base=0), Descent(0.5), maxiters=1)
+
+
+def test_terabyte_shaped_properties():
+    """BASELINE config 4 geometry on one GPU: 26 tables with rows = min(TERABYTE_EMBEDDING_SIZES, 40M)
+    (src/data/criteo.jl:379-406), D = 128 (104.5 GB of fp32 tables), B = 2048.  Size-independent
+    properties: lookup == rows of the zero-copy views, idempotence, sortedness / permutation, the update's
+    checksum of checksums, and the inverse step restoring the tables."""
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
+    from dlrm_jl_b200.model import TERABYTE_EMBEDDING_SIZES
+    free, _total = torch.cuda.mem_get_info()
+    ROWS = [min(r, 40_000_000) for r in TERABYTE_EMBEDDING_SIZES]
+    D, B = 128, 2048
+    if free < sum(ROWS) * D * 4 + (8 << 30):
+        pytest.skip("needs ~113 GB of free HBM")
+    t = EmbeddingTables(ROWS, D, B, 0)
+    t.init_uniform(7)
+    rng = np.random.default_rng(20261018)
+    idx_np = np.stack([rng.integers(0, r, size=B) for r in ROWS]).astype(np.int32)
+    idx_np[:, 0] = np.asarray(ROWS) - 1                     # the last row of every table (40M - 1 included)
+    idx_np[:, 1] = 0
+    idx = torch.from_numpy(idx_np).to(_dev()).unsqueeze(-1)
+    T = torch.zeros((B, 27, D), device=_dev())
+    T2 = torch.zeros((B, 27, D), device=_dev())
+    t.lookup(idx, T, 1, sort=True)
+    t.lookup(idx, T2, 1)
+    assert torch.equal(T, T2)
+    for k in range(26):
+        assert torch.equal(T[:, 1 + k], t.table(k)[idx[k, :, 0].long()])
+    for k in (0, 5, 9, 19, 25):
+        uniq, seg, perm = t.sort_dedup_export(k, B)
+        keys = idx_np[k][perm]
+        assert np.all(np.diff(keys) >= 0) and np.array_equal(np.sort(perm), np.arange(B))
+        assert np.array_equal(uniq, np.unique(idx_np[k])) and seg[-1] == B
+        u_ref, s_ref, p_ref = O.sort_dedup(idx_np[k])
+        assert np.array_equal(perm, p_ref) and np.array_equal(seg, s_ref)
+    # interaction at this geometry against the oracle on a slice of the batch
+    T[:, 0] = torch.randn((B, D), device=_dev())
+    z = interaction_fwd(T)
+    g = torch.randn((B, interaction_width(27, D)), device=_dev())
+    dx, dT = interaction_bwd(g, T)
+    sl = slice(0, 64)
+    Tn = T[sl].cpu().numpy()
+    assert O.rel_err(z[sl].cpu().numpy(), O.interaction_fwd(Tn)) < FWD_RTOL
+    dx_ref, dT_ref = O.interaction_bwd(g[sl].cpu().numpy(), Tn)
+    assert O.rel_err(dT[sl].cpu().numpy(), dT_ref) < FWD_RTOL and O.rel_err(dx[sl].cpu().numpy(), dx_ref) < FWD_RTOL
+    # update: per-table column checksums move by -lr * the column sums of the deltas
+    snap_rows = {k: t.table(k)[idx[k, :, 0].long()].clone() for k in (0, 5, 20)}
+    before = {k: t.table(k)[idx[k, :, 0].long().unique()].double().sum(dim=0) for k in range(26)}
+    t.update_sorted(dT, 1, 0.1)
+    for k in range(26):
+        after = t.table(k)[idx[k, :, 0].long().unique()].double().sum(dim=0)
+        want = -0.1 * dT[:, 1 + k].double().sum(dim=0)
+        assert torch.allclose(after - before[k], want, rtol=1e-4, atol=1e-5), k
+    # oracle on the touched rows of three tables (a 3-row table, and two 40M-row tables)
+    for k in (0, 5, 20):
+        rows_k, first_idx, inv = np.unique(idx_np[k], return_index=True, return_inverse=True)
+        sub = t.table(k)[torch.from_numpy(rows_k).to(_dev()).long()].cpu().numpy()
+        ref = snap_rows[k].cpu().numpy()[first_idx].copy()          # the touched rows before the update, compacted
+        O.sparse_sgd_update_fast(ref, inv.reshape(-1, 1), np.ascontiguousarray(dT[:, 1 + k].cpu().numpy()), 0.1)
+        assert O.rel_err(sub, ref) < SGD_RTOL, k
+    # inverse step restores the touched rows to rounding error
+    t.lookup(idx, T2, 1, sort=True)
+    t.update_sorted(dT, 1, -0.1)
+    for k, s in snap_rows.items():
+        assert torch.allclose(t.table(k)[idx[k, :, 0].long()], s, rtol=0, atol=1e-5), k
+    t.close()

@@ -11,9 +11,9 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdlrm_b200.so")
 
-OK, EINVAL, ECUDA, ENOMEM, EOOB, ESTATE = 0, 1, 2, 3, 4, 5
+OK, EINVAL, ECUDA, ENOMEM, EOOB, ESTATE, ENCCL = 0, 1, 2, 3, 4, 5, 6
 _STATUS_NAMES = {EINVAL: "DLRMB_EINVAL", ECUDA: "DLRMB_ECUDA", ENOMEM: "DLRMB_ENOMEM",
-                 EOOB: "DLRMB_EOOB", ESTATE: "DLRMB_ESTATE"}
+                 EOOB: "DLRMB_EOOB", ESTATE: "DLRMB_ESTATE", ENCCL: "DLRMB_ENCCL"}
 
 
 class DLRMB200Error(RuntimeError):
@@ -35,6 +35,7 @@ SIGNATURES = {
     "dlrmb_tables_create": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, C.POINTER(_vp)]),
     "dlrmb_tables_create_ex": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, _i32, C.POINTER(_vp)]),
     "dlrmb_tables_elem_bytes": (_i32, [_vp]),
+    "dlrmb_tables_reserve": (_i32, [_vp, _i64]),
     "dlrmb_tables_destroy": (_i32, [_vp]),
     "dlrmb_tables_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
     "dlrmb_tables_upload": (_i32, [_vp, _i32, _vp]),
@@ -66,6 +67,16 @@ SIGNATURES = {
     "dlrmb_dense_bwd_act_bias": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dlrmb_interaction_bwd_scatter": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "dlrmb_dac_unpack": (_i32, [_i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "dlrmb_shard_plan": (_i32, [_i32, C.POINTER(_i64), _i32, C.POINTER(_i32)]),
+    "dlrmb_comm_unique_id": (_i32, [_vp]),
+    "dlrmb_comm_create": (_i32, [_i32, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "dlrmb_comm_destroy": (_i32, [_vp]),
+    "dlrmb_comm_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    "dlrmb_comm_a2a_indices": (_i32, [_vp, C.POINTER(_i32), _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "dlrmb_comm_a2a_fwd": (_i32, [_vp, C.POINTER(_i32), _i32, _vp, _i32, _i32, _vp, _vp]),
+    "dlrmb_comm_a2a_bwd": (_i32, [_vp, C.POINTER(_i32), _i32, _vp, _i32, _i32, _vp, _vp]),
+    "dlrmb_comm_allreduce_f32": (_i32, [_vp, _vp, _i64, _vp]),
+    "dlrmb_comm_allgather": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "dlrmb_embedding_fwd_host": (_i32, [_vp, *_idx_args, _vp, _i32, _i32]),
     "dlrmb_interaction_fwd_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "dlrmb_interaction_bwd_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -50,6 +50,56 @@ static int grow(void** p, size_t* have, size_t need) {
 
 using namespace dlrmb;
 
+// sort / update workspaces, sized for `max_lookups` = max B*P per table (nothing else in the library
+// allocates per call)
+static void free_workspace(dlrmb_tables* t) {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(t->keys[i]);
+        cudaFree(t->pos[i]);
+        t->keys[i] = t->pos[i] = nullptr;
+    }
+    cudaFree(t->tile_hist);
+    cudaFree(t->digit_total);
+    cudaFree(t->partial);
+    cudaFree(t->tile_flags);
+    cudaFree(t->head_list);
+    cudaFree(t->head_count);
+    cudaFree(t->d_seg);
+    cudaFree(t->d_uniq);
+    cudaFree(t->d_nuniq);
+    t->tile_hist = t->digit_total = t->head_list = t->head_count = nullptr;
+    t->partial = nullptr;
+    t->tile_flags = nullptr;
+    t->d_seg = nullptr;
+    t->d_uniq = nullptr;
+    t->d_nuniq = nullptr;
+    t->sorted_valid = false;
+}
+
+static int alloc_workspace(dlrmb_tables* t, int64_t max_lookups) {
+    const int ntab = t->ntab;
+    t->max_lookups = max_lookups;
+    t->cap = (max_lookups + 3) / 4 * 4;
+    size_t nl = (size_t)ntab * (size_t)t->cap + 8;
+    for (int i = 0; i < 2; ++i) {
+        DLRMB_CUDA(cudaMalloc((void**)&t->keys[i], sizeof(uint32_t) * nl));
+        DLRMB_CUDA(cudaMalloc((void**)&t->pos[i], sizeof(uint32_t) * nl));
+    }
+    t->radix_tiles_cap = ceil_div64(max_lookups, 4096);
+    DLRMB_CUDA(cudaMalloc((void**)&t->tile_hist, sizeof(uint32_t) * (size_t)ntab * 512 * (size_t)t->radix_tiles_cap));
+    DLRMB_CUDA(cudaMalloc((void**)&t->digit_total, sizeof(uint32_t) * (size_t)ntab * 512));
+    t->partial_tiles_cap = update_tiles_cap(ntab, t->D, max_lookups, t->sm_count);
+    DLRMB_CUDA(cudaMalloc((void**)&t->partial, sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)t->D));
+    DLRMB_CUDA(cudaMalloc((void**)&t->tile_flags, (size_t)ntab * (size_t)t->partial_tiles_cap));
+    DLRMB_CUDA(cudaMalloc((void**)&t->head_list, sizeof(uint32_t) * (size_t)ntab * (size_t)t->partial_tiles_cap));
+    DLRMB_CUDA(cudaMalloc((void**)&t->head_count, (1 + (size_t)ntab) * sizeof(uint32_t)));   // listed heads; CTAs done per table
+    DLRMB_CUDA(cudaMemset(t->head_count, 0, (1 + (size_t)ntab) * sizeof(uint32_t)));
+    DLRMB_CUDA(cudaMalloc((void**)&t->d_seg, sizeof(int32_t) * ((size_t)max_lookups + 1)));
+    DLRMB_CUDA(cudaMalloc((void**)&t->d_uniq, sizeof(int64_t) * (size_t)max_lookups));
+    DLRMB_CUDA(cudaMalloc((void**)&t->d_nuniq, sizeof(int32_t)));
+    return DLRMB_OK;
+}
+
 #define GUARD(t)                                                     \
     DLRMB_REQUIRE((t) != nullptr, "null tables handle");             \
     DeviceGuard _guard((t)->device);                                 \
@@ -157,25 +207,10 @@ int32_t dlrmb_tables_create_ex(int32_t device, int32_t ntab, const int64_t* rows
         free(h);
         TRY_CUDA(e);
     }
-    size_t nl = (size_t)ntab * (size_t)t->cap + 8;
-    for (int i = 0; i < 2; ++i) {
-        TRY_CUDA(cudaMalloc((void**)&t->keys[i], sizeof(uint32_t) * nl));
-        TRY_CUDA(cudaMalloc((void**)&t->pos[i], sizeof(uint32_t) * nl));
+    {
+        int rc = alloc_workspace(t, max_lookups);
+        if (rc) return fail(rc);
     }
-    t->radix_tiles_cap = ceil_div64(max_lookups, 4096);
-    TRY_CUDA(cudaMalloc((void**)&t->tile_hist,
-                        sizeof(uint32_t) * (size_t)ntab * 512 * (size_t)t->radix_tiles_cap));
-    TRY_CUDA(cudaMalloc((void**)&t->digit_total, sizeof(uint32_t) * (size_t)ntab * 512));
-    t->partial_tiles_cap = update_tiles_cap(ntab, D, max_lookups, t->sm_count);
-    TRY_CUDA(cudaMalloc((void**)&t->partial,
-                        sizeof(float) * (size_t)ntab * (size_t)t->partial_tiles_cap * 2 * (size_t)D));
-    TRY_CUDA(cudaMalloc((void**)&t->tile_flags, (size_t)ntab * (size_t)t->partial_tiles_cap));
-    TRY_CUDA(cudaMalloc((void**)&t->head_list, sizeof(uint32_t) * (size_t)ntab * (size_t)t->partial_tiles_cap));
-    TRY_CUDA(cudaMalloc((void**)&t->head_count, (1 + (size_t)ntab) * sizeof(uint32_t)));   // listed heads; CTAs done per table
-    TRY_CUDA(cudaMemset(t->head_count, 0, (1 + (size_t)ntab) * sizeof(uint32_t)));
-    TRY_CUDA(cudaMalloc((void**)&t->d_seg, sizeof(int32_t) * ((size_t)max_lookups + 1)));
-    TRY_CUDA(cudaMalloc((void**)&t->d_uniq, sizeof(int64_t) * (size_t)max_lookups));
-    TRY_CUDA(cudaMalloc((void**)&t->d_nuniq, sizeof(int32_t)));
 #undef TRY_CUDA
     *out = t;
     return DLRMB_OK;
@@ -188,19 +223,7 @@ int32_t dlrmb_tables_destroy(dlrmb_tables* t) {
     cudaFree(t->slab);
     cudaFree(t->d_desc);
     cudaFree(t->d_slotmap);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(t->keys[i]);
-        cudaFree(t->pos[i]);
-    }
-    cudaFree(t->tile_hist);
-    cudaFree(t->digit_total);
-    cudaFree(t->partial);
-    cudaFree(t->tile_flags);
-    cudaFree(t->head_list);
-    cudaFree(t->head_count);
-    cudaFree(t->d_seg);
-    cudaFree(t->d_uniq);
-    cudaFree(t->d_nuniq);
+    free_workspace(t);
     cudaFree(t->stage_idx);
     cudaFree(t->stage_a);
     cudaFree(t->stage_b);
@@ -223,6 +246,16 @@ int32_t dlrmb_tables_info(const dlrmb_tables* t, int32_t* ntab, int32_t* D, int6
     if (max_lookups) *max_lookups = t->max_lookups;
     if (total_rows) *total_rows = t->total_rows;
     return DLRMB_OK;
+}
+
+int32_t dlrmb_tables_reserve(dlrmb_tables* t, int64_t max_lookups) {
+    GUARD(t);
+    DLRMB_REQUIRE(max_lookups > 0 && max_lookups < (1ll << 30), "max_lookups must be in 1..2^30 (got %lld)",
+                  (long long)max_lookups);
+    if (max_lookups <= t->max_lookups) return DLRMB_OK;
+    DLRMB_CUDA(cudaDeviceSynchronize());     // earlier launches may still use the old workspaces
+    free_workspace(t);
+    return alloc_workspace(t, max_lookups);
 }
 
 static inline char* table_ptr(dlrmb_tables* t, int k) {

@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB_DIR = os.path.join(os.path.dirname(HERE), "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdlrm_b200.so")
-SOURCES = ["api.cu", "lookup.cu", "interact.cu", "interact_warp.cu", "sort.cu", "update.cu", "loss.cu", "dense.cu", "p2p.cu", "loader.cu"]
-HEADERS = [os.path.join(HERE, "common.cuh"), os.path.join(ROOT, "include", "dlrm_b200.h")]
+SOURCES = ["api.cu", "lookup.cu", "interact.cu", "interact_warp.cu", "sort.cu", "update.cu", "loss.cu", "dense.cu", "p2p.cu", "loader.cu", "comm.cu"]
+HEADERS = [os.path.join(HERE, "common.cuh"), os.path.join(HERE, "sort_small.cuh"), os.path.join(ROOT, "include", "dlrm_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
     return LIB_PATH
 

@@ -45,7 +45,8 @@ typedef enum dlrmb_status {
     DLRMB_ECUDA = 2,  /* CUDA runtime failure; message carries cudaGetErrorString */
     DLRMB_ENOMEM = 3, /* device allocation failed */
     DLRMB_EOOB = 4,   /* dlrmb_check_indices found an index outside [base, rows+base) */
-    DLRMB_ESTATE = 5  /* call order violated (e.g. update_sorted without a sort) */
+    DLRMB_ESTATE = 5, /* call order violated (e.g. update_sorted without a sort) */
+    DLRMB_ENCCL = 6   /* NCCL failure, or libnccl.so.2 could not be loaded (dlrmb_comm_* only) */
 } dlrmb_status;
 
 #define DLRMB_ABI_VERSION 1
@@ -76,6 +77,11 @@ int32_t dlrmb_tables_create(int32_t device, int32_t ntab, const int64_t* rows, i
 int32_t dlrmb_tables_create_ex(int32_t device, int32_t ntab, const int64_t* rows, int32_t D,
                                int64_t max_lookups, int32_t elem_bytes, dlrmb_tables** out);
 int32_t dlrmb_tables_elem_bytes(const dlrmb_tables* t);
+/* Grow the sort / update workspaces to serve batches of up to `max_lookups` = B*P lookups per table
+ * (no-op when already large enough).  The tables themselves are untouched.  Synchronises the device;
+ * meant for the first batch of a run, when a host that builds its tables before it knows the batch
+ * size (DLRM.jl's `dlrm(...)` constructor) learns it. */
+int32_t dlrmb_tables_reserve(dlrmb_tables* t, int64_t max_lookups);
 int32_t dlrmb_tables_destroy(dlrmb_tables* t);
 int32_t dlrmb_tables_info(const dlrmb_tables* t, int32_t* ntab, int32_t* D, int64_t* max_lookups,
                           int64_t* total_rows);
@@ -216,6 +222,39 @@ int32_t dlrmb_interaction_bwd_scatter(int32_t device, const float* dOut, const f
                                       int32_t F, int32_t d, int32_t pad_to_mul,
                                       const dlrmb_slot_dest* dests, int64_t sample_offset, float* dx,
                                       dlrmb_stream stream);
+
+/* ---- collectives of the sharded path (new functionality; one process per GPU, NCCL over NVLink).
+ * A non-Python host runs BASELINE config 4 with these: rank 0 calls dlrmb_comm_unique_id, carries the 128
+ * bytes to the other ranks (file, socket, MPI ...), every rank calls dlrmb_comm_create.  Calls are
+ * stream-ordered and must be issued in the same order on every rank.  NCCL is bound at run time
+ * (libnccl.so.2 via dlopen), so single-GPU users do not need it.  `owner` is the host array [ntab] of
+ * dlrmb_shard_plan (rank owning each table: table count balanced first, bytes second, the big tables
+ * on different GPUs); B_global = B_local * world, sample b of the global batch belongs to rank
+ * b / B_local.
+ *   dlrmb_comm_a2a_indices   idx_local [ntab][B_local][P]  ->  idx_owned [t_mine][B_global][P]
+ *   dlrmb_comm_a2a_fwd       pooled [B_global][t_mine][D] (dlrmb_embedding_fwd with slot0 = 0 on the owner)
+ *                            ->  T [B_local][1 + ntab][D], slot 1 + k for table k (slot 0 is left for x)
+ *   dlrmb_comm_a2a_bwd       dT [B_local][1 + ntab][D]  ->  grads [B_global][t_mine][D] on each owner
+ *                            (then dlrmb_embedding_bwd_sgd with slot0 = 0)
+ *   dlrmb_comm_allreduce_f32 in-place sum of the data-parallel dense gradients
+ *   dlrmb_comm_allgather     nbytes per rank, device buffers (e.g. the 64-byte dlrmb_xbuf IPC handles that
+ *                            set up the fused peer-store exchanges above)
+ * The first a2a call sizes a staging buffer (cudaMalloc); later calls with the same geometry do not
+ * allocate and can be captured into a CUDA graph. */
+typedef struct dlrmb_comm dlrmb_comm;
+int32_t dlrmb_shard_plan(int32_t ntab, const int64_t* rows, int32_t world, int32_t* owner);
+int32_t dlrmb_comm_unique_id(uint8_t* id128);
+int32_t dlrmb_comm_create(int32_t device, const uint8_t* id128, int32_t rank, int32_t world, dlrmb_comm** out);
+int32_t dlrmb_comm_destroy(dlrmb_comm* c);
+int32_t dlrmb_comm_info(const dlrmb_comm* c, int32_t* rank, int32_t* world);
+int32_t dlrmb_comm_a2a_indices(dlrmb_comm* c, const int32_t* owner, int32_t ntab, const void* idx_local,
+                               int32_t idx_bytes, int32_t B_local, int32_t P, void* idx_owned, dlrmb_stream stream);
+int32_t dlrmb_comm_a2a_fwd(dlrmb_comm* c, const int32_t* owner, int32_t ntab, const float* pooled, int32_t B_local,
+                           int32_t D, float* T, dlrmb_stream stream);
+int32_t dlrmb_comm_a2a_bwd(dlrmb_comm* c, const int32_t* owner, int32_t ntab, const float* dT, int32_t B_local,
+                           int32_t D, float* grads, dlrmb_stream stream);
+int32_t dlrmb_comm_allreduce_f32(dlrmb_comm* c, float* buf, int64_t n, dlrmb_stream stream);
+int32_t dlrmb_comm_allgather(dlrmb_comm* c, const void* send, void* recv, int64_t nbytes, dlrmb_stream stream);
 
 /* ---- host-buffer entry points: every pointer is host memory (pageable or pinned); this is
  * the form a CPU-resident DLRM.jl model calls.  Copies run inside the call. -------------- */

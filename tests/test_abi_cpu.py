@@ -52,8 +52,24 @@ def test_julia_glue_and_integration_guide_only_name_exported_symbols(built_lib):
         used = {u for u in used if not u.endswith("_")}
         unknown = sorted(u for u in used if u not in declared and not any(d.startswith(u) for d in declared))
         assert not unknown, f"{rel} names symbols the header does not declare: {unknown}"
-    for n in re.findall(r"ccall\(\(:(dlrmb_[a-z0-9_]+),", open(os.path.join(ROOT, "julia/DLRMB200.jl")).read()):
+    jl = open(os.path.join(ROOT, "julia/DLRMB200.jl")).read()
+    for n in re.findall(r"ccall\(\(:(dlrmb_[a-z0-9_]+),", jl):
         assert hasattr(lib, n), n
+    # every ccall passes as many argument types as the C prototype (= the ctypes binding) has parameters
+    from dlrm_jl_b200 import _lib as _binding
+    calls = re.findall(r"ccall\(\(:(dlrmb_[a-z0-9_]+), libdlrm_b200\), (\w+),\s*\(([^()]*)\)", jl)
+    assert len(calls) >= 12
+    for name, ret, types in calls:
+        n_types = len([t for t in types.split(",") if t.strip()])
+        assert n_types == len(_binding.SIGNATURES[name][1]), (name, n_types)
+        assert ret in ("Int32", "Cstring"), (name, ret)
+    # the glue extends the reference's own functions for the B200 table type (not private look-alikes)
+    for needle in ("function EmbeddingTables.maplookup(strategy::PreallocationStrategy, tables::AbstractVector{<:B200Embedding}",
+                   "function EmbeddingTables.update!(opt::Flux.Descent, tables::AbstractVector{<:B200Embedding}",
+                   "struct B200Embedding{S,T} <: AbstractEmbeddingTable{S,T}",
+                   "ChainRulesCore.rrule(::typeof(EmbeddingTables.maplookup)",
+                   "SparseEmbeddingUpdate{Static{D}}(", "Base.isapprox(a::AbstractMatrix, t::B200Embedding"):
+        assert needle in jl, needle
     from dlrm_jl_b200 import _lib
     L = _lib.load()
     assert L.dlrmb_interaction_has_warp_path(27, 128) == 1 and L.dlrmb_interaction_has_warp_path(5, 12) == 0

@@ -1033,3 +1033,49 @@ def test_terabyte_shaped_properties():
     for k, s in snap_rows.items():
         assert torch.allclose(t.table(k)[idx[k, :, 0].long()], s, rtol=0, atol=1e-5), k
     t.close()
+
+
+def test_comm_c_abi_world_one_round_trip():
+    """The dlrmb_comm_* entry points (NCCL behind the C ABI) with a one-rank communicator: the exchanges
+    degenerate to sends to self, which still run the real NCCL group calls and the pack / unpack kernels.
+    (The multi-rank behaviour is exercised on 2+ GPUs by benchmarks/cabi_sharded_step.py.)"""
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    lib = _lib.load()
+    dev = _dev()
+    rows = (C.c_int64 * 5)(50, 4000, 7, 4000, 900)
+    owner = (C.c_int32 * 5)()
+    _lib.check(lib.dlrmb_shard_plan(5, rows, 2, owner))
+    assert sorted(list(owner)) == [0, 0, 1, 1, 1] or sorted(list(owner)) == [0, 0, 0, 1, 1]
+    assert owner[1] != owner[3]                                  # the two big tables on different ranks
+    _lib.check(lib.dlrmb_shard_plan(5, rows, 1, owner))
+    assert list(owner) == [0] * 5
+    uid = (C.c_uint8 * 128)()
+    _lib.check(lib.dlrmb_comm_unique_id(uid))
+    h = C.c_void_p()
+    _lib.check(lib.dlrmb_comm_create(0, uid, 0, 1, C.byref(h)))
+    r, w = C.c_int32(-1), C.c_int32(-1)
+    _lib.check(lib.dlrmb_comm_info(h, C.byref(r), C.byref(w)))
+    assert (r.value, w.value) == (0, 1)
+    s = int(torch.cuda.current_stream().cuda_stream)
+    B, P, D, ntab = 24, 3, 32, 5
+    idx = torch.randint(0, 1000, (ntab, B, P), device=dev, dtype=torch.int64)
+    idx_owned = torch.zeros_like(idx)
+    _lib.check(lib.dlrmb_comm_a2a_indices(h, owner, ntab, idx.data_ptr(), 8, B, P, idx_owned.data_ptr(), s))
+    assert torch.equal(idx_owned, idx)
+    pooled = torch.randn((B, ntab, D), device=dev)
+    T = torch.full((B, 1 + ntab, D), -1.0, device=dev)
+    _lib.check(lib.dlrmb_comm_a2a_fwd(h, owner, ntab, pooled.data_ptr(), B, D, T.data_ptr(), s))
+    assert torch.equal(T[:, 1:], pooled) and torch.all(T[:, 0] == -1.0)
+    grads = torch.zeros((B, ntab, D), device=dev)
+    _lib.check(lib.dlrmb_comm_a2a_bwd(h, owner, ntab, T.data_ptr(), B, D, grads.data_ptr(), s))
+    assert torch.equal(grads, pooled)
+    buf = torch.arange(1000, device=dev, dtype=torch.float32)
+    _lib.check(lib.dlrmb_comm_allreduce_f32(h, buf.data_ptr(), 1000, s))
+    assert torch.equal(buf, torch.arange(1000, device=dev, dtype=torch.float32))
+    blob = torch.arange(64, device=dev, dtype=torch.uint8)
+    out = torch.zeros(64, device=dev, dtype=torch.uint8)
+    _lib.check(lib.dlrmb_comm_allgather(h, blob.data_ptr(), out.data_ptr(), 64, s))
+    assert torch.equal(out, blob)
+    torch.cuda.synchronize()
+    _lib.check(lib.dlrmb_comm_destroy(h))

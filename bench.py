@@ -378,15 +378,17 @@ def run_ours(args):
         if args.exchange == "p2p":
             ok, why = 1.0, ""
             try:
-                se.enable_peer_exchange(B)
+                se.enable_peer_exchange(B, flag_barrier=(args.barrier == "flags"), P=wl["P"], idx_bytes=4)
                 se.enable_fused_backward(B)
             except Exception as exc:  # noqa: BLE001 - e.g. CUDA IPC not permitted in this container
                 ok, why = 0.0, f"{type(exc).__name__}: {exc}"
             flag = torch.tensor([ok], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank takes the same decision
             if float(flag.item()) == 1.0:
-                exchange = ("fused over NVLink peer stores: lookup -> peers' interaction inputs (forward), "
-                            "interaction backward -> owners' gradient buffers (backward)")
+                exchange = ("fused over NVLink peer stores: index columns -> owners' index buffers, lookup -> peers' "
+                            "interaction inputs (forward), interaction backward -> owners' gradient buffers (backward); ordering: "
+                            + ("flag barrier over the mapped buffers (dlrmb_peer_barrier, one tiny kernel per exchange)"
+                               if args.barrier == "flags" else "one-element NCCL all-reduce per exchange"))
             else:
                 se.peer = None
                 se.scatter_plan = None
@@ -418,6 +420,20 @@ def run_ours(args):
         bottom_f, top_f = bottom, top_logits
 
     serial = {"on": False}      # profiling pass: every kernel of the step on ONE stream (no overlap between streams)
+    n_bottom = sum(p.numel() for p in bottom.parameters())
+    comm_stream_ = torch.cuda.Stream()
+    early = world > 1 and not args.late_allreduce
+
+    def allreduce_top_grads(g):
+        """Gradient hook on the interaction output: the top MLP's backward has been launched, so its 93 % of
+        the dense gradient bytes start their all-reduce now, beside the interaction backward, the gradient
+        exchange, the bottom MLP's backward and the sparse update."""
+        main = torch.cuda.current_stream()
+        comm = main if serial["on"] else comm_stream_
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            dist.all_reduce(flat.flat[n_bottom:], op=dist.ReduceOp.SUM)
+        return g
 
     def train_step(dense, labels, idx):
         main = torch.cuda.current_stream()
@@ -437,6 +453,8 @@ def run_ours(args):
         se.sort_async()
         main.wait_stream(mlp_stream)
         z = dot(x, T, scatter=se.scatter_plan) if fused else dot(x, T)
+        if early:
+            z.register_hook(allreduce_top_grads)
         loss = sigmoid_bce(top_f(z), labels)
         loss.backward()
         main.wait_stream(mlp_stream)
@@ -446,7 +464,11 @@ def run_ours(args):
         upd_stream.wait_stream(main)
         with torch.cuda.stream(upd_stream):
             se.update(LR * flat.scale, presorted=True)
-        flat.allreduce()
+        if early:      # the bottom MLP's share now; the top MLP's has been in flight since its backward
+            dist.all_reduce(flat.flat[:n_bottom], op=dist.ReduceOp.SUM)
+            main.wait_stream(main if serial["on"] else comm_stream_)
+        else:
+            flat.allreduce()
         with torch.no_grad():
             pflat.add_(flat.flat, alpha=-LR * flat.scale)      # Flux.update!: x .-= eta * grad
         main.wait_stream(upd_stream)
@@ -594,6 +616,20 @@ def run_ours(args):
         for n, st in in_graph.items():
             if n in prof:
                 prof[n]["in_graph_avg_ms"] = st["avg_ms"]
+    # The most faithful clock: %globaltimer stamps taken by the kernels themselves (dlrmb_clock_enable) inside
+    # a capture of the REAL multi-stream step graph, replayed over the timed batches: min(CTA entry) to
+    # max(CTA exit) of each kernel, no event nodes, no serialisation.
+    dev_clock = None
+    if graph is not None:
+        try:
+            dev_clock = device_clock_pass(train_step, (s_dense, s_labels, s_idx), devb[W:W + K], dev)
+            for n, us in dev_clock.items():
+                if n in prof:
+                    prof[n]["device_clock_us"] = us
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] device-clock pass failed ({type(exc).__name__}: {exc})", file=sys.stderr)
+        barrier()
 
     # ---- e2e: host inputs in, loss out, every step.  Graph mode runs it as a two-slot pipeline, the way
     # a training loop with a prefetching loader does (DACLoader): the pinned-host ->
@@ -701,6 +737,7 @@ def run_ours(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL, "data": "synthetic",
             "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check,
+                           barrier_timeouts=(se.peer.barrier_timeouts() if se.peer is not None else 0),
                            mlp=("fused dense layers (library fp32 GEMMs, epilogue bias+relu, dlrmb_dense_bwd_act_bias)" if fused_mlp
                                 else "nn.Linear + ReLU autograd")),
             "e2e": {"value": Bg * K / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
@@ -730,6 +767,42 @@ def run_ours(args):
     if world > 1:
         torch.cuda.synchronize()
         os._exit(0)
+
+
+CLOCK_NAMES = ["lookup", "sort", "update", "update_fixup", "interaction_fwd", "interaction_bwd", "bce"]
+
+
+def device_clock_pass(train_step, statics, batches, dev):
+    """name -> microseconds per launch from the kernels' own %globaltimer stamps, inside the step graph."""
+    import torch
+    from dlrm_jl_b200 import _lib
+    lib = _lib.load()
+    nk = int(lib.dlrmb_clock_kernels())
+    n = int(lib.dlrmb_clock_buffer_bytes()) // 8
+    buf = torch.empty(n, dtype=torch.int64, device=dev)
+    view = buf.view(nk, -1, 2)
+    _lib.check(lib.dlrmb_clock_enable(buf.data_ptr()))
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            train_step(*statics)
+    finally:
+        _lib.check(lib.dlrmb_clock_enable(None))
+    acc = {}
+    for b in batches:
+        for dst, src in zip(statics, b):
+            dst.copy_(src)
+        view[:, :, 0] = 1 << 62
+        view[:, :, 1] = 0
+        g.replay()
+        torch.cuda.synchronize()
+        t0 = view[:, :, 0].min(dim=1).values.cpu().tolist()
+        t1 = view[:, :, 1].max(dim=1).values.cpu().tolist()
+        for k in range(nk):
+            if t1[k] > 0 and t0[k] < (1 << 62):
+                acc.setdefault(CLOCK_NAMES[k], []).append((t1[k] - t0[k]) * 1e-3)
+    del g
+    return {k: float(np.mean(v)) for k, v in acc.items()}
 
 
 CHECK_ROWS = 64
@@ -960,10 +1033,12 @@ def kernel_replays(se, batches, wl, dev):
 def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     """Per-kernel device time and rooflines.  Algorithmic bytes per SURVEY.md section 8(d), rank 0's share.
 
-    Three clocks per kernel, all CUDA events on the launching stream, all reported:
-      * in_step_us -- the step's own launch sequence on its real data, serialised on one stream, eager
-        launches, an event pair around the call: the kernel with the inputs and neighbours it has in the
-        step, nothing else on the GPU (the analogue of an ncu launch list, without a profiler);
+    Clocks per kernel, all reported:
+      * in_step_us -- when the step runs as a CUDA graph: the kernel's own %globaltimer stamps (first CTA in
+        to last CTA out, dlrmb_clock_enable) inside a capture of the real multi-stream step graph, replayed
+        over the timed batches -- the kernel exactly where and how it runs in the step, no event nodes;
+        otherwise (and always as event_pair_us): the step's own launch sequence serialised on one stream,
+        eager launches, a CUDA-event pair around the call (adds ~5 us per pair: the 2.7 us BCE kernel reads 8);
       * in_graph_us -- an event-record node on either side of the call inside a second capture of the
         multi-stream step graph: includes the kernels of other streams sharing the SMs and a few
         microseconds of graph-dependency latency per event pair;
@@ -992,7 +1067,11 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     alg = {"lookup": lookup_bytes, "update": update_bytes, "interaction_fwd": ifwd_bytes, "interaction_bwd": ibwd_bytes}
     kernels = {}
     for name, st in prof.items():
-        k = {"launches": st["count"], "in_step_us": 1e3 * st["avg_ms"]}
+        k = {"launches": st["count"], "in_step_us": 1e3 * st["avg_ms"], "in_step_clock": "serialised eager step, CUDA-event pair"}
+        if "device_clock_us" in st:      # the kernel's own %globaltimer stamps inside the real step graph
+            k["event_pair_us"] = k["in_step_us"]
+            k["in_step_us"] = float(st["device_clock_us"])
+            k["in_step_clock"] = "device %globaltimer stamps (first CTA in .. last CTA out) inside the step graph"
         if "in_graph_avg_ms" in st:      # event-record nodes inside the multi-stream step graph (adds graph-dependency latency)
             k["in_graph_us"] = 1e3 * st["in_graph_avg_ms"]
         if replay and name in replay:
@@ -1067,6 +1146,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
+    ap.add_argument("--late-allreduce", action="store_true",
+                    help="multi-GPU: one dense all-reduce after the whole backward pass instead of starting the top MLP's share early")
+    ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],
+                    help="multi-GPU ordering of the fused exchanges: flag barrier kernel over IPC memory, or a one-element NCCL all-reduce")
     ap.add_argument("--e2e-sync", action="store_true",
                     help="e2e leg without the input-prefetch / deferred-loss pipeline (copy, run, read, every step)")
     ap.add_argument("--unfused-mlp", action="store_true",

@@ -32,6 +32,9 @@ SIGNATURES = {
     "dlrmb_launch_count": (_i64, []),
     "dlrmb_set_option": (_i32, [C.c_char_p, _i64]),
     "dlrmb_get_option": (_i32, [C.c_char_p, C.POINTER(_i64)]),
+    "dlrmb_clock_buffer_bytes": (_i64, []),
+    "dlrmb_clock_kernels": (_i32, []),
+    "dlrmb_clock_enable": (_i32, [_vp]),
     "dlrmb_tables_create": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, C.POINTER(_vp)]),
     "dlrmb_tables_create_ex": (_i32, [_i32, _i32, C.POINTER(_i64), _i32, _i64, _i32, C.POINTER(_vp)]),
     "dlrmb_tables_elem_bytes": (_i32, [_vp]),
@@ -61,6 +64,11 @@ SIGNATURES = {
     "dlrmb_xbuf_close": (_i32, [_i32, _vp]),
     "dlrmb_tables_set_slot_map": (_i32, [_vp, C.POINTER(_i32)]),
     "dlrmb_embedding_fwd_p2p": (_i32, [_vp, *_idx_args, C.POINTER(_vp), _i32, _i32, _i32, _vp]),
+    "dlrmb_embedding_fwd_p2p_sort": (_i32, [_vp, *_idx_args, C.POINTER(_vp), _i32, _i32, _i32, _vp]),
+    "dlrmb_peer_barrier": (_i32, [_i32, C.POINTER(_vp), _i32, _i32, _i32, _vp, _vp]),
+    "dlrmb_peer_barrier_flag_bytes": (_i64, []),
+    "dlrmb_peer_barrier_state_bytes": (_i64, []),
+    "dlrmb_indices_scatter_p2p": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "dlrmb_interaction_has_warp_path": (_i32, [_i32, _i32]),
     "dlrmb_dense_fwd_bias_act": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "dlrmb_dense_bwd_scratch_floats": (_i64, [_i32]),

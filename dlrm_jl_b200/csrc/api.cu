@@ -13,6 +13,11 @@ namespace dlrmb {
 static thread_local char tl_error[512] = "";
 std::atomic<long long> g_launches{0};
 Options g_opt;
+static std::atomic<unsigned long long*> g_clock_buf{nullptr};
+unsigned long long* clock_slot(int which) {
+    unsigned long long* b = g_clock_buf.load(std::memory_order_relaxed);
+    return b ? b + (size_t)which * 2 * kClockCtas : nullptr;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -118,7 +123,7 @@ static std::atomic<int>* find_option(const char* name) {
     if (!strcmp(name, "update_tile")) return &g_opt.update_tile;
     if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
     if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
-    if (!strcmp(name, "pdl")) return &g_opt.pdl;
+    if (!strcmp(name, "bwd_packed")) return &g_opt.bwd_packed;
     return nullptr;
 }
 
@@ -126,6 +131,13 @@ int32_t dlrmb_set_option(const char* name, int64_t value) {
     std::atomic<int>* o = find_option(name);
     DLRMB_REQUIRE(o != nullptr, "unknown option '%s'", name ? name : "(null)");
     o->store((int)value);
+    return DLRMB_OK;
+}
+
+int64_t dlrmb_clock_buffer_bytes(void) { return (int64_t)CLK_COUNT * 2 * kClockCtas * sizeof(unsigned long long); }
+int32_t dlrmb_clock_kernels(void) { return CLK_COUNT; }
+int32_t dlrmb_clock_enable(void* device_buffer) {
+    g_clock_buf.store(static_cast<unsigned long long*>(device_buffer));
     return DLRMB_OK;
 }
 

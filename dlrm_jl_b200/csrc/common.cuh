@@ -59,6 +59,28 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+// ---- optional device-side kernel stamps (dlrmb_clock_enable) ---------------------------------
+// When a clock buffer is registered, thread 0 of every CTA of the main kernels stores %globaltimer
+// (32 ns steps on B200) at entry and exit into [kernel][cta][2]; the host takes min(entry), max(exit).
+// This times a kernel where it really runs -- inside the multi-stream CUDA graph of a training step --
+// without the several microseconds a CUDA-event pair adds around a 10 us kernel.  A null pointer
+// (the default) costs one predicated branch.
+constexpr int kClockCtas = 4096;     // CTAs stamped per kernel (the first 4096; every kernel here starts in launch order)
+enum ClockKernel { CLK_LOOKUP = 0, CLK_SORT, CLK_UPDATE, CLK_FIXUP, CLK_IFWD, CLK_IBWD, CLK_BCE, CLK_COUNT };
+unsigned long long* clock_slot(int which);       // host: device pointer of that kernel's stamps, or nullptr
+
+__device__ __forceinline__ unsigned long long clock_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void clock_in(unsigned long long* c, unsigned cta) {
+    if (c != nullptr && threadIdx.x == 0 && cta < (unsigned)kClockCtas) c[2 * cta] = clock_now();
+}
+__device__ __forceinline__ void clock_out(unsigned long long* c, unsigned cta) {
+    if (c != nullptr && threadIdx.x == 0 && cta < (unsigned)kClockCtas) c[2 * cta + 1] = clock_now();
+}
+
 // ---- table storage -----------------------------------------------------------------------
 struct TableDesc {
     float* base;   // [rows][D] in HBM, 256-byte aligned; f32, or bf16 when the tables store bf16
@@ -117,7 +139,7 @@ struct Options {
     std::atomic<int> update_tile{0};          // 4 | 8 | 16 | 32 entries per lane group (0 = chosen per batch)
     std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
     std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
-    std::atomic<int> pdl{1};                  // programmatic dependent launch for the chained kernels
+    std::atomic<int> bwd_packed{0};           // experiment: packed-S interaction backward                  // programmatic dependent launch for the chained kernels
 };
 extern Options g_opt;
 

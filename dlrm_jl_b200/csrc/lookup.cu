@@ -121,17 +121,25 @@ __device__ __forceinline__ void lookup_pool_body(const TableDesc* __restrict__ d
 template <typename IdxT, int VEC, int U, typename RowT>
 __global__ void __launch_bounds__(256)
 lookup_gather_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
-                     uint32_t B, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
+                     uint32_t B, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0,
+                     unsigned long long* clk) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    clock_in(clk, lin);
     lookup_gather_body<IdxT, VEC, U, RowT>(desc, idx, idx_base, B, C, cshift, out, slots, slot0, blockIdx.y,
                                            blockIdx.x, gridDim.x);
+    clock_out(clk, lin);
 }
 
 template <typename IdxT, int VEC, typename RowT>
 __global__ void __launch_bounds__(256)
 lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base,
-                   uint32_t B, uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0) {
+                   uint32_t B, uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0,
+                   unsigned long long* clk) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    clock_in(clk, lin);
     lookup_pool_body<IdxT, VEC, RowT>(desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, blockIdx.y,
                                       blockIdx.x, gridDim.x);
+    clock_out(clk, lin);
 }
 
 // Training-step form: the lookup and the index sort / dedup of the NEXT sparse update in one launch.
@@ -142,13 +150,16 @@ template <typename IdxT, int U, typename RowT, int ITEMS, bool POOL>
 __global__ void __launch_bounds__(256, 5)
 lookup_sort_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base, uint32_t B,
                    uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0, int ntab,
-                   uint32_t bx, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap) {
+                   uint32_t bx, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap,
+                   unsigned long long* clk) {
     extern __shared__ uint32_t sort_smem[];
+    clock_in(clk, blockIdx.x);
     if ((int)blockIdx.x < ntab) {
         const int k = blockIdx.x;
         const int L = (int)(B * P);
         sort_small_body<IdxT, ITEMS, 256>(idx + (size_t)k * L, idx_base, L, desc[k].rows,
                                           keys_out + (size_t)k * cap, pos_out + (size_t)k * cap, sort_smem);
+        clock_out(clk, blockIdx.x);
         return;
     }
     const uint32_t lin = blockIdx.x - ntab;
@@ -156,6 +167,7 @@ lookup_sort_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
     const uint32_t cx = lin - (uint32_t)k * bx;
     if (POOL) lookup_pool_body<IdxT, 4, RowT>(desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, k, cx, bx);
     else lookup_gather_body<IdxT, 4, U, RowT>(desc, idx, idx_base, B, C, cshift, out, slots, slot0, k, cx, bx);
+    clock_out(clk, blockIdx.x);
 }
 
 static void lookup_grid(const dlrmb_tables* t, int64_t n, int P, int64_t* bx, int* cshift, uint32_t C) {
@@ -185,9 +197,9 @@ static int launch_lookup_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B
     lookup_grid(t, n, P, &bx, &cshift, C);
     dim3 grid((unsigned)bx, (unsigned)t->ntab);
     if (P == 1)
-        lookup_gather_kernel<IdxT, VEC, U, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, cshift, out, slots, slot0);
+        lookup_gather_kernel<IdxT, VEC, U, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, C, cshift, out, slots, slot0, clock_slot(CLK_LOOKUP));
     else
-        lookup_pool_kernel<IdxT, VEC, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0);
+        lookup_pool_kernel<IdxT, VEC, RowT><<<grid, 256, 0, s>>>(t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, clock_slot(CLK_LOOKUP));
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }
@@ -229,7 +241,8 @@ static int launch_lookup_sort_i(dlrmb_tables* t, const IdxT* idx, int idx_base, 
     if (rc) return rc;
     const unsigned grid = (unsigned)(t->ntab + bx * t->ntab);
     lookup_sort_kernel<IdxT, U, RowT, ITEMS, POOL><<<grid, 256, smem, s>>>(
-        t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, t->ntab, (uint32_t)bx, t->keys[0], t->pos[0], t->cap);
+        t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, t->ntab, (uint32_t)bx, t->keys[0], t->pos[0], t->cap,
+        clock_slot(CLK_LOOKUP));
     DLRMB_LAUNCH_CHECK();
     t->sorted_buf = 0;
     return DLRMB_OK;

@@ -18,8 +18,9 @@ namespace dlrmb {
 __global__ void __launch_bounds__(256)
 bce_sigmoid_kernel(const float* __restrict__ z, const float* __restrict__ y, int B, float* __restrict__ prob,
                    float* __restrict__ dz, float* __restrict__ loss, float* __restrict__ block_sums,
-                   unsigned int* __restrict__ counter) {
+                   unsigned int* __restrict__ counter, unsigned long long* clk) {
     __shared__ float wsum[8];
+    clock_in(clk, blockIdx.x);
     __shared__ bool is_last;
     const float eps = 1.1920929e-07f;
     const float inv_b = 1.0f / (float)B;
@@ -52,13 +53,15 @@ bce_sigmoid_kernel(const float* __restrict__ z, const float* __restrict__ y, int
         *loss = s * inv_b;
         *counter = 0;
     }
+    clock_out(clk, blockIdx.x);
 }
 
 int launch_bce_sigmoid(const float* z, const float* y, int B, float* prob, float* dz, float* loss,
                        float* scratch /* >= 65 floats */, cudaStream_t s) {
     int blocks = (B + 255) / 256;
     if (blocks > 64) blocks = 64;
-    bce_sigmoid_kernel<<<blocks, 256, 0, s>>>(z, y, B, prob, dz, loss, scratch, reinterpret_cast<unsigned int*>(scratch + 64));
+    bce_sigmoid_kernel<<<blocks, 256, 0, s>>>(z, y, B, prob, dz, loss, scratch, reinterpret_cast<unsigned int*>(scratch + 64),
+                                              clock_slot(CLK_BCE));
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }

@@ -7,6 +7,7 @@
 //
 // New functionality (DLRM.jl is single-process); BASELINE.json north_star / SURVEY.md section 8(e).
 #include "common.cuh"
+#include "sort_small.cuh"
 
 struct dlrmb_xbuf {
     int device;
@@ -30,22 +31,47 @@ p2p_ldrow(const float* base, size_t r, size_t D, int c) {
     else return RowIO<RowT>::ldg1(RowIO<RowT>::row(base, r, D), c);
 }
 
-template <typename IdxT, int VEC, int U, typename RowT>
-__global__ void __launch_bounds__(256)
+// SORT_ITEMS > 0: the first `ntab` CTAs of the (then one-dimensional) grid sort the tables' index lists for
+// the coming sparse update in shared memory (sort_small.cuh), as in lookup_sort_kernel of lookup.cu.
+template <typename IdxT, int VEC, int U, typename RowT, int SORT_ITEMS>
+__global__ void __launch_bounds__(256, (SORT_ITEMS > 0) ? 4 : 1)
 lookup_p2p_kernel(const TableDesc* __restrict__ desc, const int32_t* __restrict__ slotmap,
                   const IdxT* __restrict__ idx, int idx_base, uint32_t Bg, uint32_t B_local, uint32_t P,
-                  uint32_t C, PeerPtrs peers, int slots) {
+                  uint32_t C, PeerPtrs peers, int slots, int ntab, uint32_t bx, uint32_t* __restrict__ keys_out,
+                  uint32_t* __restrict__ pos_out, int64_t cap, unsigned long long* clk) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
-    const int k = blockIdx.y;
+    int k;
+    uint32_t cx, nctas;
+    const unsigned clk_cta = blockIdx.y * gridDim.x + blockIdx.x;
+    clock_in(clk, clk_cta);
+    if constexpr (SORT_ITEMS > 0) {
+        extern __shared__ uint32_t sort_smem[];
+        if ((int)blockIdx.x < ntab) {
+            k = blockIdx.x;
+            const int L = (int)(Bg * P);
+            sort_small_body<IdxT, (SORT_ITEMS > 0 ? SORT_ITEMS : 4), 256>(idx + (size_t)k * L, idx_base, L, desc[k].rows,
+                                                                          keys_out + (size_t)k * cap, pos_out + (size_t)k * cap, sort_smem);
+            clock_out(clk, clk_cta);
+            return;
+        }
+        const uint32_t lin = blockIdx.x - ntab;
+        k = (int)(lin / bx);
+        cx = lin - (uint32_t)k * bx;
+        nctas = bx;
+    } else {
+        k = blockIdx.y;
+        cx = blockIdx.x;
+        nctas = gridDim.x;
+    }
     const float* __restrict__ tb = desc[k].base;
     const IdxT* __restrict__ ik = idx + (size_t)k * Bg * P;
     const uint32_t n = Bg * C;
-    const uint32_t step = gridDim.x * blockDim.x;
+    const uint32_t step = nctas * blockDim.x;
     const size_t D = (size_t)C * VEC;
     const size_t slot_off = (size_t)slotmap[k] * D;
     const size_t ostride = (size_t)slots * D;
 
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step * U) {
+    for (uint32_t t = cx * blockDim.x + threadIdx.x; t < n; t += step * U) {
         uint32_t b[U], c[U];
         bool ok[U];
         V acc[U];
@@ -89,11 +115,14 @@ lookup_p2p_kernel(const TableDesc* __restrict__ desc, const int32_t* __restrict_
             reinterpret_cast<V*>(dst)[c[u]] = acc[u];
         }
     }
+    clock_out(clk, clk_cta);
 }
+
+int ensure_smem_attr(const void* func, int bytes, unsigned long long* done_mask);
 
 template <typename IdxT, int VEC, typename RowT>
 static int launch_p2p_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int Bg, int P, const PeerPtrs& peers,
-                        int B_local, int slots, cudaStream_t s) {
+                        int B_local, int slots, bool with_sort, cudaStream_t s) {
     const uint32_t C = t->D / VEC;
     const int64_t n = (int64_t)Bg * C;
     DLRMB_REQUIRE(n < (1ll << 30), "B * D too large for one lookup launch (%lld chunks)", (long long)n);
@@ -101,10 +130,44 @@ static int launch_p2p_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int Bg, 
     int64_t bx = ceil_div64(n, 256 * U);
     const int64_t cap = (int64_t)t->sm_count * 32;
     if (bx * t->ntab > cap) bx = cap / t->ntab > 0 ? cap / t->ntab : 1;
+    const int64_t L = (int64_t)Bg * P;
+    if constexpr (VEC == 4) {
+        if (with_sort && L <= kFusedSortMax) {   // the sort of the coming update rides in the same launch
+            const unsigned grid1 = (unsigned)(t->ntab + bx * t->ntab);
+            if (L <= 2048) {
+                constexpr size_t smem = SmallSortGeom<8, 256>::smem_bytes();
+                static unsigned long long done = 0;
+                int rc = ensure_smem_attr((const void*)lookup_p2p_kernel<IdxT, 4, U, RowT, 8>, (int)smem, &done);
+                if (rc) return rc;
+                lookup_p2p_kernel<IdxT, 4, U, RowT, 8><<<grid1, 256, smem, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
+                                                                             peers, slots, t->ntab, (uint32_t)bx, t->keys[0], t->pos[0], t->cap, clock_slot(CLK_LOOKUP));
+            } else {
+                constexpr size_t smem = SmallSortGeom<16, 256>::smem_bytes();
+                static unsigned long long done = 0;
+                int rc = ensure_smem_attr((const void*)lookup_p2p_kernel<IdxT, 4, U, RowT, 16>, (int)smem, &done);
+                if (rc) return rc;
+                lookup_p2p_kernel<IdxT, 4, U, RowT, 16><<<grid1, 256, smem, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
+                                                                              peers, slots, t->ntab, (uint32_t)bx, t->keys[0], t->pos[0], t->cap, clock_slot(CLK_LOOKUP));
+            }
+            DLRMB_LAUNCH_CHECK();
+            t->sorted_buf = 0;
+            t->sorted_valid = true;
+            t->sorted_B = Bg;
+            t->sorted_P = P;
+            return DLRMB_OK;
+        }
+    }
     dim3 grid((unsigned)bx, (unsigned)t->ntab);
-    lookup_p2p_kernel<IdxT, VEC, U, RowT><<<grid, 256, 0, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
-                                                         peers, slots);
+    lookup_p2p_kernel<IdxT, VEC, U, RowT, 0><<<grid, 256, 0, s>>>(t->d_desc, t->d_slotmap, idx, idx_base, Bg, B_local, P, C,
+                                                            peers, slots, t->ntab, (uint32_t)bx, nullptr, nullptr, 0, clock_slot(CLK_LOOKUP));
     DLRMB_LAUNCH_CHECK();
+    if (with_sort) {   // too many keys for the 256-thread sort CTAs: the stand-alone sort, same stream
+        int rc = launch_sort(t, idx, (int)sizeof(IdxT), idx_base, Bg, P, s);
+        if (rc) return rc;
+        t->sorted_valid = true;
+        t->sorted_B = Bg;
+        t->sorted_P = P;
+    }
     return DLRMB_OK;
 }
 
@@ -190,9 +253,9 @@ int32_t dlrmb_tables_set_slot_map(dlrmb_tables* t, const int32_t* slots) {
     return DLRMB_OK;
 }
 
-int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
-                                int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
-                                int32_t B_local, int32_t slots, dlrmb_stream stream) {
+static int32_t embedding_fwd_p2p_impl(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                      int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
+                                      int32_t B_local, int32_t slots, bool with_sort, dlrmb_stream stream) {
     DLRMB_REQUIRE(t != nullptr && idx != nullptr && peer_T != nullptr, "null argument");
     DLRMB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, "idx_bytes must be 4 or 8 (got %d)", idx_bytes);
     DLRMB_REQUIRE(idx_base == 0 || idx_base == 1, "idx_base must be 0 or 1 (got %d)", idx_base);
@@ -224,18 +287,151 @@ int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_by
     const bool bf = t->elem_bytes == 2;
     if (idx_bytes == 4) {
         const uint32_t* ip = (const uint32_t*)idx;
-        if (aligned) rc = bf ? launch_p2p_t<uint32_t, 4, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
-                             : launch_p2p_t<uint32_t, 4, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
-        else rc = bf ? launch_p2p_t<uint32_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
-                     : launch_p2p_t<uint32_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
+        if (aligned) rc = bf ? launch_p2p_t<uint32_t, 4, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s)
+                             : launch_p2p_t<uint32_t, 4, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s);
+        else rc = bf ? launch_p2p_t<uint32_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s)
+                     : launch_p2p_t<uint32_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s);
     } else {
         const int64_t* ip = (const int64_t*)idx;
-        if (aligned) rc = bf ? launch_p2p_t<int64_t, 4, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
-                             : launch_p2p_t<int64_t, 4, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
-        else rc = bf ? launch_p2p_t<int64_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, s)
-                     : launch_p2p_t<int64_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, s);
+        if (aligned) rc = bf ? launch_p2p_t<int64_t, 4, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s)
+                             : launch_p2p_t<int64_t, 4, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s);
+        else rc = bf ? launch_p2p_t<int64_t, 1, __nv_bfloat16>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s)
+                     : launch_p2p_t<int64_t, 1, float>(t, ip, idx_base, B_global, P, peers, B_local, slots, with_sort, s);
     }
     return rc;
+}
+
+int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
+                                int32_t B_local, int32_t slots, dlrmb_stream stream) {
+    return embedding_fwd_p2p_impl(t, idx, idx_bytes, idx_base, B_global, P, peer_T, world, B_local, slots, false, stream);
+}
+
+int32_t dlrmb_embedding_fwd_p2p_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                     int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
+                                     int32_t B_local, int32_t slots, dlrmb_stream stream) {
+    if (t) t->sorted_valid = false;
+    return embedding_fwd_p2p_impl(t, idx, idx_bytes, idx_base, B_global, P, peer_T, world, B_local, slots, true, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Stream-ordered cross-GPU ordering without NCCL: flag barrier over the IPC-mapped buffers
+// ---------------------------------------------------------------------------------------------
+// Every rank owns a flag array [channels][world] of 32-bit epochs inside a dlrmb_xbuf that its peers
+// map.  dlrmb_peer_barrier launches ONE tiny kernel that (1) bumps this rank's epoch of the channel,
+// (2) after a system-scope fence stores it into slot [channel][rank] of every rank's array over
+// NVLink, (3) waits until all `world` slots of its OWN array have reached the epoch.  Placed on the
+// stream behind a kernel that stored into peers' buffers and in front of the kernels that consume
+// what the peers stored, it is the ordering point of the fused exchanges: kernel completion makes the
+// producer's peer stores visible before the flag store is issued, and nobody passes before every
+// rank's flag -- hence every rank's data -- has arrived.  The epoch lives in device memory, so the
+// call can be captured into a CUDA graph and replayed.  Each rank must run on its own GPU (the wait
+// spins on flags that kernels of other processes set).
+namespace dlrmb {
+
+struct PeerFlagPtrs {
+    uint32_t* p[kMaxPeers];
+};
+
+constexpr int kBarrierChannels = 8;
+// state: [0 .. kBarrierChannels) epochs, [kBarrierChannels] = number of timed-out waits
+
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(PeerFlagPtrs peers, int world, int rank, int channel, uint32_t* __restrict__ state,
+                    unsigned long long timeout_ns) {
+    const int lane = threadIdx.x;
+    uint32_t epoch = 0;
+    if (lane == 0) {
+        epoch = state[channel] + 1u;
+        state[channel] = epoch;
+    }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
+    if (lane < world) {
+        // the stream's earlier kernels (whose peer stores this flag publishes) have completed; the fence
+        // orders their effects, as this thread observes them, before the flag store at system scope
+        __threadfence_system();
+        volatile uint32_t* dst = peers.p[lane] + (size_t)channel * kMaxPeers + rank;
+        *dst = epoch;
+        const volatile uint32_t* mine = peers.p[rank] + (size_t)channel * kMaxPeers + lane;
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        // epochs only grow; compare as a signed distance so a wrap after 2^31 steps stays correct
+        while ((int32_t)(*mine - epoch) < 0) {
+            __nanosleep(40);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {       // a peer is gone: do not hang the GPU, leave a trace for the host
+                atomicAdd(state + kBarrierChannels, 1u);
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+
+// idx_local [ntab][B_local][P] of this rank's samples -> the owners' index buffers
+// [t_owner][B_global][P] (rows rank*B_local ...), one 4- or 8-byte store per index over NVLink
+struct IdxDest {
+    void* base;        // owner's buffer for this table: [B_global][P]
+};
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+indices_scatter_kernel(const IdxT* __restrict__ idx_local, const IdxDest* __restrict__ dests, int ntab, int B_local,
+                       int P, int rank) {
+    const int k = blockIdx.y;
+    const int n = B_local * P;
+    const IdxT* src = idx_local + (size_t)k * n;
+    IdxT* dst = static_cast<IdxT*>(dests[k].base) + (size_t)rank * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace dlrmb
+
+extern "C" {
+
+int32_t dlrmb_peer_barrier(int32_t device, uint32_t* const* peer_flags, int32_t world, int32_t rank, int32_t channel,
+                           uint32_t* state, dlrmb_stream stream) {
+    DLRMB_REQUIRE(peer_flags && state, "null argument");
+    DLRMB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad world / rank (%d, %d)", world, rank);
+    DLRMB_REQUIRE(channel >= 0 && channel < kBarrierChannels, "channel must be in 0..%d", kBarrierChannels - 1);
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    PeerFlagPtrs peers;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        peers.p[r] = r < world ? peer_flags[r] : nullptr;
+        DLRMB_REQUIRE(r >= world || peer_flags[r] != nullptr, "peer_flags[%d] is null", r);
+    }
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peers, world, rank, channel, state, 4000000000ull);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+int64_t dlrmb_peer_barrier_flag_bytes(void) { return (int64_t)kBarrierChannels * kMaxPeers * sizeof(uint32_t); }
+int64_t dlrmb_peer_barrier_state_bytes(void) { return (int64_t)(kBarrierChannels + 1) * sizeof(uint32_t); }
+
+int32_t dlrmb_indices_scatter_p2p(int32_t device, const void* idx_local, int32_t idx_bytes, int32_t ntab,
+                                  int32_t B_local, int32_t P, const void* const* dests_dev, int32_t rank,
+                                  dlrmb_stream stream) {
+    DLRMB_REQUIRE(idx_local && dests_dev, "null argument");
+    DLRMB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, "idx_bytes must be 4 or 8 (got %d)", idx_bytes);
+    DLRMB_REQUIRE(ntab > 0 && ntab <= 65535 && B_local > 0 && P > 0 && rank >= 0, "bad index scatter geometry");
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    const int n = B_local * P;
+    int bx = (n + 255) / 256;
+    if (bx > 64) bx = 64;
+    dim3 grid((unsigned)bx, (unsigned)ntab);
+    const IdxDest* d = reinterpret_cast<const IdxDest*>(dests_dev);
+    if (idx_bytes == 4)
+        indices_scatter_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)idx_local, d, ntab, B_local, P, rank);
+    else
+        indices_scatter_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int64_t*)idx_local, d, ntab, B_local, P, rank);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
 }
 
 }  // extern "C"

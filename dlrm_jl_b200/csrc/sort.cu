@@ -31,11 +31,14 @@ namespace dlrmb {
 template <typename IdxT, int ITEMS, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 sort_small_kernel(const IdxT* __restrict__ idx, int idx_base, int L, const TableDesc* __restrict__ desc,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap) {
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ pos_out, int64_t cap,
+                  unsigned long long* clk) {
     extern __shared__ uint32_t sort_smem[];
     const int k = blockIdx.x;
+    clock_in(clk, blockIdx.x);
     sort_small_body<IdxT, ITEMS, THREADS>(idx + (size_t)k * L, idx_base, L, desc[k].rows,
                                           keys_out + (size_t)k * cap, pos_out + (size_t)k * cap, sort_smem);
+    clock_out(clk, blockIdx.x);
 }
 
 template <typename IdxT, int ITEMS, int THREADS>
@@ -45,7 +48,7 @@ static int launch_sort_small(dlrmb_tables* t, const IdxT* idx, int idx_base, int
     int rc = ensure_smem_attr((const void*)sort_small_kernel<IdxT, ITEMS, THREADS>, (int)smem, &attr_done);
     if (rc) return rc;
     sort_small_kernel<IdxT, ITEMS, THREADS><<<t->ntab, THREADS, smem, s>>>(idx, idx_base, L, t->d_desc, t->keys[0],
-                                                                          t->pos[0], t->cap);
+                                                                          t->pos[0], t->cap, clock_slot(CLK_SORT));
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }
@@ -254,8 +257,8 @@ static int launch_sort_t(dlrmb_tables* t, const IdxT* idx, int idx_base, int B, 
         if (L <= 1024) rc = launch_sort_small<IdxT, 4, 256>(t, idx, idx_base, L, s);
         else if (L <= 2048) rc = launch_sort_small<IdxT, 8, 256>(t, idx, idx_base, L, s);
         else if (L <= 4096) rc = launch_sort_small<IdxT, 16, 256>(t, idx, idx_base, L, s);
-        else if (L <= 8192) rc = launch_sort_small<IdxT, 16, 512>(t, idx, idx_base, L, s);
-        else rc = launch_sort_small<IdxT, 32, 512>(t, idx, idx_base, L, s);
+        else if (L <= 8192) rc = launch_sort_small<IdxT, 8, 1024>(t, idx, idx_base, L, s);
+        else rc = launch_sort_small<IdxT, 16, 1024>(t, idx, idx_base, L, s);
         if (rc) return rc;
         t->sorted_buf = 0;
         return DLRMB_OK;

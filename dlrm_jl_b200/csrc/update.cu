@@ -238,9 +238,12 @@ __global__ void __launch_bounds__(THREADS, (NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1)
 update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys,
                     const uint32_t* __restrict__ pos, const float* __restrict__ dT, float lr,
                     float* __restrict__ partial, uint8_t* __restrict__ flags,
-                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm) {
+                    uint32_t* __restrict__ head_list, uint32_t* __restrict__ head_count, UpdateGeom gm,
+                    unsigned long long* clk) {
     using V = typename UV<VEC>::type;
     constexpr int U = 4;
+    const unsigned clk_cta = blockIdx.y * gridDim.x + blockIdx.x;
+    clock_in(clk, clk_cta);
     __shared__ V s_carry[THREADS * NCH];   // per group: partial of the run carried in from the previous tile
     __shared__ V s_head[THREADS * NCH];    // per group: partial of the run that continues into the next tile
     __shared__ uint8_t s_flag[THREADS];
@@ -418,6 +421,7 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
             }
             flags[(size_t)k * gm.pcap + cta] = cta_flag;
         }
+        clock_out(clk, clk_cta);
         return;
     }
 
@@ -433,7 +437,10 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         s_nheads = 0;
     }
     __syncthreads();
-    if (!s_first) return;
+    if (!s_first) {
+        clock_out(clk, clk_cta);
+        return;
+    }
     __threadfence();
     // list the table's head chunks (order irrelevant: distinct runs touch distinct rows)
     uint32_t* my_heads = head_list + (size_t)k * gm.pcap;
@@ -444,8 +451,9 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     }
     __syncthreads();
     const uint32_t n_heads = s_nheads;
-    if (n_heads == 0) return;
-    fixup_runs_grouped<VEC, NCH, RowT>(desc, keys, lr, partial, flags, my_heads, n_heads, grp, G, sl, gm);
+    if (n_heads != 0) fixup_runs_grouped<VEC, NCH, RowT>(desc, keys, lr, partial, flags, my_heads, n_heads, grp, G, sl, gm);
+    __syncthreads();      // thread 0 stamps the exit after every lane group of the CTA has finished its runs
+    clock_out(clk, clk_cta);
 }
 
 template <int VEC, int NCH, typename RowT>
@@ -453,12 +461,14 @@ __global__ void __launch_bounds__(256)
 update_fixup_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restrict__ keys, float lr,
                     const float* __restrict__ partial, const uint8_t* __restrict__ flags,
                     const uint32_t* __restrict__ head_list, const uint32_t* __restrict__ head_count,
-                    UpdateGeom gm) {
+                    UpdateGeom gm, unsigned long long* clk) {
     using V = typename UV<VEC>::type;
     __shared__ V red[256 * NCH];
     __shared__ int s_first;
+    clock_in(clk, blockIdx.x);
     fixup_runs<VEC, NCH, 256, RowT>(desc, keys, lr, partial, flags, head_list, *head_count, blockIdx.x,
                                     gridDim.x, gm, red, &s_first);
+    clock_out(clk, blockIdx.x);
 }
 
 static int lanes_per_row_log2(int C) {
@@ -527,17 +537,17 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
                               g_opt.update_two_launches.load(std::memory_order_relaxed) == 0;
     if (inline_fixup) {
         update_tiles_kernel<VEC, NCH, THREADS, RowT, true><<<grid, THREADS, 0, s>>>(
-            t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm);
+            t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm, clock_slot(CLK_UPDATE));
         DLRMB_LAUNCH_CHECK();
         return DLRMB_OK;
     }
     DLRMB_CUDA(cudaMemsetAsync(t->head_count, 0, sizeof(uint32_t), s));
     update_tiles_kernel<VEC, NCH, THREADS, RowT, false><<<grid, THREADS, 0, s>>>(
-        t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm);
+        t->d_desc, keys, pos, dT, lr, t->partial, t->tile_flags, t->head_list, t->head_count, gm, clock_slot(CLK_UPDATE));
     DLRMB_LAUNCH_CHECK();
     unsigned fgrid = (unsigned)(total_chunks < (int64_t)t->sm_count * 8 ? total_chunks : (int64_t)t->sm_count * 8);
     update_fixup_kernel<VEC, NCH, RowT><<<fgrid, 256, 0, s>>>(t->d_desc, keys, lr, t->partial, t->tile_flags,
-                                                        t->head_list, t->head_count, gm);
+                                                        t->head_list, t->head_count, gm, clock_slot(CLK_FIXUP));
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
 }

@@ -174,16 +174,23 @@ class EmbeddingTables:
         arr = (C.c_int32 * self.ntab)(*[int(v) for v in slots])
         _lib.check(self._lib.dlrmb_tables_set_slot_map(self._h, arr))
 
-    def lookup_p2p(self, idx: torch.Tensor, peer_ptrs: Sequence[int], B_local: int, slots: int, idx_base: int = 0) -> None:
+    FUSED_SORT_MAX = 4096     # kFusedSortMax of csrc/common.cuh: largest B*P whose sort rides in the lookup launch
+
+    def lookup_p2p(self, idx: torch.Tensor, peer_ptrs: Sequence[int], B_local: int, slots: int, idx_base: int = 0,
+                   sort: bool = False) -> None:
         """Pool this rank's tables for the global batch and store every pooled row directly into
-        the owning rank's interaction buffer (NVLink peer stores): lookup + forward exchange fused."""
+        the owning rank's interaction buffer (NVLink peer stores): lookup + forward exchange fused.
+        ``sort=True`` also sorts / dedups the indices for this batch's sparse update in the same launch
+        (dlrmb_embedding_fwd_p2p_sort)."""
         ntab, Bg, P = idx.shape
         world = len(peer_ptrs)
         arr = (C.c_void_p * world)(*[int(p) for p in peer_ptrs])
+        fn = self._lib.dlrmb_embedding_fwd_p2p_sort if sort else self._lib.dlrmb_embedding_fwd_p2p
         with _prof.range("lookup"):
-            _lib.check(self._lib.dlrmb_embedding_fwd_p2p(
-                self._h, idx.data_ptr(), idx.element_size(), idx_base, Bg, P, arr, world, B_local, slots,
-                _stream_ptr(self.device)))
+            _lib.check(fn(self._h, idx.data_ptr(), idx.element_size(), idx_base, Bg, P, arr, world, B_local, slots,
+                          _stream_ptr(self.device)))
+        if sort:
+            self._pending_side = False
 
     def sort(self, idx: torch.Tensor, idx_base: int = 0, side_stream: bool = False) -> None:
         """Index sort/dedup for the next update.  With ``side_stream`` it is issued on a second

@@ -141,7 +141,7 @@ class PeerExchange:
     peer stores against the consumers (a one-element NCCL all-reduce by default)."""
 
     def __init__(self, B_local: int, ntab: int, D: int, rank: int, world: int, device, group=None,
-                 barrier: Optional[Callable] = None):
+                 barrier: Optional[Callable] = None, flag_barrier: bool = True):
         import ctypes as C
 
         from . import _lib
@@ -161,6 +161,7 @@ class PeerExchange:
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle), group=group)
         self.peer_ptrs = []
+        self._owned, self._mapped = [], [self.peer_ptrs]      # exchange buffers / peer mappings to release in close()
         for r in range(world):
             if r == rank:
                 self.peer_ptrs.append(p.value)
@@ -176,6 +177,47 @@ class PeerExchange:
         self.peer_G_ptrs = None
         self._gbuf = None
         self._closed = False
+        self._fbuf = None
+        self.peer_flag_ptrs = None
+        self._ibuf = None
+        self.idx_owned = None
+        self._idx_dests = None
+        if barrier is None and flag_barrier:
+            # ordering without NCCL: a flag array per rank, mapped by every peer (dlrmb_peer_barrier)
+            self._fbuf, _own, self.peer_flag_ptrs = self._share(int(self.lib.dlrmb_peer_barrier_flag_bytes()))
+            self._bstate = torch.zeros(int(self.lib.dlrmb_peer_barrier_state_bytes()) // 4, dtype=torch.int32, device=self.device)
+            self._flag_arr = (C.c_void_p * world)(*[int(q) for q in self.peer_flag_ptrs])
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)           # every rank's flag array exists and is zero before anyone signals
+
+    def enable_index_exchange(self, sharding: "TableSharding", B_local: int, P: int, idx_bytes: int = 4):
+        """Index exchange by peer stores: an index buffer [t_mine][B_global][P] on every rank, mapped
+        everywhere; each rank stores its samples' index columns straight into the owners' buffers."""
+        from .embedding import _DevicePtrView
+        counts = sharding.counts()
+        t_mine = counts[self.rank]
+        Bg = B_local * self.world
+        per_table = Bg * P * idx_bytes
+        self._ibuf, own, peer_idx = self._share(max(1, t_mine) * per_table)
+        dt, ts = (torch.int32, "<i4") if idx_bytes == 4 else (torch.int64, "<i8")
+        self.idx_owned = torch.as_tensor(_DevicePtrView(own, (max(1, t_mine), Bg, P), self, ts), device=self.device)
+        assert self.idx_owned.dtype == dt
+        dests = [peer_idx[sharding.owner[k]] + sharding.local[sharding.owner[k]].index(k) * per_table
+                 for k in range(len(sharding.rows))]
+        self._idx_dests = torch.tensor(dests, dtype=torch.int64, device=self.device)
+        self._idx_geom = (len(sharding.rows), B_local, P, idx_bytes)
+
+    def scatter_indices(self, idx_local: torch.Tensor) -> torch.Tensor:
+        """idx_local [ntab][B_local][P] -> the owners' buffers (peer stores) + barrier; returns this rank's
+        idx_owned [t_mine][B_global][P]."""
+        from . import _lib
+        ntab, Bl, P, ib = self._idx_geom
+        assert tuple(idx_local.shape) == (ntab, Bl, P) and idx_local.element_size() == ib and idx_local.is_contiguous()
+        _lib.check(self.lib.dlrmb_indices_scatter_p2p(
+            self.device.index or 0, idx_local.data_ptr(), ib, ntab, Bl, P, self._idx_dests.data_ptr(), self.rank,
+            int(torch.cuda.current_stream(self.device).cuda_stream)))
+        self.barrier(0)
+        return self.idx_owned
 
     def close(self) -> None:
         """Unmap the peers' buffers (cudaIpcCloseMemHandle) and free this rank's exchange buffers.  Every
@@ -184,15 +226,16 @@ class PeerExchange:
             return
         self._closed = True
         dev = self.device.index or 0
-        for ptrs in (self.peer_ptrs, self.peer_G_ptrs or []):
+        for ptrs in self._mapped:
             for r, q in enumerate(ptrs):
                 if r != self.rank and q:
                     self.lib.dlrmb_xbuf_close(dev, q)
-        self.T = self.G = None
-        for h in (self._xbuf, self._gbuf):
+        self.T = self.G = self.idx_owned = None
+        for h in [self._xbuf] + self._owned:
             if h is not None:
                 self.lib.dlrmb_xbuf_destroy(h)
-        self._xbuf = self._gbuf = None
+        self._xbuf = self._gbuf = self._fbuf = self._ibuf = None
+        self._owned, self._mapped = [], []
 
     def __del__(self):
         try:
@@ -221,6 +264,8 @@ class PeerExchange:
             q = C.c_void_p()
             _lib.check(self.lib.dlrmb_xbuf_open(self.device.index or 0, (C.c_uint8 * 64).from_buffer_copy(handles[r]), C.byref(q)))
             ptrs.append(q.value)
+        self._owned.append(h)
+        self._mapped.append(ptrs)
         return h, p.value, ptrs
 
     def enable_gradient_exchange(self, sharding: "TableSharding", B_local: int, D: int):
@@ -240,11 +285,25 @@ class PeerExchange:
         dests = torch.tensor(rows, dtype=torch.int64, device=self.device)
         return ScatterPlan(dests, self.rank * B_local)
 
-    def barrier(self) -> None:
+    def barrier(self, channel: int = 0) -> None:
+        """Order this rank's earlier peer stores before every rank's later reads (stream-ordered).
+        Flag barrier over the mapped buffers (one tiny kernel, dlrmb_peer_barrier) when available; a
+        caller-supplied callable (tests: host-side barrier) or a one-element NCCL all-reduce otherwise."""
         if self._barrier is not None:
             self._barrier()
+        elif self.peer_flag_ptrs is not None:
+            from . import _lib
+            _lib.check(self.lib.dlrmb_peer_barrier(
+                self.device.index or 0, self._flag_arr, self.world, self.rank, channel, self._bstate.data_ptr(),
+                int(torch.cuda.current_stream(self.device).cuda_stream)))
         else:
             dist.all_reduce(self._flag, group=self.group)
+
+    def barrier_timeouts(self) -> int:
+        """Number of flag-barrier waits that gave up (a peer died); 0 in a healthy run."""
+        if self.peer_flag_ptrs is None:
+            return 0
+        return int(self._bstate[-1].item())
 
 
 class _ShardedLookupFn(torch.autograd.Function):
@@ -266,7 +325,7 @@ class _ShardedLookupFn(torch.autograd.Function):
             se.lookup_fn(idx_local, T, 1)
             se.presorted = se.lookup_sorts
             return T
-        idx_owned = exchange_indices(idx_local, se.sharding, se.rank, se.group)
+        idx_owned = se._exchange_indices(idx_local)
         se.idx_owned = idx_owned
         se.presorted = False
         Bg = idx_owned.shape[1]
@@ -274,8 +333,10 @@ class _ShardedLookupFn(torch.autograd.Function):
             # fused path: pooled rows go straight into the owners' T over NVLink; the barrier
             # orders every rank's stores before anyone reads its own T
             if len(se.local_ids):
-                se.tables.lookup_p2p(idx_owned, se.peer.peer_ptrs, Bl, 1 + se.ntab, se.idx_base)
-            se.peer.barrier()
+                fuse = idx_owned.shape[1] * idx_owned.shape[2] <= se.tables.FUSED_SORT_MAX
+                se.tables.lookup_p2p(idx_owned, se.peer.peer_ptrs, Bl, 1 + se.ntab, se.idx_base, sort=fuse)
+                se.presorted = fuse
+            se.peer.barrier(1)
             # a fresh alias every step: the persistent buffer tensor itself must never pick up
             # autograd history (a stale grad_fn from an earlier step would chain the graphs)
             return se.peer.T.detach()
@@ -338,28 +399,49 @@ class ShardedEmbedding:
         """Forward of the fully fused path: no autograd node (the gradient never comes back through
         T; it is scattered to the owners by the interaction backward)."""
         with torch.no_grad():
-            idx_owned = exchange_indices(idx_local, self.sharding, self.rank, self.group)
+            idx_owned = self._exchange_indices(idx_local)
             self.idx_owned = idx_owned
             self.presorted = False
             if len(self.local_ids):
-                self.tables.lookup_p2p(idx_owned, self.peer.peer_ptrs, idx_local.shape[1], 1 + self.ntab, self.idx_base)
-            self.peer.barrier()
+                # up to 4096 lookups per table the sort of the coming update rides in the lookup launch
+                fuse = idx_owned.shape[1] * idx_owned.shape[2] <= self.tables.FUSED_SORT_MAX
+                self.tables.lookup_p2p(idx_owned, self.peer.peer_ptrs, idx_local.shape[1], 1 + self.ntab, self.idx_base,
+                                       sort=fuse)
+                self.presorted = fuse
+            self.peer.barrier(1)
             return self.peer.T.detach()
 
+    def _exchange_indices(self, idx_local: torch.Tensor) -> torch.Tensor:
+        """Index columns to the tables' owners: peer stores + flag barrier when the index buffers are
+        mapped (`enable_index_exchange`), NCCL all-to-all otherwise."""
+        if self.peer is not None and self.peer._idx_dests is not None:
+            owned = self.peer.scatter_indices(idx_local)
+            return owned[:len(self.local_ids)] if len(self.local_ids) else owned[:0]
+        return exchange_indices(idx_local, self.sharding, self.rank, self.group)
+
     def finish_backward(self) -> None:
-        """After loss.backward() on the fused path: every rank's gradient rows have landed."""
-        self.peer.barrier()
+        """After loss.backward() on the fused path: every rank's gradient rows have landed.  The index
+        sort of this step (side stream) is joined first: once a rank passes this barrier its peers may
+        start the next step and overwrite the index buffer the sort reads."""
+        if len(self.local_ids) and getattr(self.tables, "_pending_side", False):
+            torch.cuda.current_stream(self.tables.device).wait_event(self.tables._sorted_event)
+            self.tables._pending_side = False
+        self.peer.barrier(2)
         self.owned_grad = self.peer.G
 
-    def enable_peer_exchange(self, B_local: int, barrier: Optional[Callable] = None) -> None:
+    def enable_peer_exchange(self, B_local: int, barrier: Optional[Callable] = None, flag_barrier: bool = True,
+                             P: Optional[int] = None, idx_bytes: int = 4) -> None:
         """Switch the forward exchange to the fused lookup + NVLink peer-store kernel.  Safe with
-        one buffer per rank when every step also runs the backward exchange (a collective all
-        ranks reach only after they have finished reading T)."""
+        one buffer per rank when every step also runs the backward exchange (a barrier all ranks
+        reach only after they have finished reading T).  With ``P`` (lookups per sample) given, the
+        index exchange also goes over peer stores instead of an NCCL all-to-all."""
         if self.world == 1:
             return
         self.tables.set_slot_map([1 + k for k in self.local_ids] or [1])
         self.peer = PeerExchange(B_local, self.ntab, self.D, self.rank, self.world, self.tables.device,
-                                 self.group, barrier)
+                                 self.group, barrier, flag_barrier)
+        if P is not None:
+            self.peer.enable_index_exchange(self.sharding, B_local, P, idx_bytes)
 
     @classmethod
     def create(cls, rows: Sequence[int], D: int, B_local: int, P: int, rank: int, world: int, device,

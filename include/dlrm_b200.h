@@ -60,10 +60,20 @@ int64_t dlrmb_launch_count(void);
  *   "update_two_launches" 1 = separate fix-up launch of the sparse update at every batch size
  *   "update_tile" 4|8|16|32 = entries per lane group of the sparse update (0 = chosen per batch)
  *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
- *   "pdl" 0 = launch without programmatic dependent launch attributes
  * Defaults are the measured-fastest configuration; unknown names return DLRMB_EINVAL. */
 int32_t dlrmb_set_option(const char* name, int64_t value);
 int32_t dlrmb_get_option(const char* name, int64_t* value);
+/* Device-side kernel stamps for measurement: with a buffer of dlrmb_clock_buffer_bytes() registered,
+ * thread 0 of the first 4096 CTAs of every launch of the main kernels stores %globaltimer (nanoseconds,
+ * 32 ns steps) at entry and exit into buffer[kernel][cta][2] (uint64; kernel order: lookup, sort, update,
+ * update fix-up, interaction forward, interaction backward, sigmoid + BCE; dlrmb_clock_kernels() of them).
+ * The caller pre-fills entries with UINT64_MAX/2 and exits with 0 and reads min(entry) / max(exit) after
+ * the launches have completed: the duration of a kernel where it really runs (e.g. inside a multi-stream
+ * CUDA graph of a training step) without the microseconds a CUDA-event pair adds.  The pointer is read when a
+ * launch is ISSUED (or captured); pass NULL to switch the stamps off (the default). */
+int64_t dlrmb_clock_buffer_bytes(void);
+int32_t dlrmb_clock_kernels(void);
+int32_t dlrmb_clock_enable(void* device_buffer);
 
 /* ---- table storage: replaces SimpleEmbedding{Static{D}}(data) on an `embedding_allocator`
  * array (src/model/model.jl:185-206, src/data/criteo.jl:413,490) and the CachedArrays-backed
@@ -206,6 +216,33 @@ int32_t dlrmb_tables_set_slot_map(dlrmb_tables* t, const int32_t* slots);
 int32_t dlrmb_embedding_fwd_p2p(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
                                 int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
                                 int32_t B_local, int32_t slots, dlrmb_stream stream);
+
+/* Training-step form of dlrmb_embedding_fwd_p2p: also sorts / dedups the owned indices for the coming
+ * dlrmb_embedding_update_sorted (in extra CTAs of the same launch when B_global * P <= 4096, by the
+ * stand-alone sort kernel on the same stream above that). */
+int32_t dlrmb_embedding_fwd_p2p_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
+                                     int32_t B_global, int32_t P, float* const* peer_T, int32_t world,
+                                     int32_t B_local, int32_t slots, dlrmb_stream stream);
+
+/* Ordering point of the fused exchanges without NCCL: a flag barrier over IPC-mapped memory, one tiny
+ * kernel per call.  Every rank allocates a zero-initialised dlrmb_xbuf of dlrmb_peer_barrier_flag_bytes()
+ * (its flag array, mapped by all peers) and a zero-initialised private device buffer of
+ * dlrmb_peer_barrier_state_bytes() (epochs; the last word counts waits that timed out after 4 s).
+ * dlrmb_peer_barrier(stream): everything this rank stored into peers' buffers earlier on `stream` is
+ * visible to a peer once that peer's own barrier call of the same `channel` (0..7) has passed, and
+ * vice versa.  `peer_flags` is a host array of `world` device pointers (rank r's flag array at r).
+ * Graph-capturable (the epoch lives in device memory).  Every rank must have its own GPU. */
+int32_t dlrmb_peer_barrier(int32_t device, uint32_t* const* peer_flags, int32_t world, int32_t rank, int32_t channel,
+                           uint32_t* state, dlrmb_stream stream);
+int64_t dlrmb_peer_barrier_flag_bytes(void);
+int64_t dlrmb_peer_barrier_state_bytes(void);
+/* Index exchange by peer stores: idx_local [ntab][B_local][P] (this rank's samples, every table) goes to
+ * the owners' index buffers: `dests_dev` is a DEVICE array of ntab pointers, entry k = the owner's buffer
+ * [B_global][P] of table k (inside its idx_owned [t_owner][B_global][P]); this rank fills rows
+ * [rank * B_local, (rank + 1) * B_local).  Follow with dlrmb_peer_barrier. */
+int32_t dlrmb_indices_scatter_p2p(int32_t device, const void* idx_local, int32_t idx_bytes, int32_t ntab,
+                                  int32_t B_local, int32_t P, const void* const* dests_dev, int32_t rank,
+                                  dlrmb_stream stream);
 
 /* Interaction backward fused with the gradient exchange: as dlrmb_interaction_bwd, but the gradient
  * row of feature slot f >= 1 of local sample b is stored at

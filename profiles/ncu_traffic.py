@@ -8,9 +8,10 @@ import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3,
         "usecond": 1.0, "msecond": 1e3}
-NAMES = {"lookup_gather_kernel": "lookup", "lookup_pool_kernel": "lookup", "update_tiles_kernel": "update",
+NAMES = {"lookup_sort_kernel": "lookup", "lookup_gather_kernel": "lookup", "lookup_pool_kernel": "lookup", "update_tiles_kernel": "update",
          "update_fixup_kernel": "update_fixup", "interaction_fwd_kernel": "interaction_fwd",
          "interaction_bwd_kernel": "interaction_bwd",
+         "interaction_fwd_mma_kernel": "interaction_fwd",
          "interaction_fwd_warp_kernel": "interaction_fwd", "interaction_bwd_warp_kernel": "interaction_bwd", "sort_small_kernel": "sort"}
 
 

@@ -104,7 +104,9 @@ def _step_worker(rank, world, port, q, D, BL, P, rows, steps):
             torch.cuda.synchronize()
             dist.barrier()
 
-        se.enable_peer_exchange(BL, barrier=barrier)
+        # index exchange by peer stores too (int64 ids here); the flag barrier itself needs one GPU per
+        # rank, so the ordering is the host-side barrier above
+        se.enable_peer_exchange(BL, barrier=barrier, P=P, idx_bytes=8)
         se.enable_fused_backward(BL)
         mine = se.local_ids
 

@@ -142,7 +142,7 @@ def run_case(rows, D, B, P, alpha, nb, use_graph, iters, interaction=True, label
         us = time_graph(lambda i: interaction_bwd(gs[i], Ts[i]), nb, use_graph, iters)
         rec("interaction_bwd", us, B * (w + 2 * F * D + D) * 4)
         res["interaction_bwd"]["gflops"] = 2.0 * B * F * F * D / us / 1e3
-    res["options"] = {k: _lib.get_option(k) for k in ("interact_general", "update_two_launches", "update_tile", "bwd_packed")}
+    res["options"] = {k: _lib.get_option(k) for k in ("interact_general", "update_two_launches", "update_tile")}
     t.close()
     del T, dT, idx
     torch.cuda.empty_cache()

@@ -123,7 +123,6 @@ static std::atomic<int>* find_option(const char* name) {
     if (!strcmp(name, "update_tile")) return &g_opt.update_tile;
     if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
     if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
-    if (!strcmp(name, "bwd_packed")) return &g_opt.bwd_packed;
     return nullptr;
 }
 

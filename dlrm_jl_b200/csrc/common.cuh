@@ -139,7 +139,6 @@ struct Options {
     std::atomic<int> update_tile{0};          // 4 | 8 | 16 | 32 entries per lane group (0 = chosen per batch)
     std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
     std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
-    std::atomic<int> bwd_packed{0};           // experiment: packed-S interaction backward                  // programmatic dependent launch for the chained kernels
 };
 extern Options g_opt;
 

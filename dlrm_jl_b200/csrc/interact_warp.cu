@@ -16,7 +16,9 @@
 //     flight per lane, no shared-memory staging of T at all); S is expanded once per sample into
 //     shared memory with every entry duplicated, so one broadcast LDS.128 feeds four FFMA2.  The
 //     per-output summation order (j ascending, one fused multiply-add per term) is the tiled
-//     kernel's, so both produce the same bits;
+//     kernel's, so both produce the same bits.  (Measured and not kept in round 2: S stored once with
+//     the FFMA2 halves carrying two different j -- half the S wavefronts, but F*d/2 register moves per
+//     sample: 23.8 vs 16.2 us at B = 2048; profiles/r02_interaction_variants_not_kept.txt.)
 //   * forward: T rows arrive by TMA bulk copies (cp.async.bulk, one per row, one mbarrier per
 //     warp) at bank-staggered row addresses and the Gram matrix is computed on the tensor cores in
 //     3xTF32 form (see interaction_fwd_mma_kernel); the sample's output row is assembled in the dead
@@ -182,161 +184,6 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
         for (int q = 0; q < G::NF; ++q) {
             const int f = f0 + q;
             const float4 r = make_float4(lo2[q].x, lo2[q].y, hi2[q].x, hi2[q].y);
-            if (SCATTER) {
-                if (f >= 1) {
-                    const SlotDestW dd = dests[f];
-                    float* row = dd.base + (sample_offset + b) * dd.sample_stride + dd.offset;
-                    reinterpret_cast<float4*>(row)[kl] = r;
-                }
-            } else {
-                reinterpret_cast<float4*>(dT)[((size_t)b * F + f) * G::LPS + kl] = r;
-            }
-            if (f == 0) {
-                const float* g = gb + 4 * kl;    // row width is odd in general: 4-byte aligned only
-                reinterpret_cast<float4*>(dx)[(size_t)b * G::LPS + kl] =
-                    make_float4(__fadd_rn(__ldg(g), r.x), __fadd_rn(__ldg(g + 1), r.y),
-                                __fadd_rn(__ldg(g + 2), r.z), __fadd_rn(__ldg(g + 3), r.w));
-            }
-        }
-    }
-    clock_out(clk, blockIdx.x);
-}
-
-// Packed-S variant of the backward.  Same mapping (a lane keeps its float4 column slice of all F rows of
-// T in registers), but S is stored ONCE per entry (no duplication) and the two halves of an FFMA2 carry
-// two different j: with the T slices held as pairs (t[2p].c, t[2p+1].c) per component c, one broadcast
-// LDS.128 of four consecutive S[f][j] feeds eight FFMA2, and the even-j / odd-j partial sums are added at
-// the end.  Half the S loads and a quarter of the S stores of the duplicated layout (ncu, B = 2048:
-// 1.82 M shared wavefronts per launch there), for F * d / 2 register moves per sample.
-template <int F, int D>
-struct Bwd2Geom {
-    static constexpr int LPS = D / 4;
-    static constexpr int SPW = 32 / LPS;
-    static constexpr int FP4 = (F + 3) & ~3;     // S row length, multiple of 4 (zero padded)
-    static constexpr int NP = FP4 / 2;           // j pairs
-    static constexpr int NPAIR = F * (F - 1) / 2;
-    static constexpr int NI = (NPAIR + 31) / 32;
-    static constexpr int SSTRIDE = F * FP4 + 4;  // floats per sample of S (+16 B bank stagger)
-    static constexpr int WARPS = 2;
-    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? 144 : 168; }
-    static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4; }
-};
-
-template <int F, int D, bool SCATTER>
-__global__ void __launch_bounds__(Bwd2Geom<F, D>::WARPS * 32) __maxnreg__((Bwd2Geom<F, D>::max_regs(SCATTER)))
-interaction_bwd_packed_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
-                              float* __restrict__ dT, float* __restrict__ dx,
-                              const SlotDestW* __restrict__ dests, long long sample_offset, unsigned long long* clk) {
-    using G = Bwd2Geom<F, D>;
-    extern __shared__ float4 smem4[];
-    clock_in(clk, blockIdx.x);
-    float* Sd = reinterpret_cast<float*>(smem4);                                   // [WARPS][SPW][SSTRIDE]
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long group = (long long)blockIdx.x * G::WARPS + warp;     // SPW consecutive samples
-    if (group * G::SPW >= B) {                                           // warp-uniform
-        clock_out(clk, blockIdx.x);
-        return;
-    }
-    const int sub = lane / G::LPS;
-    const int kl = lane - sub * G::LPS;
-    const long long b = group * G::SPW + sub;
-    const bool valid = b < B;
-
-    unsigned short pv[G::NI];
-    float gv[G::NI];
-    {
-        const float* gp = dOut + (size_t)(group * G::SPW) * width + D;
-#pragma unroll
-        for (int i = 0; i < G::NI; ++i) {
-            const int m = lane + 32 * i;
-            pv[i] = kPairTable.v[m < G::NPAIR ? m : 0];
-            gv[i] = (m < G::NPAIR) ? __ldg(gp + m) : 0.f;
-        }
-    }
-
-    // T column slices, held as j pairs per component: px[p] = (T[2p][4kl], T[2p+1][4kl]), ...
-    float2 px[G::NP], py[G::NP], pz[G::NP], pw[G::NP];
-    {
-        const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)(valid ? b : 0) * F * G::LPS + kl;
-        float4 t[G::FP4];
-#pragma unroll
-        for (int j = 0; j < G::FP4; ++j)
-            t[j] = (valid && j < F) ? __ldg(Tp + (size_t)j * G::LPS) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int p = 0; p < G::NP; ++p) {
-            px[p] = make_float2(t[2 * p].x, t[2 * p + 1].x);
-            py[p] = make_float2(t[2 * p].y, t[2 * p + 1].y);
-            pz[p] = make_float2(t[2 * p].z, t[2 * p + 1].z);
-            pw[p] = make_float2(t[2 * p].w, t[2 * p + 1].w);
-        }
-    }
-
-    // S of the warp's samples: Sw[s][f][j] = S[f][j], zero diagonal / padding
-    float* Sw = Sd + (size_t)warp * G::SPW * G::SSTRIDE;
-#pragma unroll 1
-    for (int s2 = 0; s2 < G::SPW; ++s2) {
-        const long long bb = group * G::SPW + s2;
-        if (bb >= B) break;                                  // warp-uniform
-        float* Sb = Sw + (size_t)s2 * G::SSTRIDE;
-        if (s2 > 0) {
-            const float* gp = dOut + (size_t)bb * width + D;
-#pragma unroll
-            for (int i = 0; i < G::NI; ++i) {
-                const int m = lane + 32 * i;
-                gv[i] = (m < G::NPAIR) ? __ldg(gp + m) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < G::NI; ++i) {
-            if (lane + 32 * i < G::NPAIR) {
-                const int hi = pv[i] >> 8, lo = pv[i] & 0xff;
-                Sb[hi * G::FP4 + lo] = gv[i];
-                Sb[lo * G::FP4 + hi] = gv[i];
-            }
-        }
-        for (int f = lane; f < F; f += 32) {
-            Sb[f * G::FP4 + f] = 0.f;
-#pragma unroll
-            for (int j = F; j < G::FP4; ++j) Sb[f * G::FP4 + j] = 0.f;
-        }
-    }
-    __syncwarp();
-    if (!valid) {
-        clock_out(clk, blockIdx.x);
-        return;
-    }
-
-    const float* Srow = Sw + (size_t)sub * G::SSTRIDE;
-    const float* gb = dOut + (size_t)b * width;
-#pragma unroll 1
-    for (int f0 = 0; f0 < F; f0 += 2) {
-        float2 ax[2], ay[2], az[2], aw[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) ax[q] = ay[q] = az[q] = aw[q] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int p4 = 0; p4 < G::FP4 / 4; ++p4) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (f0 + q >= F) continue;
-                const float4 sv = *reinterpret_cast<const float4*>(Srow + (f0 + q) * G::FP4 + 4 * p4);
-                const float2 s0 = make_float2(sv.x, sv.y), s1 = make_float2(sv.z, sv.w);
-                ax[q] = ffma2(s0, px[2 * p4], ax[q]);
-                ay[q] = ffma2(s0, py[2 * p4], ay[q]);
-                az[q] = ffma2(s0, pz[2 * p4], az[q]);
-                aw[q] = ffma2(s0, pw[2 * p4], aw[q]);
-                ax[q] = ffma2(s1, px[2 * p4 + 1], ax[q]);
-                ay[q] = ffma2(s1, py[2 * p4 + 1], ay[q]);
-                az[q] = ffma2(s1, pz[2 * p4 + 1], az[q]);
-                aw[q] = ffma2(s1, pw[2 * p4 + 1], aw[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int f = f0 + q;
-            if (f >= F) continue;
-            const float4 r = make_float4(ax[q].x + ax[q].y, ay[q].x + ay[q].y, az[q].x + az[q].y, aw[q].x + aw[q].y);
             if (SCATTER) {
                 if (f >= 1) {
                     const SlotDestW dd = dests[f];
@@ -523,33 +370,8 @@ int launch_fwd_mma(float* T, const float* x, int B, int width, float* out, cudaS
 }
 
 template <int F, int D>
-int launch_bwd_packed(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
-                      const void* dests, long long sample_offset, cudaStream_t s) {
-    using G = Bwd2Geom<F, D>;
-    static unsigned long long attr_done[2] = {0, 0};
-    const size_t smem = G::smem_bytes();
-    const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
-    const long long grid = (groups + G::WARPS - 1) / G::WARPS;
-    if (dests) {
-        int rc = ensure_smem_attr((const void*)interaction_bwd_packed_kernel<F, D, true>, (int)smem, &attr_done[1]);
-        if (rc) return rc;
-        interaction_bwd_packed_kernel<F, D, true><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
-            dOut, T, B, width, dT, dx, static_cast<const SlotDestW*>(dests), sample_offset, clock_slot(CLK_IBWD));
-    } else {
-        int rc = ensure_smem_attr((const void*)interaction_bwd_packed_kernel<F, D, false>, (int)smem, &attr_done[0]);
-        if (rc) return rc;
-        interaction_bwd_packed_kernel<F, D, false><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
-            dOut, T, B, width, dT, dx, nullptr, 0, clock_slot(CLK_IBWD));
-    }
-    DLRMB_LAUNCH_CHECK();
-    return DLRMB_OK;
-}
-
-template <int F, int D>
 int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
                     const void* dests, long long sample_offset, cudaStream_t s) {
-    if (g_opt.bwd_packed.load(std::memory_order_relaxed))
-        return launch_bwd_packed<F, D>(dOut, T, B, width, dT, dx, dests, sample_offset, s);
     using G = BwdGeom<F, D>;
     static unsigned long long attr_done[2] = {0, 0};
     const size_t smem = G::smem_bytes();

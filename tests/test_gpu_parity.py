@@ -1079,24 +1079,3 @@ def test_comm_c_abi_world_one_round_trip():
     assert torch.equal(out, blob)
     torch.cuda.synchronize()
     _lib.check(lib.dlrmb_comm_destroy(h))
-
-
-@pytest.mark.parametrize("B,F,d", WARP_SHAPES)
-def test_interaction_backward_packed_variant_vs_oracle(B, F, d, lib_options):
-    """The packed-S backward (option "bwd_packed"): same contract, different summation association
-    (even-j / odd-j partial sums), so it is held to the 1e-5 tolerance rather than to the tiled kernel's bits."""
-    from dlrm_jl_b200.interact import interaction_bwd, interaction_width
-    rng = np.random.default_rng(B + 3 * F + d)
-    T = rng.standard_normal((B, F, d)).astype(np.float32)
-    Td = torch.from_numpy(T).to(_dev())
-    for pad in (1, 16):
-        w = interaction_width(F, d, pad)
-        g = rng.standard_normal((B, w)).astype(np.float32)
-        gd = torch.from_numpy(g).to(_dev())
-        lib_options("bwd_packed", 0)
-        dx0, dT0 = interaction_bwd(gd, Td, pad)
-        lib_options("bwd_packed", 1)
-        dx1, dT1 = interaction_bwd(gd, Td, pad)
-        dx_ref, dT_ref = O.interaction_bwd(g, T, w - d - F * (F - 1) // 2)
-        assert O.rel_err(dT1.cpu().numpy(), dT_ref) < FWD_RTOL and O.rel_err(dx1.cpu().numpy(), dx_ref) < FWD_RTOL
-        assert O.rel_err(dT1.cpu().numpy(), dT0.cpu().numpy()) < FWD_RTOL

@@ -379,7 +379,7 @@ def run_ours(args):
             ok, why = 1.0, ""
             try:
                 se.enable_peer_exchange(B, flag_barrier=(args.barrier == "flags"), P=wl["P"], idx_bytes=4)
-                se.enable_fused_backward(B)
+                se.enable_fused_backward(B, split_dx=not args.no_split_dx)
             except Exception as exc:  # noqa: BLE001 - e.g. CUDA IPC not permitted in this container
                 ok, why = 0.0, f"{type(exc).__name__}: {exc}"
             flag = torch.tensor([ok], device=dev)
@@ -1146,6 +1146,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
+    ap.add_argument("--no-split-dx", action="store_true",
+                    help="multi-GPU: one interaction-backward kernel for dx and the gradient exchange (the bottom MLP's backward then "
+                         "waits for the peer stores)")
     ap.add_argument("--late-allreduce", action="store_true",
                     help="multi-GPU: one dense all-reduce after the whole backward pass instead of starting the top MLP's share early")
     ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],

@@ -4,8 +4,8 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
 TAG=${TAG:-r02c}
-timeout 300 python benchmarks/cabi_sharded_step.py --gpus 2 --mode nccl > $O/${TAG}_cabi_nccl.json 2> $O/${TAG}_cabi_nccl.err; echo "cabi nccl rc=$?"; cat $O/${TAG}_cabi_nccl.json; tail -3 $O/${TAG}_cabi_nccl.err
-timeout 300 python benchmarks/cabi_sharded_step.py --gpus 2 --mode p2p > $O/${TAG}_cabi_p2p.json 2> $O/${TAG}_cabi_p2p.err; echo "cabi p2p rc=$?"; cat $O/${TAG}_cabi_p2p.json; tail -3 $O/${TAG}_cabi_p2p.err
+timeout 300 python tests/cabi_sharded_step.py --gpus 2 --mode nccl > $O/${TAG}_cabi_nccl.json 2> $O/${TAG}_cabi_nccl.err; echo "cabi nccl rc=$?"; cat $O/${TAG}_cabi_nccl.json; tail -3 $O/${TAG}_cabi_nccl.err
+timeout 300 python tests/cabi_sharded_step.py --gpus 2 --mode p2p > $O/${TAG}_cabi_p2p.json 2> $O/${TAG}_cabi_p2p.err; echo "cabi p2p rc=$?"; cat $O/${TAG}_cabi_p2p.json; tail -3 $O/${TAG}_cabi_p2p.err
 timeout 600 python bench.py --no-cpu-baseline --no-host-leg > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err; echo "bench n1 rc=$?"
 for b in flags nccl; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --barrier $b > $O/${TAG}_bench_n2_$b.json 2> $O/${TAG}_bench_n2_$b.err; echo "bench n2 $b rc=$?"

@@ -1,12 +1,14 @@
 #!/bin/bash
-# Round 2, GPU visit H (8 GPUs): bench at N = 8.
+# Round 2, GPU visit H (8 GPUs): bench at N = 8 with and without the split-dx backward, then N = 4.
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
 TAG=${TAG:-r02h}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 > $O/${TAG}_bench_n8.json 2> $O/${TAG}_bench_n8.err; echo "bench n8 rc=$?"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 > $O/${TAG}_bench_n8.json 2> $O/${TAG}_bench_n8.err; echo "bench n8 rc=$?"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --no-split-dx > $O/${TAG}_bench_n8_nosplit.json 2> $O/${TAG}_bench_n8_nosplit.err; echo "bench n8 nosplit rc=$?"
+CUDA_VISIBLE_DEVICES=0,1,2,3 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 4 --no-split-dx > $O/${TAG}_bench_n4_nosplit.json 2> $O/${TAG}_bench_n4_nosplit.err; echo "bench n4 rc=$?"
 python - <<PY
 import json
-for f in ("bench_n8",):
+for f in ("bench_n8","bench_n8_nosplit","bench_n4_nosplit"):
     try:
         r=json.load(open("$O/${TAG}_%s.json"%f))
         print(f, round(r["value"]), round(r["ms_per_step"],4), "e2e", round(r["e2e"]["value"]), {k:(round(v['in_step_us'],2), round(v.get('event_pair_us',0),2)) for k,v in r.get('kernels',{}).items() if not k.startswith('_')}, r['config'].get('exchange_check'), r['config'].get('barrier_timeouts'))

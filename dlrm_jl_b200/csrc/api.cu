@@ -432,6 +432,16 @@ int32_t dlrmb_interaction_bwd_scatter(int32_t device, const float* dOut, const f
                                      (long long)sample_offset, device_sm_count(device), (cudaStream_t)stream);
 }
 
+int32_t dlrmb_interaction_bwd_dx(int32_t device, const float* dOut, const float* T, int32_t B, int32_t F, int32_t d,
+                                 int32_t pad_to_mul, float* dx, dlrmb_stream stream) {
+    int rc = check_interaction_args(B, F, d, pad_to_mul);
+    if (rc) return rc;
+    DLRMB_REQUIRE(dOut && T && dx, "null buffer");
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    return launch_interaction_bwd_dx(dOut, T, B, F, d, pad_to_mul, dx, device_sm_count(device), (cudaStream_t)stream);
+}
+
 int32_t dlrmb_embedding_sort(dlrmb_tables* t, const void* idx, int32_t idx_bytes, int32_t idx_base,
                              int32_t B, int32_t P, dlrmb_stream stream) {
     GUARD(t);

@@ -203,6 +203,8 @@ int launch_interaction_bwd(const float* dOut, const float* T, int B, int F, int 
 int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
                               float* dT, float* dx, const void* dests, long long sample_offset,
                               int sm_count, cudaStream_t s);
+int launch_interaction_bwd_dx(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul, float* dx,
+                              int sm_count, cudaStream_t s);
 bool interaction_has_warp_path(int F, int d);
 int launch_sort(dlrmb_tables* t, const void* idx, int idx_bytes, int idx_base, int B, int P,
                 cudaStream_t s);

@@ -482,6 +482,50 @@ interaction_bwd_generic_kernel(const float* __restrict__ dOut, const float* __re
     }
 }
 
+// dx alone: dx[b] = dOut[b][:d] + sum_j S[0][j] T[b][j]  (S[0][j] = the gradient of pair (j, 0), j >= 1).
+// The sharded step launches it in front of the scattering backward: the bottom MLP's backward only needs
+// dx, so it can start while the full pullback is still pushing its 24 MB of gradient rows over NVLink.
+// One thread per (sample, 16-byte chunk); terms are accumulated in ascending j with one fused
+// multiply-add each -- the order of the full kernels, so the bits agree with their dx.
+__global__ void __launch_bounds__(256)
+interaction_bwd_dx_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int F, int d4, int width,
+                          float* __restrict__ dx) {
+    const int64_t n = (int64_t)B * d4;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const int d = d4 * 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int64_t b = i / d4;
+        const int c = (int)(i - b * d4);
+        const float* g = dOut + (size_t)b * width;
+        const float4* Tb = reinterpret_cast<const float4*>(T) + (size_t)b * F * d4 + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        {   // j = 0: S[0][0] = 0 (kept so that signed zeros match the full kernels)
+            const float4 t = __ldg(Tb);
+            acc.x = fmaf(0.f, t.x, acc.x); acc.y = fmaf(0.f, t.y, acc.y); acc.z = fmaf(0.f, t.z, acc.z); acc.w = fmaf(0.f, t.w, acc.w);
+        }
+        for (int j = 1; j < F; ++j) {
+            const float sj = __ldg(g + d + j * (j - 1) / 2);
+            const float4 t = __ldg(Tb + (size_t)j * d4);
+            acc.x = fmaf(sj, t.x, acc.x); acc.y = fmaf(sj, t.y, acc.y); acc.z = fmaf(sj, t.z, acc.z); acc.w = fmaf(sj, t.w, acc.w);
+        }
+        const float* gx = g + 4 * c;      // row width is odd in general: 4-byte aligned only
+        reinterpret_cast<float4*>(dx)[i] = make_float4(__fadd_rn(__ldg(gx), acc.x), __fadd_rn(__ldg(gx + 1), acc.y),
+                                                       __fadd_rn(__ldg(gx + 2), acc.z), __fadd_rn(__ldg(gx + 3), acc.w));
+    }
+}
+
+int launch_interaction_bwd_dx(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul, float* dx,
+                              int sm_count, cudaStream_t s) {
+    const int width = interaction_width(F, d, pad_to_mul);
+    DLRMB_REQUIRE(d % 4 == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0,
+                  "dlrmb_interaction_bwd_dx needs d %% 4 == 0 and 16-byte aligned T / dx");
+    int64_t blocks = ceil_div64((int64_t)B * (d / 4), 256);
+    if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+    interaction_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, s>>>(dOut, T, B, F, d / 4, width, dx);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
 int launch_interaction_bwd_ex(const float* dOut, const float* T, int B, int F, int d, int pad_to_mul,
                               float* dT, float* dx, const void* dests, long long sample_offset,
                               int sm_count, cudaStream_t s);

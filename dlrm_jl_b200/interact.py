@@ -86,10 +86,17 @@ class ScatterPlan:
     embedding tables are sharded: `dests` is a device int64 tensor [F][3] laid out as the C struct
     dlrmb_slot_dest {base pointer, floats per destination sample, float offset of the table}."""
 
-    def __init__(self, dests: torch.Tensor, sample_offset: int):
+    def __init__(self, dests: torch.Tensor, sample_offset: int, stream: "torch.cuda.Stream" = None):
+        """``stream``: when given, the backward is split -- dx alone (dlrmb_interaction_bwd_dx) on the
+        current stream, the full pullback with the peer stores on ``stream`` -- so whatever consumes dx
+        (the bottom MLP's backward) overlaps the gradient exchange; wait for ``done`` before using the
+        exchanged rows (ShardedEmbedding.finish_backward does)."""
         assert dests.dtype == torch.int64 and dests.dim() == 2 and dests.shape[1] == 3 and dests.is_contiguous()
         self.dests = dests
         self.sample_offset = int(sample_offset)
+        self.stream = stream
+        self.done = torch.cuda.Event() if stream is not None else None
+        self._keep = None
 
 
 class _DotInteractionScatterFn(torch.autograd.Function):
@@ -120,6 +127,21 @@ class _DotInteractionScatterFn(torch.autograd.Function):
         dOut = dOut.contiguous()
         dx = torch.empty((B, d), dtype=torch.float32, device=T.device)
         lib = _lib.load()
+        if plan.stream is not None and d % 4 == 0:
+            # dx first, on this stream: autograd's consumers of dx do not wait for the peer stores
+            _lib.check(lib.dlrmb_interaction_bwd_dx(
+                T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul, dx.data_ptr(), _stream(T)))
+            cur = torch.cuda.current_stream(T.device)
+            plan.stream.wait_stream(cur)
+            dx_full = torch.empty_like(dx)
+            with torch.cuda.stream(plan.stream):
+                with _prof.range("interaction_bwd"):
+                    _lib.check(lib.dlrmb_interaction_bwd_scatter(
+                        T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
+                        plan.dests.data_ptr(), plan.sample_offset, dx_full.data_ptr(), plan.stream.cuda_stream))
+                plan.done.record(plan.stream)
+            plan._keep = (dOut, dx_full)      # alive until the exchange has been joined (finish_backward)
+            return dx, None, None, None
         with _prof.range("interaction_bwd"):
             _lib.check(lib.dlrmb_interaction_bwd_scatter(
                 T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,

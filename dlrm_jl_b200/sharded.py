@@ -268,7 +268,7 @@ class PeerExchange:
         self._mapped.append(ptrs)
         return h, p.value, ptrs
 
-    def enable_gradient_exchange(self, sharding: "TableSharding", B_local: int, D: int):
+    def enable_gradient_exchange(self, sharding: "TableSharding", B_local: int, D: int, split_dx: bool = False):
         """Gradient buffer G [B_global][tables of this rank][D] on every rank, mapped everywhere, and
         the per-slot destination table the scattered interaction backward reads."""
         from .embedding import _DevicePtrView
@@ -283,7 +283,7 @@ class PeerExchange:
             o = sharding.owner[k]
             rows.append([self.peer_G_ptrs[o], counts[o] * D, sharding.local[o].index(k) * D])
         dests = torch.tensor(rows, dtype=torch.int64, device=self.device)
-        return ScatterPlan(dests, self.rank * B_local)
+        return ScatterPlan(dests, self.rank * B_local, torch.cuda.Stream(self.device) if split_dx else None)
 
     def barrier(self, channel: int = 0) -> None:
         """Order this rank's earlier peer stores before every rank's later reads (stream-ordered).
@@ -388,12 +388,14 @@ class ShardedEmbedding:
         self.peer: Optional[PeerExchange] = None
         self.scatter_plan = None
 
-    def enable_fused_backward(self, B_local: int) -> None:
+    def enable_fused_backward(self, B_local: int, split_dx: bool = False) -> None:
         """Also fuse the backward exchange: the interaction backward stores dT rows into the owners'
         gradient buffers (pass `self.scatter_plan` to DotInteraction), `finish_backward()` orders the
-        stores before the sparse update.  Needs enable_peer_exchange first."""
+        stores before the sparse update.  Needs enable_peer_exchange first.  ``split_dx``: dx is computed
+        by a small kernel of its own ahead of the scattering pullback, which then runs on a side stream
+        beside the bottom MLP's backward."""
         assert self.peer is not None
-        self.scatter_plan = self.peer.enable_gradient_exchange(self.sharding, B_local, self.D)
+        self.scatter_plan = self.peer.enable_gradient_exchange(self.sharding, B_local, self.D, split_dx)
 
     def lookup_fused(self, idx_local: torch.Tensor) -> torch.Tensor:
         """Forward of the fully fused path: no autograd node (the gradient never comes back through
@@ -426,6 +428,10 @@ class ShardedEmbedding:
         if len(self.local_ids) and getattr(self.tables, "_pending_side", False):
             torch.cuda.current_stream(self.tables.device).wait_event(self.tables._sorted_event)
             self.tables._pending_side = False
+        plan = self.scatter_plan
+        if plan is not None and plan.stream is not None and plan._keep is not None:
+            torch.cuda.current_stream(self.tables.device).wait_event(plan.done)     # this rank's peer stores are issued
+            plan._keep = None
         self.peer.barrier(2)
         self.owned_grad = self.peer.G
 

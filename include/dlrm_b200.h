@@ -293,6 +293,13 @@ int32_t dlrmb_comm_a2a_bwd(dlrmb_comm* c, const int32_t* owner, int32_t ntab, co
 int32_t dlrmb_comm_allreduce_f32(dlrmb_comm* c, float* buf, int64_t n, dlrmb_stream stream);
 int32_t dlrmb_comm_allgather(dlrmb_comm* c, const void* send, void* recv, int64_t nbytes, dlrmb_stream stream);
 
+/* dx of dot_back alone (src/model/interact.jl:434: dx = dOut[1:d, :] + dT[1:d, :]) without the rest of dT:
+ * what the bottom MLP's backward waits for.  The sharded step launches it in front of
+ * dlrmb_interaction_bwd_scatter (on another stream), so the bottom MLP's backward overlaps the gradient
+ * exchange.  Same bits as the dx of the full kernels for the specialised shapes.  Needs d % 4 == 0. */
+int32_t dlrmb_interaction_bwd_dx(int32_t device, const float* dOut, const float* T, int32_t B, int32_t F, int32_t d,
+                                 int32_t pad_to_mul, float* dx, dlrmb_stream stream);
+
 /* ---- host-buffer entry points: every pointer is host memory (pageable or pinned); this is
  * the form a CPU-resident DLRM.jl model calls.  Copies run inside the call. -------------- */
 int32_t dlrmb_embedding_fwd_host(dlrmb_tables* t, const void* idx, int32_t idx_bytes,

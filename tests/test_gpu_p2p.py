@@ -107,7 +107,7 @@ def _step_worker(rank, world, port, q, D, BL, P, rows, steps):
         # index exchange by peer stores too (int64 ids here); the flag barrier itself needs one GPU per
         # rank, so the ordering is the host-side barrier above
         se.enable_peer_exchange(BL, barrier=barrier, P=P, idx_bytes=8)
-        se.enable_fused_backward(BL)
+        se.enable_fused_backward(BL, split_dx=(D == 128))      # the bench's form: dx first, peer stores on a side stream
         mine = se.local_ids
 
         def gather_tables():

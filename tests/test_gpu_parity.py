@@ -1038,7 +1038,7 @@ def test_terabyte_shaped_properties():
 def test_comm_c_abi_world_one_round_trip():
     """The dlrmb_comm_* entry points (NCCL behind the C ABI) with a one-rank communicator: the exchanges
     degenerate to sends to self, which still run the real NCCL group calls and the pack / unpack kernels.
-    (The multi-rank behaviour is exercised on 2+ GPUs by benchmarks/cabi_sharded_step.py.)"""
+    (The multi-rank behaviour is exercised on 2+ GPUs by tests/cabi_sharded_step.py.)"""
     import ctypes as C
     from dlrm_jl_b200 import _lib
     lib = _lib.load()
@@ -1079,3 +1079,35 @@ def test_comm_c_abi_world_one_round_trip():
     assert torch.equal(out, blob)
     torch.cuda.synchronize()
     _lib.check(lib.dlrmb_comm_destroy(h))
+
+
+@pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (77, 27, 64), (33, 8, 16), (19, 11, 128), (5, 1, 16)])
+def test_interaction_backward_dx_alone_and_split_scatter(B, F, d):
+    """dlrmb_interaction_bwd_dx == the dx of the full pullback (same bits for the specialised shapes: same
+    summation order), and a ScatterPlan with a side stream (dx first, peer stores beside whatever consumes
+    dx) gives the same dx and the same scattered rows as the single-kernel scatter."""
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    from dlrm_jl_b200.interact import DotInteraction, ScatterPlan, interaction_bwd, interaction_width
+    rng = np.random.default_rng(B * 3 + F)
+    T = torch.from_numpy(rng.standard_normal((B, F, d)).astype(np.float32)).to(_dev())
+    g = torch.from_numpy(rng.standard_normal((B, interaction_width(F, d))).astype(np.float32)).to(_dev())
+    dx_ref, dT_ref = interaction_bwd(g, T)
+    dx = torch.empty((B, d), device=_dev())
+    _lib.check(_lib.load().dlrmb_interaction_bwd_dx(0, g.data_ptr(), T.data_ptr(), B, F, d, 1, dx.data_ptr(),
+                                                    int(torch.cuda.current_stream().cuda_stream)))
+    if _lib.load().dlrmb_interaction_has_warp_path(F, d):
+        assert torch.equal(dx, dx_ref)
+    assert O.rel_err(dx.cpu().numpy(), dx_ref.cpu().numpy()) < 1e-6
+    if F < 2:
+        return
+    buf = torch.full((B + 3, F - 1, d), -7.0, device=_dev())
+    dests = torch.zeros((F, 3), dtype=torch.int64)
+    for f in range(1, F):
+        dests[f, 0], dests[f, 1], dests[f, 2] = buf.data_ptr(), (F - 1) * d, (f - 1) * d
+    plan = ScatterPlan(dests.to(_dev()), 2, stream=torch.cuda.Stream())
+    x = T[:, 0].clone().requires_grad_(True)
+    DotInteraction()(x, T.clone(), scatter=plan).backward(g)
+    torch.cuda.current_stream().wait_event(plan.done)
+    assert torch.equal(x.grad, dx)
+    assert torch.equal(buf[2:2 + B], dT_ref[:, 1:]) and torch.all(buf[:2] == -7.0) and torch.all(buf[2 + B:] == -7.0)

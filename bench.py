@@ -379,7 +379,7 @@ def run_ours(args):
             ok, why = 1.0, ""
             try:
                 se.enable_peer_exchange(B, flag_barrier=(args.barrier == "flags"), P=wl["P"], idx_bytes=4)
-                se.enable_fused_backward(B, split_dx=not args.no_split_dx)
+                se.enable_fused_backward(B, split_dx=args.split_dx)
             except Exception as exc:  # noqa: BLE001 - e.g. CUDA IPC not permitted in this container
                 ok, why = 0.0, f"{type(exc).__name__}: {exc}"
             flag = torch.tensor([ok], device=dev)
@@ -619,10 +619,11 @@ def run_ours(args):
     # The most faithful clock: %globaltimer stamps taken by the kernels themselves (dlrmb_clock_enable) inside
     # a capture of the REAL multi-stream step graph, replayed over the timed batches: min(CTA entry) to
     # max(CTA exit) of each kernel, no event nodes, no serialisation.
-    dev_clock = None
+    dev_clock, timeline = None, None
     if graph is not None:
         try:
             dev_clock = device_clock_pass(train_step, (s_dense, s_labels, s_idx), devb[W:W + K], dev)
+            timeline = dev_clock.pop("_timeline", None)
             for n, us in dev_clock.items():
                 if n in prof:
                     prof[n]["device_clock_us"] = us
@@ -748,6 +749,10 @@ def run_ours(args):
         }
         line.update(hot_path_report(wl, world, rank, se, prof, ms_step, replay))
         line["hot_path"]["kernel_timing"] = prof_mode
+        if timeline:
+            line["hot_path"]["timeline_us"] = dict(timeline, note="[first CTA in, last CTA out] of each kernel, microseconds from the "
+                                                   "first stamp of the step, from the kernels' own %globaltimer stamps inside the step graph "
+                                                   f"(rank 0; step = {ms_step * 1e3:.0f} us)")
         if world == 1 and not args.no_host_leg:
             try:
                 line["e2e_host"] = e2e_host_leg(se, wl, host[W:W + min(K, 10)], dev)
@@ -788,7 +793,7 @@ def device_clock_pass(train_step, statics, batches, dev):
             train_step(*statics)
     finally:
         _lib.check(lib.dlrmb_clock_enable(None))
-    acc = {}
+    acc, starts, ends = {}, {}, {}
     for b in batches:
         for dst, src in zip(statics, b):
             dst.copy_(src)
@@ -798,11 +803,17 @@ def device_clock_pass(train_step, statics, batches, dev):
         torch.cuda.synchronize()
         t0 = view[:, :, 0].min(dim=1).values.cpu().tolist()
         t1 = view[:, :, 1].max(dim=1).values.cpu().tolist()
-        for k in range(nk):
-            if t1[k] > 0 and t0[k] < (1 << 62):
-                acc.setdefault(CLOCK_NAMES[k], []).append((t1[k] - t0[k]) * 1e-3)
+        live = [k for k in range(nk) if t1[k] > 0 and t0[k] < (1 << 62)]
+        origin = min(t0[k] for k in live) if live else 0
+        for k in live:
+            acc.setdefault(CLOCK_NAMES[k], []).append((t1[k] - t0[k]) * 1e-3)
+            starts.setdefault(CLOCK_NAMES[k], []).append((t0[k] - origin) * 1e-3)
+            ends.setdefault(CLOCK_NAMES[k], []).append((t1[k] - origin) * 1e-3)
     del g
-    return {k: float(np.mean(v)) for k, v in acc.items()}
+    out = {k: float(np.mean(v)) for k, v in acc.items()}
+    # where the kernels sit in the step: microseconds from the first stamp of the step (the lookup's first CTA)
+    out["_timeline"] = {k: [round(float(np.mean(starts[k])), 1), round(float(np.mean(ends[k])), 1)] for k in acc}
+    return out
 
 
 CHECK_ROWS = 64
@@ -1146,9 +1157,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")
-    ap.add_argument("--no-split-dx", action="store_true",
-                    help="multi-GPU: one interaction-backward kernel for dx and the gradient exchange (the bottom MLP's backward then "
-                         "waits for the peer stores)")
+    ap.add_argument("--split-dx", action="store_true",
+                    help="multi-GPU: dx from a kernel of its own ahead of the scattering interaction backward, which then runs on a "
+                         "side stream beside the bottom MLP's backward (measured: no gain at 2 and 8 GPUs, off by default)")
     ap.add_argument("--late-allreduce", action="store_true",
                     help="multi-GPU: one dense all-reduce after the whole backward pass instead of starting the top MLP's share early")
     ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],

@@ -123,6 +123,7 @@ static std::atomic<int>* find_option(const char* name) {
     if (!strcmp(name, "update_tile")) return &g_opt.update_tile;
     if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
     if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
+    if (!strcmp(name, "fwd_ksplit")) return &g_opt.fwd_ksplit;
     return nullptr;
 }
 

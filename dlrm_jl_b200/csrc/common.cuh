@@ -136,9 +136,11 @@ constexpr int kFusedSortMax = 4096;
 struct Options {
     std::atomic<int> interact_general{0};     // 1: general tiled interaction kernels even for the specialised shapes
     std::atomic<int> update_two_launches{0};  // 1: separate fix-up launch at every batch size
-    std::atomic<int> update_tile{0};          // 4 | 8 | 16 | 32 entries per lane group (0 = chosen per batch)
+    std::atomic<int> update_tile{0};          // 4, 8, .. 32 entries per lane group (0 = chosen per batch)
     std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
     std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
+    std::atomic<int> fwd_ksplit{1};           // tensor-core forward: 0 = one warp per sample always, 1 = two warps per sample for
+                                              // one-wave batches (default), 2 = two warps per sample always
 };
 extern Options g_opt;
 

@@ -18,7 +18,7 @@
 //     per-output summation order (j ascending, one fused multiply-add per term) is the tiled
 //     kernel's, so both produce the same bits.  (Measured and not kept in round 2: S stored once with
 //     the FFMA2 halves carrying two different j -- half the S wavefronts, but F*d/2 register moves per
-//     sample: 23.8 vs 16.2 us at B = 2048; profiles/r02_interaction_variants_not_kept.txt.)
+//     sample: 23.8 vs 16.2 us at B = 2048; profiles/r02_interaction_variants.txt.)
 //   * forward: T rows arrive by TMA bulk copies (cp.async.bulk, one per row, one mbarrier per
 //     warp) at bank-staggered row addresses and the Gram matrix is computed on the tensor cores in
 //     3xTF32 form (see interaction_fwd_mma_kernel); the sample's output row is assembled in the dead
@@ -356,6 +356,144 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
     clock_out(clk, blockIdx.x);
 }
 
+// Two warps per sample, for batches that are a single wave of the kernel above (B <= 4096 at d >= 64): the
+// CTA (64 threads) owns ONE sample, warp h contracts the k range [h * D/2, (h+1) * D/2) of the same shared
+// tile, warp 1 hands its partial accumulators to warp 0 through the dead part of the tile.  At one sample
+// per warp the MMA phase is a dependent chain per accumulator tile on 14 warps per SM (tensor pipe 36 %
+// active, ncu); splitting k halves that chain and doubles the warps that feed the pipe, for three
+// 64-thread barriers and 3 KB of shared traffic.  At large batches (several waves, the load of one
+// sample overlapping the MMAs of another) the one-warp kernel is the faster one and stays in charge.
+template <int F, int D>
+__global__ void __launch_bounds__(64)
+interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int width,
+                                  float* __restrict__ out, unsigned long long* clk) {
+    using G = MmaGeom<F, D>;
+    extern __shared__ float4 smem4[];
+    clock_in(clk, blockIdx.x);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* Ts = reinterpret_cast<float*>(smem4);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(Ts + G::SSZ);
+    const long long b = blockIdx.x;          // grid = B
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                     ::"r"(smem_addr(bar)), "r"((unsigned)(F * D * sizeof(float))) : "memory");
+    }
+    __syncthreads();
+    if (warp == 0 && lane < F) {   // one TMA bulk copy per feature row (slot 0 from x when it is handed separately)
+        const float* src = (x != nullptr && lane == 0) ? x + (size_t)b * D : T + ((size_t)b * F + lane) * D;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(smem_addr(Ts + lane * G::LDF)), "l"(src), "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar))
+                     : "memory");
+    }
+
+    const int g = lane >> 2, t = lane & 3;
+    int roff[G::RBP];
+#pragma unroll
+    for (int rb = 0; rb < G::RBP; ++rb) roff[rb] = min(8 * rb + g, F - 1) * G::LDF + t;   // clamped rows are discarded below
+
+    float acc[G::MT][G::NT][4];
+#pragma unroll
+    for (int i = 0; i < G::MT; ++i)
+#pragma unroll
+        for (int j = 0; j < G::NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+    {   // wait for the tile (both warps poll the same barrier)
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done) : "r"(smem_addr(bar)), "r"(0) : "memory");
+        }
+    }
+    if (x != nullptr && warp == 1) {   // fused fast_vcat: x also becomes slot 0 of T in global memory
+        for (int c = lane; c < D / 4; c += 32)
+            reinterpret_cast<float4*>(T + (size_t)b * F * D)[c] = reinterpret_cast<const float4*>(Ts)[c];
+    }
+
+    const int kbeg = warp * (D / 2);
+#pragma unroll 2
+    for (int k0 = kbeg; k0 < kbeg + D / 2; k0 += 8) {
+        unsigned hi[G::RBP][2], lo[G::RBP][2];
+#pragma unroll
+        for (int rb = 0; rb < G::RBP; ++rb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float v = Ts[roff[rb] + k0 + 4 * h];
+                const unsigned vh = __float_as_uint(v) & 0xffffe000u;
+                hi[rb][h] = vh;
+                lo[rb][h] = __float_as_uint(v - __uint_as_float(vh)) & 0xffffe000u;
+            }
+#pragma unroll
+        for (int i = 0; i < G::MT; ++i) {
+            const unsigned ah[4] = {hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1]};
+            const unsigned al[4] = {lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1]};
+#pragma unroll
+            for (int j = 0; j < G::NT; ++j) {
+                if (j > 2 * i + 1) continue;            // tile entirely above the diagonal
+                mma_tf32(acc[i][j], al, hi[j][0], hi[j][1]);
+                mma_tf32(acc[i][j], ah, lo[j][0], lo[j][1]);
+                mma_tf32(acc[i][j], ah, hi[j][0], hi[j][1]);
+            }
+        }
+    }
+    __syncthreads();   // both warps are done reading rows >= 1: their space becomes scratch
+
+    float* Os = Ts + G::LDF;                  // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
+    float* red = Os + ((G::NPAIR + 3) & ~3);  // warp 1's partial accumulators: [tile][e][lane]
+    static_assert(((G::NPAIR + 3) & ~3) + G::MT * G::NT * 4 * 32 <= (F - 1) * G::LDF, "scratch must fit behind row 0");
+    if (warp == 1) {
+#pragma unroll
+        for (int i = 0; i < G::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < G::NT; ++j) {
+                if (j > 2 * i + 1) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) red[((i * G::NT + j) * 4 + e) * 32 + lane] = acc[i][j][e];
+            }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < G::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < G::NT; ++j) {
+                if (j > 2 * i + 1) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = acc[i][j][e] + red[((i * G::NT + j) * 4 + e) * 32 + lane];
+                    const int row = 16 * i + g + ((e & 2) ? 8 : 0);
+                    const int col = 8 * j + 2 * t + (e & 1);
+                    if (col < row && row < F) Os[row * (row - 1) / 2 + col] = v;
+                }
+            }
+    }
+    __syncthreads();
+
+    float* og = out + (size_t)b * width;
+    for (int c = threadIdx.x; c < D; c += 64) og[c] = Ts[c];
+    for (int c = threadIdx.x; c < G::NPAIR; c += 64) og[D + c] = Os[c];
+    for (int c = D + G::NPAIR + threadIdx.x; c < width; c += 64) og[c] = 0.f;   // pad_to_mul padding
+    clock_out(clk, blockIdx.x);
+}
+
+template <int F, int D>
+int launch_fwd_mma_ksplit(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
+    using G = MmaGeom<F, D>;
+    static unsigned long long attr_done = 0;
+    const size_t smem = (size_t)G::SSZ * 4 + 16;
+    int rc = ensure_smem_attr((const void*)interaction_fwd_mma_ksplit_kernel<F, D>, (int)smem, &attr_done);
+    if (rc) return rc;
+    interaction_fwd_mma_ksplit_kernel<F, D><<<(unsigned)B, 64, smem, s>>>(T, x, B, width, out, clock_slot(CLK_IFWD));
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
 template <int F, int D>
 int launch_fwd_mma(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
     using G = MmaGeom<F, D>;
@@ -392,6 +530,8 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
     return DLRMB_OK;
 }
 
+constexpr int kKsplitMaxBatch = 4096;   // up to here the forward is one wave of CTAs on 148 SMs
+
 // dlrmb_set_option("interact_general", 1) sends the specialised shapes through the general tiled kernels
 // of interact.cu (parity tests compare the two); default = the specialised kernels.
 bool warp_path_enabled() { return g_opt.interact_general.load(std::memory_order_relaxed) == 0; }
@@ -414,6 +554,13 @@ bool interaction_has_warp_path(int F, int d) {
 int try_interaction_fwd_warp(float* T, const float* x, int B, int F, int d, int width, float* out,
                              cudaStream_t s) {
     if (!warp_path_enabled()) return -1;
+    {   // one-wave batches of the wide Criteo shapes: two warps per sample ("fwd_ksplit" = 0 keeps one warp per sample)
+        const int mode = g_opt.fwd_ksplit.load(std::memory_order_relaxed);
+        if (mode != 0 && (mode == 2 || B <= kKsplitMaxBatch)) {
+            if (F == 27 && d == 128) return launch_fwd_mma_ksplit<27, 128>(T, x, B, width, out, s);
+            if (F == 27 && d == 64) return launch_fwd_mma_ksplit<27, 64>(T, x, B, width, out, s);
+        }
+    }
 #define X(FF, DD) if (F == FF && d == DD) return launch_fwd_mma<FF, DD>(T, x, B, width, out, s);
     DLRMB_WARP_SHAPES(X)
 #undef X

@@ -477,16 +477,20 @@ static int lanes_per_row_log2(int C) {
     return l;
 }
 
-// Entries per lane-group tile: the smallest of 4..32 with which the whole batch is ONE wave of
-// resident CTAs (`resident_threads` per SM follow from the kernel's launch bound).  At DLRM batch
-// sizes a second wave costs a full dependent key -> row -> store latency chain; measured on B200
-// (26 tables x 2048 lookups): D = 128 tile 4 / 8 / 16 -> 24.2 / 17.8 / 16.0 us, D = 64 -> 14.9 /
-// 11.3 / 12.2 us, i.e. the first tile that fits one wave wins.
+// Entries per lane-group tile: the smallest multiple of 4 (the keys of a batch are one 16-byte load) up to
+// 32 with which the whole batch is ONE wave of resident CTAs (`resident_threads` per SM follow from the
+// kernel's launch bound).  At DLRM batch sizes a second wave costs a full dependent key -> row -> store
+// latency chain, and a longer tile costs one such chain per 4 entries; measured on B200 (26 tables x 2048
+// lookups): D = 128 tile 4 / 8 / 16 -> 24.2 / 17.8 / 16.0 us, D = 64 -> 14.9 / 11.3 / 12.2 us, i.e. the
+// first tile that fits one wave wins.  (Round 1 only tried powers of two: an owner with 4 tables x 16384
+// lookups -- 8 GPUs -- then jumped from 16 to 32 entries, 37 us instead of 18 us for the 3-table owners.)
 static int choose_update_tile(int64_t total_entries, int lpr, int sm_count, int resident_threads) {
     const int64_t capacity = (int64_t)sm_count * resident_threads / lpr;
-    int tile = 4;
-    while (tile < 32 && total_entries > capacity * tile) tile *= 2;
-    return tile;
+    int64_t tile = (total_entries + capacity - 1) / capacity;
+    tile = (tile + 3) / 4 * 4;
+    if (tile < 4) tile = 4;
+    if (tile > 32) tile = 32;
+    return (int)tile;
 }
 
 // Upper bound on chunks (CTAs) per table for any batch with B*P <= max_lookups.
@@ -517,7 +521,7 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
                                  THREADS * ((NCH <= 1) ? 3 : ((NCH <= 2) ? 2 : 1)));
     {   // tuning aid (dlrmb_set_option("update_tile", v)): 4, 8, 16 or 32 entries per lane group
         const int v = g_opt.update_tile.load(std::memory_order_relaxed);
-        if (v == 4 || v == 8 || v == 16 || v == 32) gm.tile = v;
+        if (v >= 4 && v <= 32 && v % 4 == 0) gm.tile = v;
     }
     gm.tiles = (gm.L + gm.tile - 1) / gm.tile;
     gm.chunks = (gm.tiles + G - 1) / G;

@@ -58,8 +58,10 @@ int64_t dlrmb_launch_count(void);
 /* Process-wide tuning / test switches, read by the launchers (never from the environment):
  *   "interact_general" 1 = run the general tiled interaction kernels even for the specialised shapes
  *   "update_two_launches" 1 = separate fix-up launch of the sparse update at every batch size
- *   "update_tile" 4|8|16|32 = entries per lane group of the sparse update (0 = chosen per batch)
+ *   "update_tile" 4, 8, .. 32 = entries per lane group of the sparse update (0 = chosen per batch)
  *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
+ *   "fwd_ksplit" 0|1|2 = tensor-core forward with one warp per sample always / two warps per sample for one-wave
+ *                        batches (default) / two warps per sample always
  * Defaults are the measured-fastest configuration; unknown names return DLRMB_EINVAL. */
 int32_t dlrmb_set_option(const char* name, int64_t value);
 int32_t dlrmb_get_option(const char* name, int64_t* value);

@@ -1111,3 +1111,50 @@ def test_interaction_backward_dx_alone_and_split_scatter(B, F, d):
     torch.cuda.current_stream().wait_event(plan.done)
     assert torch.equal(x.grad, dx)
     assert torch.equal(buf[2:2 + B], dT_ref[:, 1:]) and torch.all(buf[:2] == -7.0) and torch.all(buf[2 + B:] == -7.0)
+
+
+@pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (1, 27, 128), (301, 27, 64), (5000, 27, 128)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_interaction_forward_one_and_two_warps_per_sample(B, F, d, mode, lib_options):
+    """The tensor-core forward with one warp per sample (mode 0), two warps per sample splitting k (mode 2) and
+    the default choice by batch size (mode 1): same contract and tolerance, integer inputs exact, fused
+    fast_vcat, padding."""
+    from dlrm_jl_b200.interact import interaction_fwd
+    rng = np.random.default_rng(B + F + d)
+    T = rng.standard_normal((B, F, d)).astype(np.float32)
+    lib_options("fwd_ksplit", mode)
+    for pad in (1, 16):
+        ref = O.interaction_fwd(T, pad)
+        Tz = T.copy()
+        Tz[:, 0] = 0
+        Tzd = torch.from_numpy(Tz).to(_dev())
+        out = interaction_fwd(Tzd, torch.from_numpy(T[:, 0].copy()).to(_dev()), pad_to_mul=pad).cpu().numpy()
+        assert out.shape == ref.shape and O.rel_err(out, ref) < FWD_RTOL
+        assert np.array_equal(out[:, :d], T[:, 0]) and np.array_equal(Tzd.cpu().numpy(), T)
+        assert np.all(out[:, d + F * (F - 1) // 2:] == 0)
+    Ti = rng.integers(-4, 5, size=(64, F, d)).astype(np.float32)
+    assert np.array_equal(interaction_fwd(torch.from_numpy(Ti).to(_dev())).cpu().numpy(), O.interaction_fwd(Ti))
+
+
+@pytest.mark.parametrize("tile", [4, 12, 20, 28, 32])
+def test_sparse_sgd_any_tile_length_gives_the_same_tables(tile, lib_options):
+    """The tile (entries per lane group) is any multiple of 4 up to 32, chosen per batch so that the update is
+    one wave; every choice must give oracle-level tables, inline and two-launch fix-up bit-equal."""
+    rng = np.random.default_rng(tile)
+    rows, D, B = [3, 40, 50000, 7, 1000], 128, 5000 + tile
+    tables = _rand_tables(rng, rows, D)
+    idx = [np.minimum((rng.pareto(1.05, size=(B, 1)) * 1.0).astype(np.int64), r - 1) for r in rows]
+    idx[2] = rng.integers(0, rows[2], size=(B, 1))
+    dT = (rng.standard_normal((B, len(rows), D)) * 0.01).astype(np.float32)
+    lib_options("update_tile", tile)
+    lib_options("update_two_launches", 0)
+    a = _run_update(tables, idx, dT, 0, 0.5, steps=2)
+    lib_options("update_two_launches", 1)
+    b = _run_update(tables, idx, dT, 0, 0.5, steps=2)
+    ref = [tb.copy() for tb in tables]
+    for _ in range(2):
+        for k in range(len(rows)):
+            O.sparse_sgd_update_fast(ref[k], idx[k], np.ascontiguousarray(dT[:, k]), 0.5)
+    for k in range(len(rows)):
+        assert np.array_equal(a[k], b[k]), k
+        assert O.rel_err(a[k], ref[k]) < SGD_RTOL, k

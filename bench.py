@@ -423,6 +423,12 @@ def run_ours(args):
     n_bottom = sum(p.numel() for p in bottom.parameters())
     comm_stream_ = torch.cuda.Stream()
     early = world > 1 and not args.late_allreduce
+    # the bottom MLP's gradients (0.7 MB) end the step on the critical path: one-shot all-reduce over the
+    # IPC-mapped buffers (push + flag barrier + rank-ordered sum) instead of a latency-bound NCCL call
+    small_ar = (early and se.peer is not None and se.peer.peer_flag_ptrs is not None and n_bottom % 4 == 0
+                and not args.nccl_bottom_allreduce)
+    if small_ar:
+        se.peer.enable_small_allreduce(n_bottom)
 
     def allreduce_top_grads(g):
         """Gradient hook on the interaction output: the top MLP's backward has been launched, so its 93 % of
@@ -432,13 +438,14 @@ def run_ours(args):
         comm = main if serial["on"] else comm_stream_
         comm.wait_stream(main)
         with torch.cuda.stream(comm):
-            dist.all_reduce(flat.flat[n_bottom:], op=dist.ReduceOp.SUM)
+            with _prof.range("allreduce_top_mlp"):
+                dist.all_reduce(flat.flat[n_bottom:], op=dist.ReduceOp.SUM)
         return g
 
     def train_step(dense, labels, idx):
         main = torch.cuda.current_stream()
         mlp_stream = main if serial["on"] else mlp_stream_
-        upd_stream = main if serial["on"] else upd_stream_
+        se.update_inside_backward(LR * flat.scale, main if serial["on"] else upd_stream_)
         if not fused_mlp:
             flat.zero()        # autograd accumulates into the bucket; the fused layers overwrite it
         # bottom MLP on a second stream: it is independent of the embedding exchange until the
@@ -446,7 +453,7 @@ def run_ours(args):
         # autograd replays backward ops on their forward stream, its backward hides the gradient
         # all-to-all and the sparse update)
         mlp_stream.wait_stream(main)
-        with torch.cuda.stream(mlp_stream):
+        with torch.cuda.stream(mlp_stream), _prof.range("bottom_mlp_fwd"):
             x = bottom_f(dense)
         fused = se.scatter_plan is not None
         T = se.lookup_fused(idx) if fused else se.lookup(idx, anchor)
@@ -455,23 +462,26 @@ def run_ours(args):
         z = dot(x, T, scatter=se.scatter_plan) if fused else dot(x, T)
         if early:
             z.register_hook(allreduce_top_grads)
-        loss = sigmoid_bce(top_f(z), labels)
+        with _prof.range("top_mlp_fwd"):
+            logits = top_f(z)
+        loss = sigmoid_bce(logits, labels)
+        # the sparse update is launched from inside the backward pass (se.update_inside_backward below): it
+        # touches the tables only and runs on upd_stream beside the bottom MLP's backward and the dense reduction
         loss.backward()
         main.wait_stream(mlp_stream)
-        if fused:
-            se.finish_backward()
-        # the sparse update touches the tables only: it runs beside the dense all-reduce + dense SGD
-        upd_stream.wait_stream(main)
-        with torch.cuda.stream(upd_stream):
-            se.update(LR * flat.scale, presorted=True)
         if early:      # the bottom MLP's share now; the top MLP's has been in flight since its backward
-            dist.all_reduce(flat.flat[:n_bottom], op=dist.ReduceOp.SUM)
+            if small_ar:
+                se.peer.allreduce_small(flat.flat[:n_bottom])
+            else:
+                with _prof.range("allreduce_bottom_mlp"):
+                    dist.all_reduce(flat.flat[:n_bottom], op=dist.ReduceOp.SUM)
             main.wait_stream(main if serial["on"] else comm_stream_)
-        else:
-            flat.allreduce()
-        with torch.no_grad():
+        elif world > 1:
+            with _prof.range("allreduce_dense"):
+                flat.allreduce()
+        with torch.no_grad(), _prof.range("dense_sgd"):
             pflat.add_(flat.flat, alpha=-LR * flat.scale)      # Flux.update!: x .-= eta * grad
-        main.wait_stream(upd_stream)
+        main.wait_stream(main if serial["on"] else upd_stream_)
         return loss.detach()
 
     # synthetic batches: host-pinned copies (e2e) and device copies (value)
@@ -565,7 +575,7 @@ def run_ours(args):
     # (cudaEventRecordExternal), replayed per batch -- the kernels run back to back exactly as in the
     # timed graph.  Fallback (no graph / no external events): eager launches with an event pair
     # around every call, each step queued behind a device-side spin so the host runs ahead.
-    prof, prof_mode = None, None
+    prof, prof_mode, graph_map = None, None, None
     if graph is not None:
         try:
             _prof.enable(True, external=True)
@@ -582,6 +592,8 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 for name, ms in _prof.read_replay().items():
                     acc.setdefault(name, []).extend(ms)
+                if i == K - 1:
+                    graph_map = {n: [round(v[0][0], 1), round(v[0][1], 1)] for n, v in _prof.read_replay_timeline().items() if v}
             barrier()
             prof = {n: {"count": len(v), "total_ms": float(sum(v)), "avg_ms": float(sum(v) / max(1, len(v)))}
                     for n, v in acc.items()}
@@ -739,6 +751,10 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL, "data": "synthetic",
             "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check,
                            barrier_timeouts=(se.peer.barrier_timeouts() if se.peer is not None else 0),
+                           dense_allreduce=("none (single GPU)" if world == 1 else
+                                            ("top MLP gradients: NCCL all-reduce started from a gradient hook as soon as the top MLP's backward is "
+                                             "launched; bottom MLP gradients: " + ("one-shot all-reduce over NVLink peer stores (dlrmb_peer_allreduce_f32)"
+                                                                                  if small_ar else "NCCL all-reduce") if early else "one NCCL all-reduce after backward")),
                            mlp=("fused dense layers (library fp32 GEMMs, epilogue bias+relu, dlrmb_dense_bwd_act_bias)" if fused_mlp
                                 else "nn.Linear + ReLU autograd")),
             "e2e": {"value": Bg * K / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
@@ -749,6 +765,11 @@ def run_ours(args):
         }
         line.update(hot_path_report(wl, world, rank, se, prof, ms_step, replay))
         line["hot_path"]["kernel_timing"] = prof_mode
+        if graph_map:
+            line["hot_path"]["step_map_us"] = dict(graph_map, note="[start, end] of every bracketed call of the step (this repo's kernels, "
+                                                   "the MLP blocks, the NCCL all-reduces, the dense SGD), microseconds from the first stamp, from "
+                                                   "CUDA event-record nodes inside a capture of the step graph, last timed batch, rank 0; each node "
+                                                   "adds a few microseconds, so this is a map of the step, not a stopwatch")
         if timeline:
             line["hot_path"]["timeline_us"] = dict(timeline, note="[first CTA in, last CTA out] of each kernel, microseconds from the "
                                                    "first stamp of the step, from the kernels' own %globaltimer stamps inside the step graph "
@@ -774,6 +795,7 @@ def run_ours(args):
         os._exit(0)
 
 
+OWN_KERNELS = {"lookup", "sort", "update", "update_fixup", "interaction_fwd", "interaction_bwd", "bce", "indices_scatter"}
 CLOCK_NAMES = ["lookup", "sort", "update", "update_fixup", "interaction_fwd", "interaction_bwd", "bce"]
 
 
@@ -1077,7 +1099,11 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     ibwd_bytes = B * (width + 2 * F * D + D) * 4
     alg = {"lookup": lookup_bytes, "update": update_bytes, "interaction_fwd": ifwd_bytes, "interaction_bwd": ibwd_bytes}
     kernels = {}
+    others = {}     # bracketed calls that are not this repo's kernels (MLP blocks, NCCL, dense SGD): event-pair time only
     for name, st in prof.items():
+        if not (name in OWN_KERNELS or name.startswith("peer_barrier")):
+            others[name] = round(1e3 * st["avg_ms"], 2)
+            continue
         k = {"launches": st["count"], "in_step_us": 1e3 * st["avg_ms"], "in_step_clock": "serialised eager step, CUDA-event pair"}
         if "device_clock_us" in st:      # the kernel's own %globaltimer stamps inside the real step graph
             k["event_pair_us"] = k["in_step_us"]
@@ -1102,7 +1128,7 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
     cand = [n for n in ("update", "lookup", "interaction_fwd", "interaction_bwd") if n in kernels]
     dom = max(cand, key=lambda n: kernels[n]["in_step_us"]) if cand else None
     out = {"kernels": kernels,
-           "hot_path": {"own_kernels_us_per_step": 1e3 * own_ms, "share_of_step": own_ms / ms_step if ms_step else None,
+           "hot_path": {"other_calls_event_pair_us": others, "own_kernels_us_per_step": 1e3 * own_ms, "share_of_step": own_ms / ms_step if ms_step else None,
                         "samples_per_s_own_kernels_only": (B / (own_ms * 1e-3)) if own_ms else None}}
     emb_names = [n for n in ("lookup", "sort", "update") if n in kernels]
     emb_us = sum(kernels[n]["in_step_us"] for n in emb_names)
@@ -1160,6 +1186,8 @@ def main():
     ap.add_argument("--split-dx", action="store_true",
                     help="multi-GPU: dx from a kernel of its own ahead of the scattering interaction backward, which then runs on a "
                          "side stream beside the bottom MLP's backward (measured: no gain at 2 and 8 GPUs, off by default)")
+    ap.add_argument("--nccl-bottom-allreduce", action="store_true",
+                    help="multi-GPU: NCCL for the bottom MLP's gradient all-reduce instead of the one-shot peer-store all-reduce")
     ap.add_argument("--late-allreduce", action="store_true",
                     help="multi-GPU: one dense all-reduce after the whole backward pass instead of starting the top MLP's share early")
     ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],

@@ -68,6 +68,7 @@ SIGNATURES = {
     "dlrmb_peer_barrier": (_i32, [_i32, C.POINTER(_vp), _i32, _i32, _i32, _vp, _vp]),
     "dlrmb_peer_barrier_flag_bytes": (_i64, []),
     "dlrmb_peer_barrier_state_bytes": (_i64, []),
+    "dlrmb_peer_allreduce_f32": (_i32, [_i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "dlrmb_indices_scatter_p2p": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "dlrmb_interaction_has_warp_path": (_i32, [_i32, _i32]),
     "dlrmb_dense_fwd_bias_act": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _vp]),

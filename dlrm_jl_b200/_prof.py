@@ -64,6 +64,21 @@ def read_replay() -> Dict[str, List[float]]:
     return {name: [a.elapsed_time(b) for a, b in pairs] for name, pairs in _events.items()}
 
 
+def read_replay_timeline() -> Dict[str, List[Tuple[float, float]]]:
+    """Graph mode: name -> [(start, end)] in microseconds from the earliest start stamp of the last replay: where
+    every bracketed call sits in the step (event-record nodes add a few microseconds of latency each, so this
+    is a map of the step, not a stopwatch)."""
+    firsts = [pairs[0][0] for pairs in _events.values() if pairs]
+    if not firsts:
+        return {}
+    origin = firsts[0]
+    for ev in firsts[1:]:
+        if ev.elapsed_time(origin) > 0:      # ev is earlier than the current origin
+            origin = ev
+    return {name: [(1e3 * origin.elapsed_time(a), 1e3 * origin.elapsed_time(b)) for a, b in pairs]
+            for name, pairs in _events.items()}
+
+
 def time_launches(fn, nb: int, iters: int = 10, use_graph: bool = True) -> float:
     """Microseconds per launch of `fn(i)`, i = 0..nb-1 (each i a different input batch): the nb launches
     are captured into one CUDA graph and the replays are timed with CUDA events, so the figure is

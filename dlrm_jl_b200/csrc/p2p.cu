@@ -435,3 +435,83 @@ int32_t dlrmb_indices_scatter_p2p(int32_t device, const void* idx_local, int32_t
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// One-shot all-reduce of a SMALL float buffer over the IPC-mapped exchange buffers
+// ---------------------------------------------------------------------------------------------
+// The data-parallel step ends with the all-reduce of the bottom MLP's gradients (0.7 MB): it sits on the
+// critical path (bottom MLP backward -> all-reduce -> dense SGD) and is latency-, not bandwidth-bound.
+// Every rank owns a buffer [2][world][n] (two halves, alternating by step so that a fast peer's next push
+// cannot overwrite what a slow rank is still summing).  push: every rank stores its n floats into slot
+// [half][rank] of EVERY rank's buffer over NVLink; flag barrier; sum: every rank adds the `world` slots of
+// its own buffer in rank order -- the same order on every rank, so all ranks hold bit-identical sums.
+// (world - 1) * n * 4 bytes leave each GPU: right for buffers up to ~1 MB; large buffers stay with NCCL's
+// reduce-scatter + all-gather.
+namespace dlrmb {
+
+struct PeerFloatPtrs {
+    float* p[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256)
+allreduce_push_kernel(PeerFloatPtrs peers, int world, int rank, const float4* __restrict__ data, int n4,
+                      const uint32_t* __restrict__ state, int channel) {
+    const uint32_t half = state[channel] & 1u;           // epoch BEFORE this step's barrier
+    const size_t off = ((size_t)half * world + rank) * n4;
+    const int peer = blockIdx.y;
+    float4* dst = reinterpret_cast<float4*>(peers.p[peer]) + off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) dst[i] = data[i];
+}
+
+__global__ void __launch_bounds__(256)
+allreduce_sum_kernel(const float4* __restrict__ mine, int world, float4* __restrict__ data, int n4,
+                     const uint32_t* __restrict__ state, int channel) {
+    const uint32_t half = (state[channel] - 1u) & 1u;    // the barrier in between has bumped the epoch
+    const float4* src = mine + (size_t)half * world * n4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 acc = src[i];
+        for (int r = 1; r < world; ++r) {
+            const float4 v = src[(size_t)r * n4 + i];
+            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+        }
+        data[i] = acc;
+    }
+}
+
+}  // namespace dlrmb
+
+extern "C" {
+
+int32_t dlrmb_peer_allreduce_f32(int32_t device, float* const* peer_bufs, uint32_t* const* peer_flags, int32_t world,
+                                 int32_t rank, int32_t channel, uint32_t* state, float* data, int64_t n,
+                                 dlrmb_stream stream) {
+    DLRMB_REQUIRE(peer_bufs && peer_flags && state && data, "null argument");
+    DLRMB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad world / rank (%d, %d)", world, rank);
+    DLRMB_REQUIRE(channel >= 0 && channel < kBarrierChannels, "channel must be in 0..%d", kBarrierChannels - 1);
+    DLRMB_REQUIRE(n > 0 && n % 4 == 0 && n < (1ll << 28), "n must be a positive multiple of 4 (got %lld)", (long long)n);
+    DLRMB_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, "data must be 16-byte aligned");
+    DeviceGuard guard(device);
+    DLRMB_REQUIRE(guard.ok, "cudaSetDevice(%d) failed", device);
+    PeerFloatPtrs bufs;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        bufs.p[r] = r < world ? peer_bufs[r] : nullptr;
+        DLRMB_REQUIRE(r >= world || peer_bufs[r] != nullptr, "peer_bufs[%d] is null", r);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n4 = (int)(n / 4);
+    int bx = (n4 + 255) / 256;
+    if (bx > 64) bx = 64;
+    allreduce_push_kernel<<<dim3((unsigned)bx, (unsigned)world), 256, 0, s>>>(bufs, world, rank, reinterpret_cast<const float4*>(data), n4,
+                                                                           state, channel);
+    DLRMB_LAUNCH_CHECK();
+    int rc = dlrmb_peer_barrier(device, peer_flags, world, rank, channel, state, stream);
+    if (rc) return rc;
+    int sx = (n4 + 255) / 256;
+    if (sx > 592) sx = 592;
+    allreduce_sum_kernel<<<(unsigned)sx, 256, 0, s>>>(reinterpret_cast<const float4*>(bufs.p[rank]), world,
+                                                     reinterpret_cast<float4*>(data), n4, state, channel);
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
+}  // extern "C"

@@ -97,6 +97,7 @@ class ScatterPlan:
         self.stream = stream
         self.done = torch.cuda.Event() if stream is not None else None
         self._keep = None
+        self.on_launched = None      # callable run right after the scattering backward has been launched
 
 
 class _DotInteractionScatterFn(torch.autograd.Function):
@@ -141,11 +142,15 @@ class _DotInteractionScatterFn(torch.autograd.Function):
                         plan.dests.data_ptr(), plan.sample_offset, dx_full.data_ptr(), plan.stream.cuda_stream))
                 plan.done.record(plan.stream)
             plan._keep = (dOut, dx_full)      # alive until the exchange has been joined (finish_backward)
+            if plan.on_launched is not None:
+                plan.on_launched()
             return dx, None, None, None
         with _prof.range("interaction_bwd"):
             _lib.check(lib.dlrmb_interaction_bwd_scatter(
                 T.device.index or 0, dOut.data_ptr(), T.data_ptr(), B, F, d, ctx.pad_to_mul,
                 plan.dests.data_ptr(), plan.sample_offset, dx.data_ptr(), _stream(T)))
+        if plan.on_launched is not None:
+            plan.on_launched()
         return dx, None, None, None
 
 

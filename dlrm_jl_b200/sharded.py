@@ -207,15 +207,35 @@ class PeerExchange:
         self._idx_dests = torch.tensor(dests, dtype=torch.int64, device=self.device)
         self._idx_geom = (len(sharding.rows), B_local, P, idx_bytes)
 
+    def enable_small_allreduce(self, n: int) -> None:
+        """Exchange buffer [2][world][n] floats for `allreduce_small` (dlrmb_peer_allreduce_f32)."""
+        import ctypes as C
+        assert self.peer_flag_ptrs is not None, "the one-shot all-reduce is ordered by the flag barrier"
+        self._ar_n = int(n)
+        self._arbuf, _own, ptrs = self._share(2 * self.world * self._ar_n * 4)
+        self._ar_arr = (C.c_void_p * self.world)(*[int(q) for q in ptrs])
+
+    def allreduce_small(self, t: torch.Tensor) -> None:
+        """In-place sum of `t` (contiguous f32, numel == the enabled n, a multiple of 4) over all ranks: every
+        rank pushes its copy into every rank's buffer over NVLink, flag barrier, rank-ordered local sum."""
+        from . import _lib, _prof
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == self._ar_n
+        with _prof.range("peer_allreduce"):
+            _lib.check(self.lib.dlrmb_peer_allreduce_f32(
+                self.device.index or 0, self._ar_arr, self._flag_arr, self.world, self.rank, 3, self._bstate.data_ptr(),
+                t.data_ptr(), t.numel(), int(torch.cuda.current_stream(self.device).cuda_stream)))
+
     def scatter_indices(self, idx_local: torch.Tensor) -> torch.Tensor:
         """idx_local [ntab][B_local][P] -> the owners' buffers (peer stores) + barrier; returns this rank's
         idx_owned [t_mine][B_global][P]."""
         from . import _lib
         ntab, Bl, P, ib = self._idx_geom
         assert tuple(idx_local.shape) == (ntab, Bl, P) and idx_local.element_size() == ib and idx_local.is_contiguous()
-        _lib.check(self.lib.dlrmb_indices_scatter_p2p(
-            self.device.index or 0, idx_local.data_ptr(), ib, ntab, Bl, P, self._idx_dests.data_ptr(), self.rank,
-            int(torch.cuda.current_stream(self.device).cuda_stream)))
+        from . import _prof
+        with _prof.range("indices_scatter"):
+            _lib.check(self.lib.dlrmb_indices_scatter_p2p(
+                self.device.index or 0, idx_local.data_ptr(), ib, ntab, Bl, P, self._idx_dests.data_ptr(), self.rank,
+                int(torch.cuda.current_stream(self.device).cuda_stream)))
         self.barrier(0)
         return self.idx_owned
 
@@ -292,10 +312,11 @@ class PeerExchange:
         if self._barrier is not None:
             self._barrier()
         elif self.peer_flag_ptrs is not None:
-            from . import _lib
-            _lib.check(self.lib.dlrmb_peer_barrier(
-                self.device.index or 0, self._flag_arr, self.world, self.rank, channel, self._bstate.data_ptr(),
-                int(torch.cuda.current_stream(self.device).cuda_stream)))
+            from . import _lib, _prof
+            with _prof.range(f"peer_barrier_{channel}"):
+                _lib.check(self.lib.dlrmb_peer_barrier(
+                    self.device.index or 0, self._flag_arr, self.world, self.rank, channel, self._bstate.data_ptr(),
+                    int(torch.cuda.current_stream(self.device).cuda_stream)))
         else:
             dist.all_reduce(self._flag, group=self.group)
 
@@ -355,6 +376,7 @@ class _ShardedLookupFn(torch.autograd.Function):
             se.owned_grad = dT.contiguous()      # [B][1 + ntab][D], consumed with slot0 = 1
         else:
             se.owned_grad = exchange_grads(dT.contiguous(), se.sharding, se.rank, se.group)
+        se._update_from_backward(fused=False)
         return None, None, None
 
 
@@ -387,6 +409,29 @@ class ShardedEmbedding:
         self.slot0 = 1 if world == 1 else 0
         self.peer: Optional[PeerExchange] = None
         self.scatter_plan = None
+        self._auto_update = None
+
+    def update_inside_backward(self, lr: float, stream: "torch.cuda.Stream") -> None:
+        """Launch the sparse update from INSIDE the backward pass, on ``stream``, as soon as the pooled-embedding
+        gradient exists (the lookup's pullback, or the scattering interaction backward on the fused path)
+        instead of after ``loss.backward()`` has returned.  The update touches the tables only, so it then runs
+        beside the bottom MLP's backward (autograd joins every backward stream before ``backward()`` returns, so
+        a call placed after it starts a whole bottom-MLP backward later).  The caller joins ``stream`` at the
+        end of the step; do not call :meth:`update` / :meth:`finish_backward` yourself in this mode."""
+        self._auto_update = (float(lr), stream)
+        if self.scatter_plan is not None:
+            self.scatter_plan.on_launched = lambda: self._update_from_backward(fused=True)
+
+    def _update_from_backward(self, fused: bool) -> None:
+        if self._auto_update is None:
+            return
+        lr, stream = self._auto_update
+        cur = torch.cuda.current_stream(self.tables.device)
+        stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            if fused:
+                self.finish_backward()
+            self.update(lr)
 
     def enable_fused_backward(self, B_local: int, split_dx: bool = False) -> None:
         """Also fuse the backward exchange: the interaction backward stores dT rows into the owners'
@@ -396,6 +441,8 @@ class ShardedEmbedding:
         beside the bottom MLP's backward."""
         assert self.peer is not None
         self.scatter_plan = self.peer.enable_gradient_exchange(self.sharding, B_local, self.D, split_dx)
+        if self._auto_update is not None:
+            self.scatter_plan.on_launched = lambda: self._update_from_backward(fused=True)
 
     def lookup_fused(self, idx_local: torch.Tensor) -> torch.Tensor:
         """Forward of the fully fused path: no autograd node (the gradient never comes back through

@@ -238,6 +238,17 @@ int32_t dlrmb_peer_barrier(int32_t device, uint32_t* const* peer_flags, int32_t 
                            uint32_t* state, dlrmb_stream stream);
 int64_t dlrmb_peer_barrier_flag_bytes(void);
 int64_t dlrmb_peer_barrier_state_bytes(void);
+/* One-shot all-reduce (sum, in place) of a SMALL float buffer over IPC-mapped memory: the bottom MLP's
+ * gradients at the end of the data-parallel step, which sit on the critical path and are latency-bound.
+ * Every rank allocates a zero-initialised dlrmb_xbuf of 2 * world * n floats (mapped by all peers;
+ * `peer_bufs` = host array of the `world` device pointers) and shares the flag arrays / state of
+ * dlrmb_peer_barrier (a channel of its own).  push (each rank stores its n floats into its slot of every
+ * rank's buffer) -> flag barrier -> every rank sums the slots in rank order: bit-identical sums on all
+ * ranks.  n % 4 == 0, data 16-byte aligned.  (world - 1) * n * 4 bytes leave each GPU, so this is for
+ * buffers up to about 1 MB; larger ones stay with dlrmb_comm_allreduce_f32 / NCCL. */
+int32_t dlrmb_peer_allreduce_f32(int32_t device, float* const* peer_bufs, uint32_t* const* peer_flags, int32_t world,
+                                 int32_t rank, int32_t channel, uint32_t* state, float* data, int64_t n,
+                                 dlrmb_stream stream);
 /* Index exchange by peer stores: idx_local [ntab][B_local][P] (this rank's samples, every table) goes to
  * the owners' index buffers: `dests_dev` is a DEVICE array of ntab pointers, entry k = the owner's buffer
  * [B_global][P] of table k (inside its idx_owned [t_owner][B_global][P]); this rank fills rows

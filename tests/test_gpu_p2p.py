@@ -30,7 +30,35 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _arm_watchdog(seconds: int = 200) -> None:
+    """A worker that is stuck dumps every thread's stack to stderr and exits instead of hanging the suite."""
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
+def _collect(procs, q, world, timeout):
+    """Results of the workers; whatever happens, no worker survives the test."""
+    import queue
+    res = []
+    try:
+        for _ in range(world):
+            try:
+                res.append(q.get(timeout=timeout))
+            except queue.Empty:
+                res.append((-1, False, {}, "a worker did not answer within %d s (see its stack dump on stderr)" % timeout))
+                break
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.terminate()
+                p.join(timeout=10)
+    return res
+
+
 def _worker(rank, world, port, q):
+    _arm_watchdog()
     try:
         from dlrm_jl_b200.sharded import ShardedEmbedding
         from oracle import oracle as O
@@ -80,14 +108,14 @@ def test_fused_lookup_peer_store_two_ranks_one_gpu():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=180) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-    for rank, ok, err in res:
+    res = _collect(procs, q, world, 240)
+    for r in res:
+        rank, ok, err = r[0], r[1], r[-1]
         assert ok, f"rank {rank}: pooled rows stored by peers differ from the oracle lookup {err}"
 
 
 def _step_worker(rank, world, port, q, D, BL, P, rows, steps):
+    _arm_watchdog()
     try:
         from dlrm_jl_b200.interact import DotInteraction, interaction_width
         from dlrm_jl_b200.sharded import ShardedEmbedding
@@ -137,9 +165,15 @@ def _step_worker(rank, world, port, q, D, BL, P, rows, steps):
             T = se.lookup_fused(torch.from_numpy(idx_all[rank]).to(dev))
             se.sort_async()
             z = dot(x, T, scatter=se.scatter_plan)
-            z.backward(torch.from_numpy(gz_all[rank]).to(dev))
-            se.finish_backward()
-            se.update(lr)
+            if D == 16:     # the bench's form: barrier + update launched from inside the backward pass, on a side stream
+                side = torch.cuda.Stream()
+                se.update_inside_backward(lr, side)
+                z.backward(torch.from_numpy(gz_all[rank]).to(dev))
+                torch.cuda.current_stream().wait_stream(side)
+            else:
+                z.backward(torch.from_numpy(gz_all[rank]).to(dev))
+                se.finish_backward()
+                se.update(lr)
             barrier()
             # ---- unsharded oracle step on the same inputs
             T_ref = O.lookup(ref_tables, list(idx_all[rank]), slot0=1)
@@ -187,9 +221,7 @@ def test_sharded_training_step_matches_unsharded_oracle(world, D, BL, P, rows):
     procs = [ctx.Process(target=_step_worker, args=(r, world, port, q, D, BL, P, rows, 2)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
+    res = _collect(procs, q, world, 240)
     for rank, ok_T, worst, err in res:
         assert not err, f"rank {rank}: {err}"
         assert ok_T, f"rank {rank}: pooled rows / fused fast_vcat differ from the oracle"

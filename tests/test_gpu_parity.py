@@ -1158,3 +1158,32 @@ def test_sparse_sgd_any_tile_length_gives_the_same_tables(tile, lib_options):
     for k in range(len(rows)):
         assert np.array_equal(a[k], b[k]), k
         assert O.rel_err(a[k], ref[k]) < SGD_RTOL, k
+
+
+def test_sparse_update_launched_inside_backward_equals_explicit_update():
+    """ShardedEmbedding.update_inside_backward (the bench's form: the update is launched by the lookup's pullback
+    on a side stream, beside the rest of the backward pass) gives the tables of the explicit update call."""
+    from dlrm_jl_b200.interact import DotInteraction, interaction_width
+    from dlrm_jl_b200.sharded import ShardedEmbedding
+    rows, D, B = [50, 7, 400, 3, 1200, 33, 9] + [20 + 31 * k for k in range(19)], 64, 300
+    rng = np.random.default_rng(3)
+    idx = torch.from_numpy(np.stack([rng.integers(0, r, size=(B, 1)) for r in rows]).astype(np.int32)).to(_dev())
+    x_np = rng.standard_normal((B, D)).astype(np.float32)
+    g = torch.from_numpy(rng.standard_normal((B, interaction_width(27, D))).astype(np.float32)).to(_dev())
+    got = []
+    for inside in (False, True):
+        se = ShardedEmbedding.create(rows, D, B, 1, 0, 1, _dev())
+        side = torch.cuda.Stream()
+        if inside:
+            se.update_inside_backward(0.3, side)
+        anchor = torch.zeros(1, device=_dev(), requires_grad=True)
+        x = torch.from_numpy(x_np).to(_dev()).requires_grad_(True)
+        T = se.lookup(idx, anchor)
+        DotInteraction()(x, T).backward(g)
+        if inside:
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            se.update(0.3)
+        got.append([se.tables.download(k) for k in range(len(rows))])
+    for a, b in zip(*got):
+        assert np.array_equal(a, b)

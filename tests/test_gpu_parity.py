@@ -1187,3 +1187,35 @@ def test_sparse_update_launched_inside_backward_equals_explicit_update():
         got.append([se.tables.download(k) for k in range(len(rows))])
     for a, b in zip(*got):
         assert np.array_equal(a, b)
+
+
+def test_tables_reserve_grows_the_workspaces_and_keeps_the_tables():
+    """dlrmb_tables_reserve (what the Julia glue calls when a batch is larger than any before): the sort /
+    update workspaces grow, the tables keep their bits, and the larger batch then runs."""
+    import ctypes as C
+    from dlrm_jl_b200 import DLRMB200Error, _lib
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    rng = np.random.default_rng(21)
+    rows, D = [300, 5, 70000], 32
+    tables = _rand_tables(rng, rows, D)
+    t = EmbeddingTables.from_arrays(tables, 64, 0)
+    B = 5000
+    idx = torch.from_numpy(np.stack([rng.integers(0, r, size=(B, 1)) for r in rows])).to(_dev())
+    T = torch.empty((B, 4, D), device=_dev())
+    with pytest.raises(DLRMB200Error, match="max_lookups"):
+        t.lookup(idx, T, 1)
+    _lib.check(_lib.load().dlrmb_tables_reserve(t._h, B))
+    _lib.check(_lib.load().dlrmb_tables_reserve(t._h, 10))           # never shrinks
+    ml = C.c_int64()
+    _lib.check(_lib.load().dlrmb_tables_info(t._h, None, None, C.byref(ml), None))
+    assert ml.value == B
+    for k in range(3):
+        assert np.array_equal(t.download(k), tables[k])
+    t.lookup(idx, T, 1, sort=True)
+    assert np.array_equal(T[:, 1:].cpu().numpy(), O.lookup(tables, list(idx.cpu().numpy()), slot0=1)[:, 1:])
+    dT = torch.randn((B, 4, D), device=_dev())
+    t.update_sorted(dT, 1, 0.1)
+    for k in range(3):
+        ref = tables[k].copy()
+        O.sparse_sgd_update_fast(ref, idx[k].cpu().numpy(), np.ascontiguousarray(dT[:, 1 + k].cpu().numpy()), 0.1)
+        assert O.rel_err(t.download(k), ref) < SGD_RTOL

@@ -217,16 +217,16 @@ def auto_rows_cap(wl, budget_bytes: int) -> int:
 
 
 def cpu_arm(wl, steps: int, warmup: int, rows_cap: int, budget_s: float = 25.0):
-    """Full training step on the CPU.  Bounded sample: tables capped at `rows_cap` rows each (0 = the
-    largest cap that fits 45 % of the available host RAM, at most 48 GiB of tables so the set-up stays
-    within a minute or two); everything else (batch, D, MLP sizes, step structure) is the workload's."""
+    """Full training step on the CPU.  Tables capped at `rows_cap` rows each (0 = the largest cap that fits
+    55 % of the available host RAM, at most 112 GiB: the full-size Terabyte-shaped tables, 97 GiB, on a box with
+    ~180 GiB free); everything else (batch, D, MLP sizes, step structure) is the workload's."""
     import torch
     from oracle import c_oracle as CO
     threads = host_threads()
     torch.set_num_threads(threads)
     ram_total, ram_avail = host_ram_bytes()
     if rows_cap <= 0:
-        budget = min(int(0.45 * ram_avail) if ram_avail else (4 << 30), 48 << 30)
+        budget = min(int(0.55 * ram_avail) if ram_avail else (4 << 30), 112 << 30)
         rows_cap = auto_rows_cap(wl, budget)
     rows = [min(r, rows_cap) for r in wl["rows"]]
     D, B, F = wl["D"], wl["B"], wl["F"]
@@ -1179,7 +1179,7 @@ def main():
     ap.add_argument("--workload", default="terabyte", choices=["terabyte", "kaggle", "sweep"])
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--cpu-rows-cap", type=int, default=0,
-                    help="CPU arm: rows per table (0 = as many as 45 %% of the available host RAM holds, 48 GiB at most)")
+                    help="CPU arm: rows per table (0 = as many as 55 %% of the available host RAM holds, 112 GiB at most)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU forward exchange: fused lookup + NVLink peer stores, or NCCL all-to-all")

@@ -11,7 +11,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
 NAMES = {"lookup_sort_kernel": "lookup", "lookup_gather_kernel": "lookup", "lookup_pool_kernel": "lookup", "update_tiles_kernel": "update",
          "update_fixup_kernel": "update_fixup", "interaction_fwd_kernel": "interaction_fwd",
          "interaction_bwd_kernel": "interaction_bwd",
-         "interaction_fwd_mma_kernel": "interaction_fwd",
+         "interaction_fwd_mma_kernel": "interaction_fwd", "interaction_fwd_mma_ksplit_kernel": "interaction_fwd",
          "interaction_fwd_warp_kernel": "interaction_fwd", "interaction_bwd_warp_kernel": "interaction_bwd", "sort_small_kernel": "sort"}
 
 

@@ -61,11 +61,12 @@ struct DeviceGuard {
 
 // ---- optional device-side kernel stamps (dlrmb_clock_enable) ---------------------------------
 // When a clock buffer is registered, thread 0 of every CTA of the main kernels stores %globaltimer
-// (32 ns steps on B200) at entry and exit into [kernel][cta][2]; the host takes min(entry), max(exit).
+// (32 ns steps on B200) at entry (atomic min) and exit (atomic max) into [kernel][cta % kClockCtas][2]; the
+// host pre-fills the slots and takes min(entry), max(exit).
 // This times a kernel where it really runs -- inside the multi-stream CUDA graph of a training step --
 // without the several microseconds a CUDA-event pair adds around a 10 us kernel.  A null pointer
 // (the default) costs one predicated branch.
-constexpr int kClockCtas = 4096;     // CTAs stamped per kernel (the first 4096; every kernel here starts in launch order)
+constexpr int kClockCtas = 4096;     // stamp slots per kernel; CTA c folds into slot c % 4096 (earliest entry, latest exit)
 enum ClockKernel { CLK_LOOKUP = 0, CLK_SORT, CLK_UPDATE, CLK_FIXUP, CLK_IFWD, CLK_IBWD, CLK_BCE, CLK_COUNT };
 unsigned long long* clock_slot(int which);       // host: device pointer of that kernel's stamps, or nullptr
 
@@ -75,10 +76,10 @@ __device__ __forceinline__ unsigned long long clock_now() {
     return t;
 }
 __device__ __forceinline__ void clock_in(unsigned long long* c, unsigned cta) {
-    if (c != nullptr && threadIdx.x == 0 && cta < (unsigned)kClockCtas) c[2 * cta] = clock_now();
+    if (c != nullptr && threadIdx.x == 0) atomicMin(&c[2 * (cta % (unsigned)kClockCtas)], clock_now());
 }
 __device__ __forceinline__ void clock_out(unsigned long long* c, unsigned cta) {
-    if (c != nullptr && threadIdx.x == 0 && cta < (unsigned)kClockCtas) c[2 * cta + 1] = clock_now();
+    if (c != nullptr && threadIdx.x == 0) atomicMax(&c[2 * (cta % (unsigned)kClockCtas) + 1], clock_now());
 }
 
 // ---- table storage -----------------------------------------------------------------------

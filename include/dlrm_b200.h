@@ -66,9 +66,10 @@ int64_t dlrmb_launch_count(void);
 int32_t dlrmb_set_option(const char* name, int64_t value);
 int32_t dlrmb_get_option(const char* name, int64_t* value);
 /* Device-side kernel stamps for measurement: with a buffer of dlrmb_clock_buffer_bytes() registered,
- * thread 0 of the first 4096 CTAs of every launch of the main kernels stores %globaltimer (nanoseconds,
- * 32 ns steps) at entry and exit into buffer[kernel][cta][2] (uint64; kernel order: lookup, sort, update,
- * update fix-up, interaction forward, interaction backward, sigmoid + BCE; dlrmb_clock_kernels() of them).
+ * thread 0 of every CTA of every launch of the main kernels folds %globaltimer (nanoseconds, 32 ns steps)
+ * at entry (atomic min) and exit (atomic max) into buffer[kernel][cta % 4096][2] (uint64; kernel order:
+ * lookup, sort, update, update fix-up, interaction forward, interaction backward, sigmoid + BCE;
+ * dlrmb_clock_kernels() of them).
  * The caller pre-fills entries with UINT64_MAX/2 and exits with 0 and reads min(entry) / max(exit) after
  * the launches have completed: the duration of a kernel where it really runs (e.g. inside a multi-stream
  * CUDA graph of a training step) without the microseconds a CUDA-event pair adds.  The pointer is read when a

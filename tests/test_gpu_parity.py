@@ -1219,3 +1219,49 @@ def test_tables_reserve_grows_the_workspaces_and_keeps_the_tables():
         ref = tables[k].copy()
         O.sparse_sgd_update_fast(ref, idx[k].cpu().numpy(), np.ascontiguousarray(dT[:, 1 + k].cpu().numpy()), 0.1)
         assert O.rel_err(t.download(k), ref) < SGD_RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [2048, 20000])
+def test_device_clock_stamps_cover_every_cta_of_a_large_grid(B):
+    """dlrmb_clock_enable: the kernels' own %globaltimer stamps (bench.py's in-step clock) must span the WHOLE
+    launch whatever the grid size -- CTAs fold into 4096 slots (earliest entry, latest exit).  At B = 20000 the
+    interaction kernels launch more CTAs than slots: the stamped window has to stay within the CUDA-event time
+    of the same launch and well above the share a truncated window would show."""
+    from dlrm_jl_b200 import _lib
+    from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_width
+    lib = _lib.load()
+    F, d = 27, 128
+    nk = int(lib.dlrmb_clock_kernels())
+    buf = torch.empty(int(lib.dlrmb_clock_buffer_bytes()) // 8, dtype=torch.int64, device=_dev())
+    view = buf.view(nk, -1, 2)
+    T = torch.randn(B, F, d, device=_dev())
+    dOut = torch.randn(B, interaction_width(F, d), device=_dev())
+    IFWD, IBWD = 4, 5       # kernel order of include/dlrm_b200.h
+    for which, fn in ((IFWD, lambda: interaction_fwd(T)), (IBWD, lambda: interaction_bwd(dOut, T))):
+        fn()                # warm-up without stamps
+        torch.cuda.synchronize()
+        view[:, :, 0] = 1 << 62
+        view[:, :, 1] = 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.check(lib.dlrmb_clock_enable(buf.data_ptr()))
+        try:
+            torch.cuda._sleep(4_000_000)      # ~2 ms of device spin: the host is ahead, the events time the device only
+            a.record()
+            fn()
+            b.record()
+        finally:
+            _lib.check(lib.dlrmb_clock_enable(None))
+        torch.cuda.synchronize()
+        event_us = 1e3 * a.elapsed_time(b)
+        t0 = int(view[which, :, 0].min().item())
+        t1 = int(view[which, :, 1].max().item())
+        assert t0 < (1 << 62) and t1 > 0, "no stamps written"
+        stamped_us = (t1 - t0) * 1e-3
+        assert stamped_us <= event_us + 1.0, (stamped_us, event_us)
+        # the event pair adds launch latency and an allocation on top of the kernel; a window truncated to the
+        # first 4096 of ~10000 CTAs would be below 0.45 of it at B = 20000
+        if B >= 20000:
+            assert stamped_us > 0.6 * event_us, (stamped_us, event_us)
+        others = [k for k in range(nk) if k != which]
+        assert int(view[others, :, 1].max().item()) == 0, "stamps of a kernel that did not run"

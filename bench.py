@@ -312,6 +312,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def library_options():
+    """The library's tuning switches as this run had them (dlrmb_get_option): defaults unless --opt changed them."""
+    from dlrm_jl_b200 import _lib
+    return {k: _lib.get_option(k) for k in ("interact_general", "update_two_launches", "update_tile", "update_prefetch", "fwd_ksplit")}
+
+
 def bench_config(wl, world, note="", rows_cap=None, host_ram_gb=None):
     return {
         "rows_cap": rows_cap, "host_ram_gb": host_ram_gb,
@@ -757,7 +763,7 @@ def run_ours(args):
             "metric": "dlrm_train_samples_per_sec", "value": Bg * K / (ms_total * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL, "data": "synthetic",
-            "config": dict(bench_config(wl, world), step_launch=mode, exchange=exchange, exchange_check=exchange_check,
+            "config": dict(bench_config(wl, world), library_options=library_options(), step_launch=mode, exchange=exchange, exchange_check=exchange_check,
                            barrier_timeouts=(se.peer.barrier_timeouts() if se.peer is not None else 0),
                            dense_allreduce=("none (single GPU)" if world == 1 else
                                             ("top MLP gradients: NCCL all-reduce started from a gradient hook as soon as the top MLP's backward is "
@@ -1208,6 +1214,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
     ap.add_argument("--sweep-quick", action="store_true", help="--workload sweep on a 2 x 2 x 2 x 2 corner of the grid")
     ap.add_argument("--no-host-leg", action="store_true", help="skip the e2e_host leg (hot path through the *_host entry points)")
+    ap.add_argument("--opt", action="append", default=[],
+                    help="library switch name=value (dlrmb_set_option) for A/B runs; recorded in config.library_options")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -1216,6 +1224,11 @@ def main():
     elif args.workload == "sweep":
         run_sweep(args)
     else:
+        if args.opt:
+            from dlrm_jl_b200 import _lib
+            for kv in args.opt:
+                name, value = kv.split("=")
+                _lib.set_option(name, int(value))
         run_ours(args)
 
 

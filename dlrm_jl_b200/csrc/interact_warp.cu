@@ -228,6 +228,16 @@ struct MmaGeom {
     static constexpr int NPAIR = F * (F - 1) / 2;
     static constexpr int SSZ = F * LDF;                // floats per sample
     static constexpr int WARPS = 2;
+    // The last 8-column tile of the last 16-row tile holds only the pairs among the rows past 8 * (NT - 1): three
+    // of its 128 entries at F = 27 (rows 24..26), a sixth of the sample's MMAs.  When there are at most three such
+    // pairs they are plain FP32 dot products over the warp's lanes instead, and that tile is never issued.
+    static constexpr int TAIL0 = 8 * (NT - 1);         // first row of the tail block
+    static constexpr int TAILR = F - TAIL0;            // rows in it (1..8)
+    static constexpr bool TAIL_FMA = (NT > 1) && (NT == 2 * MT) && (TAILR <= 3);
+    static constexpr int TAILP = TAIL_FMA ? TAILR * (TAILR - 1) / 2 : 0;
+    static __host__ __device__ constexpr bool tile_used(int i, int j) {
+        return j <= 2 * i + 1 && !(TAIL_FMA && i == MT - 1 && j == NT - 1);
+    }
     static constexpr size_t smem_bytes() { return (size_t)WARPS * SSZ * 4 + (size_t)WARPS * 8; }
     static_assert(F <= 32 && D % 8 == 0, "one warp covers F <= 32 rows; k-steps of 8");
     static_assert(((D + 4) / 4) % 2 == 1, "row pitch must stagger the banks");
@@ -238,6 +248,44 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// FP32 dot products of the tail block's row pairs over k in [kbeg, kend): lane-strided partial sums, then an
+// xor-tree over the warp; every lane returns the totals.  Pair order: (r0+1, r0), (r0+2, r0), (r0+2, r0+1).
+template <int F, int D>
+__device__ __forceinline__ void tail_pairs_fma(const float* Ts, int lane, int kbeg, int kend, float (&tp)[3]) {
+    using G = MmaGeom<F, D>;
+    tp[0] = tp[1] = tp[2] = 0.f;
+    if (G::TAILP == 0) return;
+    const float* r0 = Ts + G::TAIL0 * G::LDF;
+    for (int k = kbeg + lane; k < kend; k += 32) {
+        const float a = r0[k], b = r0[G::LDF + k];
+        tp[0] = fmaf(b, a, tp[0]);
+        if (G::TAILR == 3) {
+            const float c = r0[2 * G::LDF + k];
+            tp[1] = fmaf(c, a, tp[1]);
+            tp[2] = fmaf(c, b, tp[2]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (q >= G::TAILP) break;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) tp[q] += __shfl_xor_sync(0xffffffffu, tp[q], off);
+    }
+}
+
+// where the tail pairs go in the staged output row: pair (row, col) sits at row * (row - 1) / 2 + col
+template <int F, int D>
+__device__ __forceinline__ void tail_pairs_store(float* Os, int lane, const float (&tp)[3]) {
+    using G = MmaGeom<F, D>;
+    if (G::TAILP == 0) return;
+    constexpr int r1 = G::TAIL0 + 1, r2 = G::TAIL0 + 2;
+    if (lane == 0) Os[r1 * (r1 - 1) / 2 + G::TAIL0] = tp[0];
+    if (G::TAILR == 3) {
+        if (lane == 1) Os[r2 * (r2 - 1) / 2 + G::TAIL0] = tp[1];
+        if (lane == 2) Os[r2 * (r2 - 1) / 2 + G::TAIL0 + 1] = tp[2];
+    }
 }
 
 template <int F, int D>
@@ -320,7 +368,7 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
             const unsigned al[4] = {lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1]};
 #pragma unroll
             for (int j = 0; j < G::NT; ++j) {
-                if (j > 2 * i + 1) continue;            // tile entirely above the diagonal
+                if (!G::tile_used(i, j)) continue;      // tile entirely above the diagonal, or the tail tile
                 // small terms first.  (Measured and not taken: issuing the three passes tile-
                 // interleaved so that no MMA waits for its predecessor, 14.3 vs 13.8 us at B = 2048;
                 // delivering the tile as two column halves on two mbarriers so that the first half's
@@ -332,6 +380,8 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
             }
         }
     }
+    float tp[3];
+    tail_pairs_fma<F, D>(Ts, lane, 0, D, tp);
     __syncwarp();   // every lane is done reading rows >= 1: their space becomes the output staging
 
     float* Os = Ts + G::LDF;   // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
@@ -339,7 +389,7 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
     for (int i = 0; i < G::MT; ++i)
 #pragma unroll
         for (int j = 0; j < G::NT; ++j) {
-            if (j > 2 * i + 1) continue;
+            if (!G::tile_used(i, j)) continue;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int row = 16 * i + g + ((e & 2) ? 8 : 0);
@@ -347,6 +397,7 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
                 if (col < row && row < F) Os[row * (row - 1) / 2 + col] = acc[i][j][e];
             }
         }
+    tail_pairs_store<F, D>(Os, lane, tp);
     __syncwarp();
 
     float* og = out + (size_t)b * width;
@@ -435,27 +486,35 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
             const unsigned al[4] = {lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1]};
 #pragma unroll
             for (int j = 0; j < G::NT; ++j) {
-                if (j > 2 * i + 1) continue;            // tile entirely above the diagonal
+                if (!G::tile_used(i, j)) continue;      // tile entirely above the diagonal, or the tail tile
                 mma_tf32(acc[i][j], al, hi[j][0], hi[j][1]);
                 mma_tf32(acc[i][j], ah, lo[j][0], lo[j][1]);
                 mma_tf32(acc[i][j], ah, hi[j][0], hi[j][1]);
             }
         }
     }
+    float tp[3];
+    tail_pairs_fma<F, D>(Ts, lane, kbeg, kbeg + D / 2, tp);
     __syncthreads();   // both warps are done reading rows >= 1: their space becomes scratch
 
     float* Os = Ts + G::LDF;                  // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
-    float* red = Os + ((G::NPAIR + 3) & ~3);  // warp 1's partial accumulators: [tile][e][lane]
-    static_assert(((G::NPAIR + 3) & ~3) + G::MT * G::NT * 4 * 32 <= (F - 1) * G::LDF, "scratch must fit behind row 0");
+    float* red = Os + ((G::NPAIR + 3) & ~3);  // warp 1's partial accumulators: [tile][e][lane], then its tail pairs
+    float* red_tail = red + G::MT * G::NT * 4 * 32;
+    static_assert(((G::NPAIR + 3) & ~3) + G::MT * G::NT * 4 * 32 + 4 <= (F - 1) * G::LDF, "scratch must fit behind row 0");
     if (warp == 1) {
 #pragma unroll
         for (int i = 0; i < G::MT; ++i)
 #pragma unroll
             for (int j = 0; j < G::NT; ++j) {
-                if (j > 2 * i + 1) continue;
+                if (!G::tile_used(i, j)) continue;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) red[((i * G::NT + j) * 4 + e) * 32 + lane] = acc[i][j][e];
             }
+        if (G::TAILP > 0 && lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < G::TAILP) red_tail[q] = tp[q];
+        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -463,7 +522,7 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
         for (int i = 0; i < G::MT; ++i)
 #pragma unroll
             for (int j = 0; j < G::NT; ++j) {
-                if (j > 2 * i + 1) continue;
+                if (!G::tile_used(i, j)) continue;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float v = acc[i][j][e] + red[((i * G::NT + j) * 4 + e) * 32 + lane];
@@ -472,6 +531,12 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
                     if (col < row && row < F) Os[row * (row - 1) / 2 + col] = v;
                 }
             }
+        if (G::TAILP > 0) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < G::TAILP) tp[q] += red_tail[q];
+            tail_pairs_store<F, D>(Os, lane, tp);
+        }
     }
     __syncthreads();
 

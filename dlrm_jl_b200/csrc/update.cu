@@ -89,7 +89,20 @@ struct UpdateGeom {
     int chunks;          // CTAs (chunks of G tiles) per table
     int G;               // lane groups (= tiles) per CTA of update_tiles_kernel
     int64_t cap, pcap;   // stream stride per table; partial / flag stride per table (in chunks)
+    int prefetch;        // L2 prefetch of the tile's rows ahead of the walk: bit 0 table rows, bit 1 gradient rows,
+                         // bit 2 = one prefetch.global.L2 per 16-byte chunk instead of one bulk prefetch per row
 };
+
+// L2 prefetch hints.  A lane group walks its tile 4 entries at a time, each step a dependent
+// keys -> rows -> store round trip; asking L2 for every row of the tile before the walk starts turns the
+// tile's DRAM reads into one burst and the walk's loads into L2 hits.  Hints only: no data is returned, no
+// ordering is implied, and the addresses are the ones the walk itself reads.
+__device__ __forceinline__ void l2_prefetch_row(const void* p, unsigned bytes) {   // p, bytes: multiples of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // Level 3: runs that cross chunk boundaries.  One CTA per listed head chunk: the end of the run is
 // found by probing the chunk flags THREADS at a time, lane group `sub` adds the carry partials of
@@ -282,6 +295,37 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     if (active) {
         const int e0 = g * gm.tile;
         const int e1 = min(gm.L, e0 + gm.tile);
+        if (gm.prefetch & 3) {
+            const int ne = e1 - e0;
+            const unsigned row_bytes = (unsigned)(D * sizeof(RowT));
+            const char* tbytes = reinterpret_cast<const char*>(tb);
+            if (gm.prefetch & 4) {   // every lane of the group asks for its own chunks of every row
+                for (int i = 0; i < ne; ++i) {
+                    if (gm.prefetch & 1) {
+                        const char* row = tbytes + (size_t)__ldg(ks + e0 + i) * row_bytes;
+#pragma unroll
+                        for (int m = 0; m < NCH; ++m)
+                            if (chunk_ok[m]) l2_prefetch_line(row + (size_t)(sl + m * lpr) * (VEC * sizeof(RowT)));
+                    }
+                    if (gm.prefetch & 2) {
+                        const uint32_t pi = __ldg(ps + e0 + i);
+                        const float* src = gbase + (size_t)((gm.P == 1) ? pi : pi / (uint32_t)gm.P) * gstride;
+#pragma unroll
+                        for (int m = 0; m < NCH; ++m)
+                            if (chunk_ok[m]) l2_prefetch_line(src + (size_t)(sl + m * lpr) * VEC);
+                    }
+                }
+            } else {                 // lane i of the group asks for the whole rows of entry i
+                for (int i = sl; i < ne; i += lpr) {
+                    if (gm.prefetch & 1) l2_prefetch_row(tbytes + (size_t)__ldg(ks + e0 + i) * row_bytes, row_bytes);
+                    if (gm.prefetch & 2) {
+                        const uint32_t pi = __ldg(ps + e0 + i);
+                        l2_prefetch_row(gbase + (size_t)((gm.P == 1) ? pi : pi / (uint32_t)gm.P) * gstride,
+                                        (unsigned)(D * sizeof(float)));
+                    }
+                }
+            }
+        }
         uint4 kq = __ldg(reinterpret_cast<const uint4*>(ks + e0));
         uint4 pq = __ldg(reinterpret_cast<const uint4*>(ps + e0));
         uint32_t kn = (e0 + U < gm.L) ? __ldg(ks + e0 + U) : 0xffffffffu;
@@ -529,6 +573,14 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     gm.slot0 = slot0;
     gm.cap = t->cap;
     gm.pcap = t->partial_tiles_cap;
+    gm.prefetch = g_opt.update_prefetch.load(std::memory_order_relaxed) & 7;
+    // bulk prefetches take 16-byte aligned rows of a multiple of 16 bytes; otherwise one hint per chunk
+    if ((gm.prefetch & 3) && !(gm.prefetch & 4)) {
+        const bool rows16 = ((size_t)t->D * sizeof(RowT)) % 16 == 0;
+        const bool grads16 = ((size_t)t->D * sizeof(float)) % 16 == 0 && ((size_t)slots * t->D * sizeof(float)) % 16 == 0 &&
+                             (reinterpret_cast<uintptr_t>(dT) & 15) == 0;
+        if (((gm.prefetch & 1) && !rows16) || ((gm.prefetch & 2) && !grads16)) gm.prefetch |= 4;
+    }
     DLRMB_REQUIRE(gm.chunks <= gm.pcap, "internal: update chunk capacity exceeded (%d > %lld)",
                   gm.chunks, (long long)gm.pcap);
     DLRMB_REQUIRE((int64_t)t->ntab * gm.chunks < (1ll << 31), "batch too large for one update launch");
@@ -537,7 +589,12 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     dim3 grid((unsigned)gm.chunks, (unsigned)t->ntab);
     const int64_t total_chunks = (int64_t)t->ntab * gm.chunks;
     // DLRM-sized batches: level 3 runs inside the same launch (see the header comment)
-    const bool inline_fixup = (int64_t)t->ntab * gm.L <= kUpdateInlineMaxEntries &&
+    int64_t inline_max = kUpdateInlineMaxEntries;
+    {   // tuning aid (dlrmb_set_option("update_inline_log2", v)): inline fix-up up to 2^v entries per launch
+        const int v = g_opt.update_inline_log2.load(std::memory_order_relaxed);
+        if (v >= 1 && v <= 30) inline_max = 1ll << v;
+    }
+    const bool inline_fixup = (int64_t)t->ntab * gm.L <= inline_max &&
                               g_opt.update_two_launches.load(std::memory_order_relaxed) == 0;
     if (inline_fixup) {
         update_tiles_kernel<VEC, NCH, THREADS, RowT, true><<<grid, THREADS, 0, s>>>(

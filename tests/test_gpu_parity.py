@@ -1160,6 +1160,36 @@ def test_sparse_sgd_any_tile_length_gives_the_same_tables(tile, lib_options):
         assert O.rel_err(a[k], ref[k]) < SGD_RTOL, k
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3, 5, 6, 7])
+@pytest.mark.parametrize("D,dtype", [(128, "f32"), (64, "f32"), (10, "f32"), (256, "f32"), (64, "bf16"), (20, "bf16")])
+def test_sparse_sgd_l2_prefetch_hints_do_not_change_the_tables(mode, D, dtype, lib_options):
+    """update_prefetch asks L2 for a tile's table / gradient rows before the walk (bulk prefetch per row, or one
+    prefetch per 16-byte chunk when a row is not a multiple of 16 bytes: D = 10 f32, D = 20 bf16).  Hints only:
+    every mode must leave bit-identical tables, pooled (P = 3) and hot-row (Zipf) batches included."""
+    from dlrm_jl_b200.embedding import EmbeddingTables
+    rng = np.random.default_rng(100 * mode + D)
+    rows, B, P = [3, 40, 50000, 7, 1000], 2051, 3
+    tables = _rand_tables(rng, rows, D)
+    idx = [np.minimum((rng.pareto(1.05, size=(B, P)) * 1.0).astype(np.int64), r - 1) for r in rows]
+    idx[2] = rng.integers(0, rows[2], size=(B, P))
+    dev_idx = torch.from_numpy(np.stack(idx)).to(_dev())
+    g = torch.from_numpy((rng.standard_normal((B, 1 + len(rows), D)) * 0.01).astype(np.float32)).to(_dev())
+
+    def run(prefetch):
+        lib_options("update_prefetch", prefetch)
+        t = EmbeddingTables.from_arrays(tables, B * P, 0, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32)
+        for _ in range(2):
+            t.bwd_sgd(dev_idx, g, 1, 0.5)
+        out = [t.download(k) for k in range(len(rows))]
+        t.close()
+        return out
+
+    base = run(0)
+    got = run(mode)
+    for k in range(len(rows)):
+        assert np.array_equal(base[k], got[k]), (k, mode)
+
+
 def test_sparse_update_launched_inside_backward_equals_explicit_update():
     """ShardedEmbedding.update_inside_backward (the bench's form: the update is launched by the lookup's pullback
     on a side stream, beside the rest of the backward pass) gives the tables of the explicit update call."""

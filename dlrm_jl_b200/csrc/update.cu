@@ -295,6 +295,11 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
     if (active) {
         const int e0 = g * gm.tile;
         const int e1 = min(gm.L, e0 + gm.tile);
+        uint4 kq = __ldg(reinterpret_cast<const uint4*>(ks + e0));
+        uint4 pq = __ldg(reinterpret_cast<const uint4*>(ps + e0));
+        uint32_t kn = (e0 + U < gm.L) ? __ldg(ks + e0 + U) : 0xffffffffu;
+        const uint32_t kprev = (e0 > 0) ? __ldg(ks + e0 - 1) : 0xffffffffu;
+        // (after the walk's first key / position loads have been issued: the hints wait for keys of their own)
         if (gm.prefetch & 3) {
             const int ne = e1 - e0;
             const unsigned row_bytes = (unsigned)(D * sizeof(RowT));
@@ -326,10 +331,6 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
                 }
             }
         }
-        uint4 kq = __ldg(reinterpret_cast<const uint4*>(ks + e0));
-        uint4 pq = __ldg(reinterpret_cast<const uint4*>(ps + e0));
-        uint32_t kn = (e0 + U < gm.L) ? __ldg(ks + e0 + U) : 0xffffffffu;
-        const uint32_t kprev = (e0 > 0) ? __ldg(ks + e0 - 1) : 0xffffffffu;
         const bool cin = e0 > 0 && kprev == kq.x;
         bool cout = false;
         bool first = cin;

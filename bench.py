@@ -315,7 +315,7 @@ def run_reference(args):
 def library_options():
     """The library's tuning switches as this run had them (dlrmb_get_option): defaults unless --opt changed them."""
     from dlrm_jl_b200 import _lib
-    return {k: _lib.get_option(k) for k in ("interact_general", "update_two_launches", "update_tile", "update_prefetch", "fwd_ksplit")}
+    return {k: _lib.get_option(k) for k in ("interact_general", "update_two_launches", "update_tile", "bwd_variant", "fwd_ksplit")}
 
 
 def bench_config(wl, world, note="", rows_cap=None, host_ram_gb=None):

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""A/B of the sparse update's switches in ONE process (tables built once): L2 prefetch hints
-(`update_prefetch`), tile length (`update_tile`), same-launch fix-up limit (`update_inline_log2`).
+"""A/B of the sparse update's switches in ONE process (tables built once): tile length (`update_tile`), one- or
+two-launch fix-up (`update_two_launches`).  (Round 2, visit U also ran it with two switches that were measured
+and then removed from the library: L2 prefetch hints for a tile's rows and a larger same-launch fix-up limit --
+results in profiles/r02_update_ab.txt.)
 
     python benchmarks/ab_update.py [--workload terabyte|kaggle] [--B 2048] [--nb 16]
 
@@ -32,7 +34,7 @@ def main():
     ap.add_argument("--B", type=int, nargs="*", default=[2048])
     ap.add_argument("--nb", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--cases", default="prefetch,tile,inline")
+    ap.add_argument("--cases", default="tile,two")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     if a.workload == "kaggle":
@@ -80,16 +82,11 @@ def main():
 
         cases = a.cases.split(",")
         measure({})
-        if "prefetch" in cases:
-            for pf in (1, 2, 3, 5, 7):
-                measure({"update_prefetch": pf})
         if "tile" in cases:
             for tile in (8, 12, 20, 24, 32):
-                measure({"update_prefetch": 3, "update_tile": tile})
                 measure({"update_tile": tile})
-        if "inline" in cases and ntab * B > (1 << 18):
-            measure({"update_inline_log2": 20})
-            measure({"update_inline_log2": 20, "update_prefetch": 3})
+        if "two" in cases:
+            measure({"update_two_launches": 1})
         measure({})
         del idx, dTs, T
         torch.cuda.empty_cache()

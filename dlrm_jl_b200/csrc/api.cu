@@ -121,8 +121,7 @@ static std::atomic<int>* find_option(const char* name) {
     if (!strcmp(name, "interact_general")) return &g_opt.interact_general;
     if (!strcmp(name, "update_two_launches")) return &g_opt.update_two_launches;
     if (!strcmp(name, "update_tile")) return &g_opt.update_tile;
-    if (!strcmp(name, "update_prefetch")) return &g_opt.update_prefetch;
-    if (!strcmp(name, "update_inline_log2")) return &g_opt.update_inline_log2;
+    if (!strcmp(name, "bwd_variant")) return &g_opt.bwd_variant;
     if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
     if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
     if (!strcmp(name, "fwd_ksplit")) return &g_opt.fwd_ksplit;

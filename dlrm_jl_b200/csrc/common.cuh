@@ -138,9 +138,8 @@ struct Options {
     std::atomic<int> interact_general{0};     // 1: general tiled interaction kernels even for the specialised shapes
     std::atomic<int> update_two_launches{0};  // 1: separate fix-up launch at every batch size
     std::atomic<int> update_tile{0};          // 4, 8, .. 32 entries per lane group (0 = chosen per batch)
-    std::atomic<int> update_inline_log2{0};   // inline (same-launch) fix-up up to 2^v entries per launch (0 = 2^18)
-    std::atomic<int> update_prefetch{0};      // L2 prefetch of a tile's rows before the walk: bit 0 table rows, bit 1 gradient
-                                              // rows, bit 2 per-chunk prefetch.global.L2 instead of one bulk prefetch per row
+    std::atomic<int> bwd_variant{0};          // warp-per-sample backward at d = 128: 0 = 144 registers, 1..3 = 128 registers with
+                                              // 3 / 1 / 9 output rows per pass
     std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
     std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
     std::atomic<int> fwd_ksplit{1};           // tensor-core forward: 0 = one warp per sample always, 1 = two warps per sample for

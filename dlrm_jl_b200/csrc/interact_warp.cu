@@ -64,7 +64,7 @@ struct PairTable {
 };
 __device__ const PairTable kPairTable{};
 
-template <int F, int D>
+template <int F, int D, int VAR = 0>
 struct BwdGeom {
     static constexpr int LPS = D / 4;            // lanes per sample (one float4 of k each)
     static constexpr int SPW = 32 / LPS;         // samples per warp
@@ -72,22 +72,28 @@ struct BwdGeom {
     static constexpr int NPAIR = F * (F - 1) / 2;
     static constexpr int NI = (NPAIR + 31) / 32; // pair entries per lane
     static constexpr int SSTRIDE = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
-    static constexpr int NF = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);   // output rows per pass
+    static constexpr int NF0 = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);
+    // output rows per pass.  VAR (one sample per warp, plain stores only): 0 = NF0 rows at 144 registers, 1 = NF0 rows
+    // at 128, 2 = one row at 128, 3 = nine rows at 128 (the compiler then walks the rows one after another)
+    static constexpr int NF = (VAR == 2) ? 1 : ((VAR == 3 && F % 9 == 0) ? 9 : NF0);
     static constexpr int WARPS = 2;
-    // d = 128 (one sample per warp): 7 CTAs = 14 warps per SM make 2048 samples a single wave on 148
-    // SMs, which caps the kernel at 128 registers; the variants that would spill at that cap (several
-    // samples per warp, peer-store epilogue) need half the warps for the same batch and keep 6 CTAs
-    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? 144 : 168; }
+    // Registers are allocated per SM sub-partition (16384 each): a 32-thread warp at 144 or 168 registers leaves
+    // room for 3 warps per sub-partition = 12 per SM = 6 CTAs, so 2048 samples at d = 128 (one sample per warp,
+    // 1024 CTAs) are 888 CTAs + a second wave of 136 that starts when the first ends (per-CTA %globaltimer
+    // stamps, benchmarks/cta_timeline.py: 13 % of the CTAs enter 12 us after the first).  At 128 registers 4 warps
+    // fit per sub-partition = 8 CTAs per SM and the batch is one wave.  The variants with several samples per
+    // warp or the peer-store epilogue need half the warps for the same batch and keep 168.
+    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? (VAR == 0 ? 144 : 128) : 168; }
     static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4; }
     static_assert(F <= 32, "pair table covers F <= 32");
 };
 
-template <int F, int D, bool SCATTER>
-__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32) __maxnreg__((BwdGeom<F, D>::max_regs(SCATTER)))
+template <int F, int D, bool SCATTER, int VAR>
+__global__ void __launch_bounds__(BwdGeom<F, D, VAR>::WARPS * 32) __maxnreg__((BwdGeom<F, D, VAR>::max_regs(SCATTER)))
 interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
                             float* __restrict__ dT, float* __restrict__ dx,
                             const SlotDestW* __restrict__ dests, long long sample_offset, unsigned long long* clk) {
-    using G = BwdGeom<F, D>;
+    using G = BwdGeom<F, D, VAR>;
     extern __shared__ float4 smem4[];
     clock_in(clk, blockIdx.x);
     float* Sd = reinterpret_cast<float*>(smem4);                                   // [WARPS][SPW][SSTRIDE]
@@ -572,27 +578,46 @@ int launch_fwd_mma(float* T, const float* x, int B, int width, float* out, cudaS
     return DLRMB_OK;
 }
 
+template <int F, int D, int VAR>
+int launch_bwd_warp_plain(const float* dOut, const float* T, int B, int width, float* dT, float* dx, cudaStream_t s) {
+    using G = BwdGeom<F, D, VAR>;
+    static unsigned long long attr_done = 0;
+    const size_t smem = G::smem_bytes();
+    const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
+    const long long grid = (groups + G::WARPS - 1) / G::WARPS;
+    int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, false, VAR>, (int)smem, &attr_done);
+    if (rc) return rc;
+    interaction_bwd_warp_kernel<F, D, false, VAR><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
+        dOut, T, B, width, dT, dx, nullptr, 0, clock_slot(CLK_IBWD));
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
+}
+
 template <int F, int D>
 int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
                     const void* dests, long long sample_offset, cudaStream_t s) {
     using G = BwdGeom<F, D>;
-    static unsigned long long attr_done[2] = {0, 0};
-    const size_t smem = G::smem_bytes();
-    const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
-    const long long grid = (groups + G::WARPS - 1) / G::WARPS;
     if (dests) {
-        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, true>, (int)smem, &attr_done[1]);
+        static unsigned long long attr_done = 0;
+        const size_t smem = G::smem_bytes();
+        const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
+        const long long grid = (groups + G::WARPS - 1) / G::WARPS;
+        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, true, 0>, (int)smem, &attr_done);
         if (rc) return rc;
-        interaction_bwd_warp_kernel<F, D, true><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
+        interaction_bwd_warp_kernel<F, D, true, 0><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
             dOut, T, B, width, dT, dx, static_cast<const SlotDestW*>(dests), sample_offset, clock_slot(CLK_IBWD));
-    } else {
-        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, false>, (int)smem, &attr_done[0]);
-        if (rc) return rc;
-        interaction_bwd_warp_kernel<F, D, false><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
-            dOut, T, B, width, dT, dx, nullptr, 0, clock_slot(CLK_IBWD));
+        DLRMB_LAUNCH_CHECK();
+        return DLRMB_OK;
     }
-    DLRMB_LAUNCH_CHECK();
-    return DLRMB_OK;
+    if (G::SPW == 1) {   // one sample per warp: register-cap / rows-per-pass variants ("bwd_variant")
+        switch (g_opt.bwd_variant.load(std::memory_order_relaxed)) {
+            case 1: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
+            case 2: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
+            case 3: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 3 : 0>(dOut, T, B, width, dT, dx, s);
+            default: break;
+        }
+    }
+    return launch_bwd_warp_plain<F, D, 0>(dOut, T, B, width, dT, dx, s);
 }
 
 constexpr int kKsplitMaxBatch = 4096;   // up to here the forward is one wave of CTAs on 148 SMs

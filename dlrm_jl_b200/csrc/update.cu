@@ -89,20 +89,7 @@ struct UpdateGeom {
     int chunks;          // CTAs (chunks of G tiles) per table
     int G;               // lane groups (= tiles) per CTA of update_tiles_kernel
     int64_t cap, pcap;   // stream stride per table; partial / flag stride per table (in chunks)
-    int prefetch;        // L2 prefetch of the tile's rows ahead of the walk: bit 0 table rows, bit 1 gradient rows,
-                         // bit 2 = one prefetch.global.L2 per 16-byte chunk instead of one bulk prefetch per row
 };
-
-// L2 prefetch hints.  A lane group walks its tile 4 entries at a time, each step a dependent
-// keys -> rows -> store round trip; asking L2 for every row of the tile before the walk starts turns the
-// tile's DRAM reads into one burst and the walk's loads into L2 hits.  Hints only: no data is returned, no
-// ordering is implied, and the addresses are the ones the walk itself reads.
-__device__ __forceinline__ void l2_prefetch_row(const void* p, unsigned bytes) {   // p, bytes: multiples of 16
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void l2_prefetch_line(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 // Level 3: runs that cross chunk boundaries.  One CTA per listed head chunk: the end of the run is
 // found by probing the chunk flags THREADS at a time, lane group `sub` adds the carry partials of
@@ -244,6 +231,66 @@ __device__ __forceinline__ void fixup_runs_grouped(const TableDesc* __restrict__
     }
 }
 
+// Level 3 inside the tiles launch when the table has at most kInlineSmemChunks chunks (every DLRM-sized batch):
+// the last CTA of the table has the chunk flags, the list of head chunks and the heads' row ids in shared memory
+// (one round of loads), a lane group finds its run's end with ballots over the shared flags, and the head partial,
+// the row and the first eight carry partials of the run are requested together -- one more round of loads instead
+// of one per partial.  Same summation order as fixup_runs_grouped / fixup_runs, hence the same bits.
+constexpr int kInlineSmemChunks = 1024;
+
+template <int VEC, int NCH, typename RowT>
+__device__ __forceinline__ void fixup_runs_smem(const TableDesc* __restrict__ desc, float lr, const float* partial,
+                                                const uint8_t* s_fl, const uint16_t* s_heads, const uint32_t* s_hkey,
+                                                uint32_t n_heads, int k, int grp, int G, int sl, const UpdateGeom& gm) {
+    using V = typename UV<VEC>::type;
+    const int lpr = 1 << gm.lpr_log2;
+    const int nsub = 256 >> gm.lpr_log2;                 // lane groups of update_fixup_kernel
+    const size_t D = (size_t)gm.C * VEC;
+    const unsigned gshift = (threadIdx.x & 31) & ~(lpr - 1);
+    const unsigned gmask = (lpr >= 32) ? 0xffffffffu : (((1u << lpr) - 1u) << gshift);
+    const float* pk = partial + (size_t)k * gm.pcap * 2 * D;
+    float* tbase = desc[k].base;
+    for (uint32_t h = grp; h < n_heads; h += G) {
+        const int g = s_heads[h];
+        const uint32_t key = s_hkey[h];
+        int u_last = gm.chunks - 1;
+        for (int base = g + 1; base < gm.chunks; base += lpr) {
+            const int u = base + sl;
+            const bool ends = (u >= gm.chunks) || (s_fl[u] & FLAG_CARRY_ENDS);
+            const unsigned b = __ballot_sync(gmask, ends) >> gshift;
+            if (b != 0) {
+                u_last = min(gm.chunks - 1, base + __ffs((int)b) - 1);
+                break;
+            }
+        }
+        const int nact = min(nsub, u_last - g);
+        const V* hp = reinterpret_cast<const V*>(pk + ((size_t)g * 2 + 1) * D);
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) {
+            const int c = sl + m * lpr;
+            if (c >= gm.C) continue;
+            V total = __ldcg(hp + c);
+            const V row = RowV<VEC, RowT>::load(tbase, key, D, c);
+            for (int jb = 0; jb < nact; jb += 8) {
+                V p[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (jb + q < nact) p[q] = __ldcg(reinterpret_cast<const V*>(pk + (size_t)(g + 1 + jb + q) * 2 * D) + c);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (jb + q >= nact) break;
+                    V acc = UV<VEC>::add(UV<VEC>::zero(), p[q]);
+#pragma unroll 4
+                    for (int u = g + 1 + jb + q + nsub; u <= u_last; u += nsub)
+                        acc = UV<VEC>::add(acc, __ldcg(reinterpret_cast<const V*>(pk + (size_t)u * 2 * D) + c));
+                    total = UV<VEC>::add(total, acc);
+                }
+            }
+            RowV<VEC, RowT>::store(tbase, key, D, c, UV<VEC>::sgd(row, total, lr));
+        }
+    }
+}
+
 // head_count: [0] = listed head chunks (two-launch path), [1 + k] = CTAs of table k that are done
 // (INLINE path; zero between launches).
 template <int VEC, int NCH, int THREADS, typename RowT, bool INLINE>
@@ -299,38 +346,6 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         uint4 pq = __ldg(reinterpret_cast<const uint4*>(ps + e0));
         uint32_t kn = (e0 + U < gm.L) ? __ldg(ks + e0 + U) : 0xffffffffu;
         const uint32_t kprev = (e0 > 0) ? __ldg(ks + e0 - 1) : 0xffffffffu;
-        // (after the walk's first key / position loads have been issued: the hints wait for keys of their own)
-        if (gm.prefetch & 3) {
-            const int ne = e1 - e0;
-            const unsigned row_bytes = (unsigned)(D * sizeof(RowT));
-            const char* tbytes = reinterpret_cast<const char*>(tb);
-            if (gm.prefetch & 4) {   // every lane of the group asks for its own chunks of every row
-                for (int i = 0; i < ne; ++i) {
-                    if (gm.prefetch & 1) {
-                        const char* row = tbytes + (size_t)__ldg(ks + e0 + i) * row_bytes;
-#pragma unroll
-                        for (int m = 0; m < NCH; ++m)
-                            if (chunk_ok[m]) l2_prefetch_line(row + (size_t)(sl + m * lpr) * (VEC * sizeof(RowT)));
-                    }
-                    if (gm.prefetch & 2) {
-                        const uint32_t pi = __ldg(ps + e0 + i);
-                        const float* src = gbase + (size_t)((gm.P == 1) ? pi : pi / (uint32_t)gm.P) * gstride;
-#pragma unroll
-                        for (int m = 0; m < NCH; ++m)
-                            if (chunk_ok[m]) l2_prefetch_line(src + (size_t)(sl + m * lpr) * VEC);
-                    }
-                }
-            } else {                 // lane i of the group asks for the whole rows of entry i
-                for (int i = sl; i < ne; i += lpr) {
-                    if (gm.prefetch & 1) l2_prefetch_row(tbytes + (size_t)__ldg(ks + e0 + i) * row_bytes, row_bytes);
-                    if (gm.prefetch & 2) {
-                        const uint32_t pi = __ldg(ps + e0 + i);
-                        l2_prefetch_row(gbase + (size_t)((gm.P == 1) ? pi : pi / (uint32_t)gm.P) * gstride,
-                                        (unsigned)(D * sizeof(float)));
-                    }
-                }
-            }
-        }
         const bool cin = e0 > 0 && kprev == kq.x;
         bool cout = false;
         bool first = cin;
@@ -435,7 +450,11 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
 #pragma unroll
             for (int m = 0; m < NCH; ++m)
                 if (chunk_ok[m]) reinterpret_cast<V*>(phead)[sl + m * lpr] = tot[m];
-            if (sl == 0) s_cta_head = 1;
+            if (sl == 0) {
+                s_cta_head = 1;
+                // same-launch fix-up from shared memory: the run's row id travels with the chunk's flag
+                if (INLINE && gm.chunks <= kInlineSmemChunks) head_list[(size_t)k * gm.pcap + cta] = last_key;
+            }
             wrote_scratch = true;
         }
     }
@@ -487,6 +506,32 @@ update_tiles_kernel(const TableDesc* __restrict__ desc, const uint32_t* __restri
         return;
     }
     __threadfence();
+    if (gm.chunks <= kInlineSmemChunks) {
+        __shared__ uint8_t s_fl[kInlineSmemChunks];
+        __shared__ uint16_t s_heads[kInlineSmemChunks];
+        __shared__ uint32_t s_hkey[kInlineSmemChunks];
+        const uint8_t* fk = flags + (size_t)k * gm.pcap;
+        const uint32_t* hk = head_list + (size_t)k * gm.pcap;
+        for (int base = 0; base < gm.chunks; base += THREADS) {
+            const int u = base + tid;
+            if (u < gm.chunks) {
+                const uint8_t f = __ldcg(fk + u);
+                const uint32_t key = __ldcg(hk + u);     // meaningful for head chunks only
+                s_fl[u] = f;
+                if (f & FLAG_HEAD) {
+                    const uint32_t slot = atomicAdd(&s_nheads, 1u);
+                    s_heads[slot] = (uint16_t)u;
+                    s_hkey[slot] = key;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_heads = s_nheads;
+        if (n_heads != 0) fixup_runs_smem<VEC, NCH, RowT>(desc, lr, partial, s_fl, s_heads, s_hkey, n_heads, k, grp, G, sl, gm);
+        __syncthreads();      // thread 0 stamps the exit after every lane group of the CTA has finished its runs
+        clock_out(clk, clk_cta);
+        return;
+    }
     // list the table's head chunks (order irrelevant: distinct runs touch distinct rows)
     uint32_t* my_heads = head_list + (size_t)k * gm.pcap;
     const uint8_t* fk = flags + (size_t)k * gm.pcap;
@@ -574,14 +619,6 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     gm.slot0 = slot0;
     gm.cap = t->cap;
     gm.pcap = t->partial_tiles_cap;
-    gm.prefetch = g_opt.update_prefetch.load(std::memory_order_relaxed) & 7;
-    // bulk prefetches take 16-byte aligned rows of a multiple of 16 bytes; otherwise one hint per chunk
-    if ((gm.prefetch & 3) && !(gm.prefetch & 4)) {
-        const bool rows16 = ((size_t)t->D * sizeof(RowT)) % 16 == 0;
-        const bool grads16 = ((size_t)t->D * sizeof(float)) % 16 == 0 && ((size_t)slots * t->D * sizeof(float)) % 16 == 0 &&
-                             (reinterpret_cast<uintptr_t>(dT) & 15) == 0;
-        if (((gm.prefetch & 1) && !rows16) || ((gm.prefetch & 2) && !grads16)) gm.prefetch |= 4;
-    }
     DLRMB_REQUIRE(gm.chunks <= gm.pcap, "internal: update chunk capacity exceeded (%d > %lld)",
                   gm.chunks, (long long)gm.pcap);
     DLRMB_REQUIRE((int64_t)t->ntab * gm.chunks < (1ll << 31), "batch too large for one update launch");
@@ -590,12 +627,7 @@ static int launch_update_t(dlrmb_tables* t, const float* dT, int slots, int slot
     dim3 grid((unsigned)gm.chunks, (unsigned)t->ntab);
     const int64_t total_chunks = (int64_t)t->ntab * gm.chunks;
     // DLRM-sized batches: level 3 runs inside the same launch (see the header comment)
-    int64_t inline_max = kUpdateInlineMaxEntries;
-    {   // tuning aid (dlrmb_set_option("update_inline_log2", v)): inline fix-up up to 2^v entries per launch
-        const int v = g_opt.update_inline_log2.load(std::memory_order_relaxed);
-        if (v >= 1 && v <= 30) inline_max = 1ll << v;
-    }
-    const bool inline_fixup = (int64_t)t->ntab * gm.L <= inline_max &&
+    const bool inline_fixup = (int64_t)t->ntab * gm.L <= kUpdateInlineMaxEntries &&
                               g_opt.update_two_launches.load(std::memory_order_relaxed) == 0;
     if (inline_fixup) {
         update_tiles_kernel<VEC, NCH, THREADS, RowT, true><<<grid, THREADS, 0, s>>>(

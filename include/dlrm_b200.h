@@ -59,9 +59,8 @@ int64_t dlrmb_launch_count(void);
  *   "interact_general" 1 = run the general tiled interaction kernels even for the specialised shapes
  *   "update_two_launches" 1 = separate fix-up launch of the sparse update at every batch size
  *   "update_tile" 4, 8, .. 32 = entries per lane group of the sparse update (0 = chosen per batch)
- *   "update_prefetch" bit 0 / bit 1 = ask L2 for a tile's table rows / gradient rows before the sparse update walks
- *                     it (one bulk prefetch per row; bit 2 = one prefetch per 16-byte chunk instead)
- *   "update_inline_log2" v = sparse-update fix-up inside the tiles launch up to 2^v entries per launch (0 = 2^18)
+ *   "bwd_variant" 0..3 = warp-per-sample interaction backward (d = 128): 144 registers, or 128 registers (8 CTAs per SM)
+ *                     with 3 / 1 / 9 output rows per pass
  *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
  *   "fwd_ksplit" 0|1|2 = tensor-core forward with one warp per sample always / two warps per sample for one-wave
  *                        batches (default) / two warps per sample always

@@ -71,11 +71,19 @@ struct BwdGeom {
     static constexpr int FP2 = (F + 1) & ~1;     // S row length, even
     static constexpr int NPAIR = F * (F - 1) / 2;
     static constexpr int NI = (NPAIR + 31) / 32; // pair entries per lane
-    static constexpr int SSTRIDE = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
+    static constexpr int SSTRIDE_DUP = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
     static constexpr int NF0 = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);
     // output rows per pass.  VAR (one sample per warp, plain stores only): 0 = NF0 rows at 144 registers, 1 = NF0 rows
     // at 128, 2 = one row at 128, 3 = nine rows at 128 (the compiler then walks the rows one after another)
-    static constexpr int NF = (VAR == 2) ? 1 : ((VAR == 3 && F % 9 == 0) ? 9 : NF0);
+    static constexpr int NF = (VAR == 2 || VAR == 5) ? 1 : ((VAR == 3 && F % 9 == 0) ? 9 : NF0);
+    // VAR >= 4: S stored ONCE and multiplied with scalar FMAs (4 = NF0 rows at 144 registers, 5 = one row at 128,
+    // 6 = NF0 rows at 128).  The shared-memory -> register path returns 128 bytes per clock per SM whatever the
+    // address pattern, so a broadcast LDS.128 costs a warp 4 clocks: 2 clocks per S value with duplicated entries
+    // (1512 clocks per sample at F = 27, 10.6 us per SM at 14 samples -- the kernel's bound at B = 2048), 1 clock
+    // per value with plain entries, at the price of twice the FMA issue slots (FFMA instead of FFMA2; same flops
+    // per clock).  Same products, same order: same bits.
+    static constexpr bool DUP = VAR < 4;
+    static constexpr int SSTRIDE = DUP ? SSTRIDE_DUP : F * FP2 + 4;
     static constexpr int WARPS = 2;
     // Registers are allocated per SM sub-partition (16384 each): a 32-thread warp at 144 or 168 registers leaves
     // room for 3 warps per sub-partition = 12 per SM = 6 CTAs, so 2048 samples at d = 128 (one sample per warp,
@@ -83,7 +91,7 @@ struct BwdGeom {
     // stamps, benchmarks/cta_timeline.py: 13 % of the CTAs enter 12 us after the first).  At 128 registers 4 warps
     // fit per sub-partition = 8 CTAs per SM and the batch is one wave.  The variants with several samples per
     // warp or the peer-store epilogue need half the warps for the same batch and keep 168.
-    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? (VAR == 0 ? 144 : 128) : 168; }
+    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? ((VAR == 0 || VAR == 4) ? 144 : 128) : 168; }
     static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4; }
     static_assert(F <= 32, "pair table covers F <= 32");
 };
@@ -139,6 +147,7 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
         const long long bb = group * G::SPW + s2;
         if (bb >= B) break;                                  // warp-uniform
         float2* Sb = reinterpret_cast<float2*>(Sw + (size_t)s2 * G::SSTRIDE);
+        float* Sb1 = Sw + (size_t)s2 * G::SSTRIDE;
         if (s2 > 0) {
             const float* gp = dOut + (size_t)bb * width + D;
 #pragma unroll
@@ -151,13 +160,23 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
         for (int i = 0; i < G::NI; ++i) {
             if (lane + 32 * i < G::NPAIR) {
                 const int hi = pv[i] >> 8, lo = pv[i] & 0xff;
-                Sb[hi * G::FP2 + lo] = make_float2(gv[i], gv[i]);
-                Sb[lo * G::FP2 + hi] = make_float2(gv[i], gv[i]);
+                if (G::DUP) {
+                    Sb[hi * G::FP2 + lo] = make_float2(gv[i], gv[i]);
+                    Sb[lo * G::FP2 + hi] = make_float2(gv[i], gv[i]);
+                } else {
+                    Sb1[hi * G::FP2 + lo] = gv[i];
+                    Sb1[lo * G::FP2 + hi] = gv[i];
+                }
             }
         }
         for (int f = lane; f < F; f += 32) {
-            Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
-            if (G::FP2 > F) Sb[f * G::FP2 + F] = make_float2(0.f, 0.f);
+            if (G::DUP) {
+                Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
+                if (G::FP2 > F) Sb[f * G::FP2 + F] = make_float2(0.f, 0.f);
+            } else {
+                Sb1[f * G::FP2 + f] = 0.f;
+                if (G::FP2 > F) Sb1[f * G::FP2 + F] = 0.f;
+            }
         }
     }
     __syncwarp();
@@ -173,16 +192,38 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
         float2 lo2[G::NF], hi2[G::NF];
 #pragma unroll
         for (int q = 0; q < G::NF; ++q) lo2[q] = hi2[q] = make_float2(0.f, 0.f);
+        if (G::DUP) {
 #pragma unroll
-        for (int jp = 0; jp < G::FP2 / 2; ++jp) {
+            for (int jp = 0; jp < G::FP2 / 2; ++jp) {
 #pragma unroll
-            for (int q = 0; q < G::NF; ++q) {
-                const float4 sv = *reinterpret_cast<const float4*>(Srow + ((f0 + q) * G::FP2 + 2 * jp) * 2);
-                lo2[q] = ffma2(make_float2(sv.x, sv.y), make_float2(t[2 * jp].x, t[2 * jp].y), lo2[q]);
-                hi2[q] = ffma2(make_float2(sv.x, sv.y), make_float2(t[2 * jp].z, t[2 * jp].w), hi2[q]);
-                if (2 * jp + 1 < F) {
-                    lo2[q] = ffma2(make_float2(sv.z, sv.w), make_float2(t[2 * jp + 1].x, t[2 * jp + 1].y), lo2[q]);
-                    hi2[q] = ffma2(make_float2(sv.z, sv.w), make_float2(t[2 * jp + 1].z, t[2 * jp + 1].w), hi2[q]);
+                for (int q = 0; q < G::NF; ++q) {
+                    const float4 sv = *reinterpret_cast<const float4*>(Srow + ((f0 + q) * G::FP2 + 2 * jp) * 2);
+                    lo2[q] = ffma2(make_float2(sv.x, sv.y), make_float2(t[2 * jp].x, t[2 * jp].y), lo2[q]);
+                    hi2[q] = ffma2(make_float2(sv.x, sv.y), make_float2(t[2 * jp].z, t[2 * jp].w), hi2[q]);
+                    if (2 * jp + 1 < F) {
+                        lo2[q] = ffma2(make_float2(sv.z, sv.w), make_float2(t[2 * jp + 1].x, t[2 * jp + 1].y), lo2[q]);
+                        hi2[q] = ffma2(make_float2(sv.z, sv.w), make_float2(t[2 * jp + 1].z, t[2 * jp + 1].w), hi2[q]);
+                    }
+                }
+            }
+        } else {
+            // S[f][j] once: one 64-bit broadcast load feeds eight scalar FMAs (the S row pitch FP2 is even, so the
+            // pair (2 jp, 2 jp + 1) is 8-byte aligned)
+#pragma unroll
+            for (int jp = 0; jp < G::FP2 / 2; ++jp) {
+#pragma unroll
+                for (int q = 0; q < G::NF; ++q) {
+                    const float2 sv = *reinterpret_cast<const float2*>(Srow + (f0 + q) * G::FP2 + 2 * jp);
+                    lo2[q].x = __fmaf_rn(sv.x, t[2 * jp].x, lo2[q].x);
+                    lo2[q].y = __fmaf_rn(sv.x, t[2 * jp].y, lo2[q].y);
+                    hi2[q].x = __fmaf_rn(sv.x, t[2 * jp].z, hi2[q].x);
+                    hi2[q].y = __fmaf_rn(sv.x, t[2 * jp].w, hi2[q].y);
+                    if (2 * jp + 1 < F) {
+                        lo2[q].x = __fmaf_rn(sv.y, t[2 * jp + 1].x, lo2[q].x);
+                        lo2[q].y = __fmaf_rn(sv.y, t[2 * jp + 1].y, lo2[q].y);
+                        hi2[q].x = __fmaf_rn(sv.y, t[2 * jp + 1].z, hi2[q].x);
+                        hi2[q].y = __fmaf_rn(sv.y, t[2 * jp + 1].w, hi2[q].y);
+                    }
                 }
             }
         }
@@ -614,6 +655,9 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
             case 1: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
             case 2: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
             case 3: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 3 : 0>(dOut, T, B, width, dT, dx, s);
+            case 4: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 4 : 0>(dOut, T, B, width, dT, dx, s);
+            case 5: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 5 : 0>(dOut, T, B, width, dT, dx, s);
+            case 6: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 6 : 0>(dOut, T, B, width, dT, dx, s);
             default: break;
         }
     }

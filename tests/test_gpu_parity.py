@@ -286,7 +286,7 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, lib_optio
         assert np.array_equal(dT_w, dT_t) and np.array_equal(dx_w, dx_t)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (1, 27, 128), (301, 27, 64), (131, 8, 16)])
 def test_interaction_backward_register_variants_bit_equal(B, F, d, variant, lib_options):
     """bwd_variant: the warp-per-sample backward at 128 registers (one wave of CTAs at B = 2048, d = 128) with 3, 1 or 9

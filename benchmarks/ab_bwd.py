@@ -2,7 +2,7 @@
 """A/B of the warp-per-sample interaction backward's variants (`bwd_variant`) in one process: cold inputs
 (nb different T / dOut per CUDA graph, together larger than L2), us per launch and fraction of the HBM peak.
 
-    python benchmarks/ab_bwd.py [--variants 0 3 4 5 6] [--B 2048 16384] [--F 27] [--D 128]
+    python benchmarks/ab_bwd.py [--variants 1 2 3 0] [--B 2048 16384] [--F 27] [--D 128]
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ from dlrm_jl_b200.interact import interaction_bwd, interaction_fwd, interaction_
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", type=int, nargs="*", default=[0, 3, 4, 5, 6])
+    ap.add_argument("--variants", type=int, nargs="*", default=[1, 2, 3, 0])
     ap.add_argument("--B", type=int, nargs="*", default=[2048, 16384])
     ap.add_argument("--F", type=int, default=27)
     ap.add_argument("--D", type=int, default=128)

@@ -73,25 +73,27 @@ struct BwdGeom {
     static constexpr int NI = (NPAIR + 31) / 32; // pair entries per lane
     static constexpr int SSTRIDE_DUP = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
     static constexpr int NF0 = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);
-    // output rows per pass.  VAR (one sample per warp, plain stores only): 0 = NF0 rows at 144 registers, 1 = NF0 rows
-    // at 128, 2 = one row at 128, 3 = nine rows at 128 (the compiler then walks the rows one after another)
-    static constexpr int NF = (VAR == 2 || VAR == 5) ? 1 : ((VAR == 3 && F % 9 == 0) ? 9 : NF0);
-    // VAR >= 4: S stored ONCE and multiplied with scalar FMAs (4 = NF0 rows at 144 registers, 5 = one row at 128,
-    // 6 = NF0 rows at 128).  The shared-memory -> register path returns 128 bytes per clock per SM whatever the
-    // address pattern, so a broadcast LDS.128 costs a warp 4 clocks: 2 clocks per S value with duplicated entries
-    // (1512 clocks per sample at F = 27, 10.6 us per SM at 14 samples -- the kernel's bound at B = 2048), 1 clock
-    // per value with plain entries, at the price of twice the FMA issue slots (FFMA instead of FFMA2; same flops
-    // per clock).  Same products, same order: same bits.
-    static constexpr bool DUP = VAR < 4;
+    // Variants of the one-sample-per-warp kernel with plain stores (d = 128; `bwd_variant` picks one, 0 = by batch):
+    //   VAR 0  FFMA2, NF0 output rows per pass, 144 registers (the round-1 kernel; also every other geometry)
+    //   VAR 1  FFMA2, nine rows per pass, 128 registers: the compiler walks the nine rows one after another, nothing
+    //          spills, and 8 CTAs fit per SM -- registers are allocated per SM sub-partition (16384 each), so a
+    //          32-thread warp at 144 or 168 registers leaves room for 3 warps per sub-partition = 6 CTAs per SM, and
+    //          2048 samples (1024 CTAs) were 888 CTAs + a second wave of 136 that started when the first ended
+    //          (per-CTA %globaltimer stamps, benchmarks/cta_timeline.py: 13 % of the CTAs entered 12 us late).
+    //          One wave: 16.2 vs 18.0 us at B = 2048, but 105 vs 100 us at B = 16384 (many waves either way).
+    //   VAR 2  S stored ONCE, scalar FMAs, NF0 rows, 144 registers.  The shared-memory -> register path returns
+    //          128 bytes per clock per SM whatever the address pattern, so a broadcast LDS.128 costs a warp 4 clocks:
+    //          2 clocks per S value with duplicated entries, 1 with plain entries, at the price of twice the FMA issue
+    //          slots (FFMA instead of FFMA2, same flops per clock): 93 vs 100 us at B = 16384 (0.82 of the HBM peak),
+    //          17.1 vs 18.0 us at B = 2048.
+    // Same products in the same order in all three: same bits (tests/test_gpu_parity.py).  Measured and not kept:
+    // FFMA2 at 128 registers with NF0 rows (84 bytes of spills) or one row per pass, scalar FMAs at 128 registers --
+    // one wave, but every CTA lives 15-20 us (profiles/r02_bwd_variants.txt).
+    static constexpr int NF = (VAR == 1 && F % 9 == 0) ? 9 : NF0;
+    static constexpr bool DUP = VAR != 2;
     static constexpr int SSTRIDE = DUP ? SSTRIDE_DUP : F * FP2 + 4;
     static constexpr int WARPS = 2;
-    // Registers are allocated per SM sub-partition (16384 each): a 32-thread warp at 144 or 168 registers leaves
-    // room for 3 warps per sub-partition = 12 per SM = 6 CTAs, so 2048 samples at d = 128 (one sample per warp,
-    // 1024 CTAs) are 888 CTAs + a second wave of 136 that starts when the first ends (per-CTA %globaltimer
-    // stamps, benchmarks/cta_timeline.py: 13 % of the CTAs enter 12 us after the first).  At 128 registers 4 warps
-    // fit per sub-partition = 8 CTAs per SM and the batch is one wave.  The variants with several samples per
-    // warp or the peer-store epilogue need half the warps for the same batch and keep 168.
-    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? ((VAR == 0 || VAR == 4) ? 144 : 128) : 168; }
+    static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? (VAR == 1 ? 128 : 144) : 168; }
     static constexpr size_t smem_bytes() { return (size_t)WARPS * SPW * SSTRIDE * 4; }
     static_assert(F <= 32, "pair table covers F <= 32");
 };
@@ -265,7 +267,7 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
 // dropped a_lo*b_lo term is 2^-20 relative).  Integer-valued inputs stay exact.  Measured against a
 // float64 Gram matrix (benchmarks/fwd_accuracy.py, B = 2048, F = 27, d = 128): relative L2 error
 // 1.2e-6 (0.15e-6 for the FP32-FMA kernels), tolerance 1e-5.
-template <int F, int D>
+template <int F, int D, int RPC = 1>
 struct MmaGeom {
     static constexpr int LDF = D + 4;                  // row pitch in floats: (D + 4) / 4 is odd, so the 8 rows x 4 k of a
                                                        // fragment load fall into 32 different banks
@@ -273,7 +275,13 @@ struct MmaGeom {
     static constexpr int RBP = 2 * MT;                 // 8-row blocks loaded per k-step
     static constexpr int NT = (F + 7) / 8;             // 8-column tiles (N)
     static constexpr int NPAIR = F * (F - 1) / 2;
-    static constexpr int SSZ = F * LDF;                // floats per sample
+    // RPC = feature rows per TMA bulk copy.  1: every row is its own copy at the bank-staggered pitch LDF.  2 or 4: RPC
+    // rows of T (contiguous in global memory) arrive as one copy and the 16-byte stagger follows every RPC rows:
+    // 1/RPC as many bulk requests per sample for an RPC-way bank conflict on the fragment loads.
+    static __host__ __device__ constexpr int roff(int r) { return (RPC == 1) ? r * LDF : (r / RPC) * (RPC * D + 4) + (r % RPC) * D; }
+    static constexpr int NCOPY = (F + RPC - 1) / RPC;
+    static constexpr int SSZ = (RPC == 1) ? F * LDF : NCOPY * (RPC * D + 4);   // floats per sample
+    static constexpr int OS_OFF = (RPC == 1) ? LDF : D;   // output staging starts behind row 0
     static constexpr int WARPS = 2;
     // The last 8-column tile of the last 16-row tile holds only the pairs among the rows past 8 * (NT - 1): three
     // of its 128 entries at F = 27 (rows 24..26), a sixth of the sample's MMAs.  When there are at most three such
@@ -288,7 +296,7 @@ struct MmaGeom {
     static constexpr size_t smem_bytes() { return (size_t)WARPS * SSZ * 4 + (size_t)WARPS * 8; }
     static_assert(F <= 32 && D % 8 == 0, "one warp covers F <= 32 rows; k-steps of 8");
     static_assert(((D + 4) / 4) % 2 == 1, "row pitch must stagger the banks");
-    static_assert(NPAIR <= (F - 1) * LDF || F == 1, "output staging must fit behind row 0");
+    static_assert(NPAIR <= SSZ - OS_OFF || F == 1, "output staging must fit behind row 0");
 };
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
@@ -299,17 +307,15 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
 
 // FP32 dot products of the tail block's row pairs over k in [kbeg, kend): lane-strided partial sums, then an
 // xor-tree over the warp; every lane returns the totals.  Pair order: (r0+1, r0), (r0+2, r0), (r0+2, r0+1).
-template <int F, int D>
+template <typename G>
 __device__ __forceinline__ void tail_pairs_fma(const float* Ts, int lane, int kbeg, int kend, float (&tp)[3]) {
-    using G = MmaGeom<F, D>;
     tp[0] = tp[1] = tp[2] = 0.f;
     if (G::TAILP == 0) return;
-    const float* r0 = Ts + G::TAIL0 * G::LDF;
     for (int k = kbeg + lane; k < kend; k += 32) {
-        const float a = r0[k], b = r0[G::LDF + k];
+        const float a = Ts[G::roff(G::TAIL0) + k], b = Ts[G::roff(G::TAIL0 + 1) + k];
         tp[0] = fmaf(b, a, tp[0]);
         if (G::TAILR == 3) {
-            const float c = r0[2 * G::LDF + k];
+            const float c = Ts[G::roff(G::TAIL0 + 2) + k];
             tp[1] = fmaf(c, a, tp[1]);
             tp[2] = fmaf(c, b, tp[2]);
         }
@@ -323,9 +329,8 @@ __device__ __forceinline__ void tail_pairs_fma(const float* Ts, int lane, int kb
 }
 
 // where the tail pairs go in the staged output row: pair (row, col) sits at row * (row - 1) / 2 + col
-template <int F, int D>
+template <typename G>
 __device__ __forceinline__ void tail_pairs_store(float* Os, int lane, const float (&tp)[3]) {
-    using G = MmaGeom<F, D>;
     if (G::TAILP == 0) return;
     constexpr int r1 = G::TAIL0 + 1, r2 = G::TAIL0 + 2;
     if (lane == 0) Os[r1 * (r1 - 1) / 2 + G::TAIL0] = tp[0];
@@ -428,7 +433,7 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
         }
     }
     float tp[3];
-    tail_pairs_fma<F, D>(Ts, lane, 0, D, tp);
+    tail_pairs_fma<G>(Ts, lane, 0, D, tp);
     __syncwarp();   // every lane is done reading rows >= 1: their space becomes the output staging
 
     float* Os = Ts + G::LDF;   // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
@@ -444,7 +449,7 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
                 if (col < row && row < F) Os[row * (row - 1) / 2 + col] = acc[i][j][e];
             }
         }
-    tail_pairs_store<F, D>(Os, lane, tp);
+    tail_pairs_store<G>(Os, lane, tp);
     __syncwarp();
 
     float* og = out + (size_t)b * width;
@@ -461,11 +466,11 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
 // active, ncu); splitting k halves that chain and doubles the warps that feed the pipe, for three
 // 64-thread barriers and 3 KB of shared traffic.  At large batches (several waves, the load of one
 // sample overlapping the MMAs of another) the one-warp kernel is the faster one and stays in charge.
-template <int F, int D>
+template <int F, int D, int RPC>
 __global__ void __launch_bounds__(64)
 interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int width,
                                   float* __restrict__ out, unsigned long long* clk) {
-    using G = MmaGeom<F, D>;
+    using G = MmaGeom<F, D, RPC>;
     extern __shared__ float4 smem4[];
     clock_in(clk, blockIdx.x);
     const int lane = threadIdx.x & 31;
@@ -481,17 +486,29 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
                      ::"r"(smem_addr(bar)), "r"((unsigned)(F * D * sizeof(float))) : "memory");
     }
     __syncthreads();
-    if (warp == 0 && lane < F) {   // one TMA bulk copy per feature row (slot 0 from x when it is handed separately)
-        const float* src = (x != nullptr && lane == 0) ? x + (size_t)b * D : T + ((size_t)b * F + lane) * D;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                     ::"r"(smem_addr(Ts + lane * G::LDF)), "l"(src), "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar))
-                     : "memory");
+    if (warp == 0 && lane < G::NCOPY) {   // one TMA bulk copy per RPC feature rows (slot 0 from x when it is handed separately)
+        const int r = lane * RPC;
+        int nrows = min(RPC, F - r);
+        const float* src = T + ((size_t)b * F + r) * D;
+        float* dst = Ts + G::roff(r);
+        if (x != nullptr && lane == 0) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(smem_addr(dst)), "l"(x + (size_t)b * D), "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar))
+                         : "memory");
+            src += D;
+            dst += D;
+            nrows -= 1;
+        }
+        if (nrows > 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(smem_addr(dst)), "l"(src), "r"((unsigned)(nrows * D * sizeof(float))), "r"(smem_addr(bar))
+                         : "memory");
     }
 
     const int g = lane >> 2, t = lane & 3;
     int roff[G::RBP];
 #pragma unroll
-    for (int rb = 0; rb < G::RBP; ++rb) roff[rb] = min(8 * rb + g, F - 1) * G::LDF + t;   // clamped rows are discarded below
+    for (int rb = 0; rb < G::RBP; ++rb) roff[rb] = G::roff(min(8 * rb + g, F - 1)) + t;   // clamped rows are discarded below
 
     float acc[G::MT][G::NT][4];
 #pragma unroll
@@ -541,13 +558,13 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
         }
     }
     float tp[3];
-    tail_pairs_fma<F, D>(Ts, lane, kbeg, kbeg + D / 2, tp);
+    tail_pairs_fma<G>(Ts, lane, kbeg, kbeg + D / 2, tp);
     __syncthreads();   // both warps are done reading rows >= 1: their space becomes scratch
 
-    float* Os = Ts + G::LDF;                  // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
+    float* Os = Ts + G::OS_OFF;               // pair m at Os[m]; row 0 (x) stays at Ts[0, D)
     float* red = Os + ((G::NPAIR + 3) & ~3);  // warp 1's partial accumulators: [tile][e][lane], then its tail pairs
     float* red_tail = red + G::MT * G::NT * 4 * 32;
-    static_assert(((G::NPAIR + 3) & ~3) + G::MT * G::NT * 4 * 32 + 4 <= (F - 1) * G::LDF, "scratch must fit behind row 0");
+    static_assert(((G::NPAIR + 3) & ~3) + G::MT * G::NT * 4 * 32 + 4 <= G::SSZ - G::OS_OFF, "scratch must fit behind row 0");
     if (warp == 1) {
 #pragma unroll
         for (int i = 0; i < G::MT; ++i)
@@ -582,7 +599,7 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
 #pragma unroll
             for (int q = 0; q < 3; ++q)
                 if (q < G::TAILP) tp[q] += red_tail[q];
-            tail_pairs_store<F, D>(Os, lane, tp);
+            tail_pairs_store<G>(Os, lane, tp);
         }
     }
     __syncthreads();
@@ -594,16 +611,25 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
     clock_out(clk, blockIdx.x);
 }
 
-template <int F, int D>
-int launch_fwd_mma_ksplit(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
-    using G = MmaGeom<F, D>;
+template <int F, int D, int RPC>
+int launch_fwd_mma_ksplit_r(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
+    using G = MmaGeom<F, D, RPC>;
     static unsigned long long attr_done = 0;
     const size_t smem = (size_t)G::SSZ * 4 + 16;
-    int rc = ensure_smem_attr((const void*)interaction_fwd_mma_ksplit_kernel<F, D>, (int)smem, &attr_done);
+    int rc = ensure_smem_attr((const void*)interaction_fwd_mma_ksplit_kernel<F, D, RPC>, (int)smem, &attr_done);
     if (rc) return rc;
-    interaction_fwd_mma_ksplit_kernel<F, D><<<(unsigned)B, 64, smem, s>>>(T, x, B, width, out, clock_slot(CLK_IFWD));
+    interaction_fwd_mma_ksplit_kernel<F, D, RPC><<<(unsigned)B, 64, smem, s>>>(T, x, B, width, out, clock_slot(CLK_IFWD));
     DLRMB_LAUNCH_CHECK();
     return DLRMB_OK;
+}
+
+template <int F, int D>
+int launch_fwd_mma_ksplit(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
+    switch (g_opt.fwd_rows_per_copy.load(std::memory_order_relaxed)) {   // feature rows per TMA bulk copy
+        case 2: return launch_fwd_mma_ksplit_r<F, D, 2>(T, x, B, width, out, s);
+        case 4: return launch_fwd_mma_ksplit_r<F, D, 4>(T, x, B, width, out, s);
+        default: return launch_fwd_mma_ksplit_r<F, D, 1>(T, x, B, width, out, s);
+    }
 }
 
 template <int F, int D>
@@ -650,16 +676,15 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
         DLRMB_LAUNCH_CHECK();
         return DLRMB_OK;
     }
-    if (G::SPW == 1) {   // one sample per warp: register-cap / rows-per-pass variants ("bwd_variant")
-        switch (g_opt.bwd_variant.load(std::memory_order_relaxed)) {
-            case 1: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
-            case 2: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
-            case 3: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 3 : 0>(dOut, T, B, width, dT, dx, s);
-            case 4: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 4 : 0>(dOut, T, B, width, dT, dx, s);
-            case 5: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 5 : 0>(dOut, T, B, width, dT, dx, s);
-            case 6: return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 6 : 0>(dOut, T, B, width, dT, dx, s);
-            default: break;
+    if (G::SPW == 1) {   // one sample per warp: see BwdGeom
+        int v = g_opt.bwd_variant.load(std::memory_order_relaxed);
+        if (v < 1 || v > 3) {   // by batch: the 128-register kernel while the batch is one wave of it (8 CTAs per SM)
+            int dev = 0;
+            cudaGetDevice(&dev);
+            v = ((long long)B <= (long long)device_sm_count(dev) * 8 * G::WARPS) ? 2 : 3;
         }
+        if (v == 2) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
+        if (v == 3) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
     }
     return launch_bwd_warp_plain<F, D, 0>(dOut, T, B, width, dT, dx, s);
 }

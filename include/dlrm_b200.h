@@ -59,9 +59,12 @@ int64_t dlrmb_launch_count(void);
  *   "interact_general" 1 = run the general tiled interaction kernels even for the specialised shapes
  *   "update_two_launches" 1 = separate fix-up launch of the sparse update at every batch size
  *   "update_tile" 4, 8, .. 32 = entries per lane group of the sparse update (0 = chosen per batch)
- *   "bwd_variant" 0..3 = warp-per-sample interaction backward (d = 128): 144 registers, or 128 registers (8 CTAs per SM)
- *                     with 3 / 1 / 9 output rows per pass
+ *   "bwd_variant" 0 = by batch size (default), 1 | 2 | 3 = warp-per-sample interaction backward (d = 128) with FFMA2 at 144
+ *                     registers / FFMA2 at 128 registers (one wave of CTAs up to 2368 samples) / S stored once + scalar FMAs
+ *   "lookup_flat" 0 | 1 | 2 = gather CTAs of the fused lookup + sort launch (P = 1) as one persistent wave over all tables:
+ *                     for batches of 1.2 to 4 waves / always / never
  *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
+ *   "fwd_rows_per_copy" 1|2|4 = feature rows per TMA bulk copy in the two-warps-per-sample forward
  *   "fwd_ksplit" 0|1|2 = tensor-core forward with one warp per sample always / two warps per sample for one-wave
  *                        batches (default) / two warps per sample always
  * Defaults are the measured-fastest configuration; unknown names return DLRMB_EINVAL. */

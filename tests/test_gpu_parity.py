@@ -286,17 +286,17 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, lib_optio
         assert np.array_equal(dT_w, dT_t) and np.array_equal(dx_w, dx_t)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 2, 3])
 @pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (1, 27, 128), (301, 27, 64), (131, 8, 16)])
 def test_interaction_backward_register_variants_bit_equal(B, F, d, variant, lib_options):
-    """bwd_variant: the warp-per-sample backward at 128 registers (one wave of CTAs at B = 2048, d = 128) with 3, 1 or 9
-    output rows per pass.  The per-output summation order does not depend on it: same bits as the 144-register
-    kernel (variant 0), which the other tests pin to the oracle and to the tiled kernel."""
+    """bwd_variant: the warp-per-sample backward with FFMA2 at 128 registers (2; one wave of CTAs at B = 2048, d = 128),
+    with S stored once and scalar FMAs (3), or chosen by batch size (0).  The per-output summation order does not
+    depend on it: same bits as the 144-register FFMA2 kernel (1), which is pinned to the oracle here."""
     from dlrm_jl_b200.interact import interaction_bwd, interaction_width
     rng = np.random.default_rng(B + F + d + variant)
     T = torch.from_numpy(rng.standard_normal((B, F, d)).astype(np.float32)).to(_dev())
     g = torch.from_numpy(rng.standard_normal((B, interaction_width(F, d))).astype(np.float32)).to(_dev())
-    lib_options("bwd_variant", 0)
+    lib_options("bwd_variant", 1)
     dx0, dT0 = interaction_bwd(g, T)
     lib_options("bwd_variant", variant)
     dx1, dT1 = interaction_bwd(g, T)
@@ -851,13 +851,18 @@ def zipf_indices(rng, rows, size, alpha):
     return (r * 2654435761 + 12345) % rows
 
 
-@pytest.mark.parametrize("B,P", [(1, 1), (5, 3), (2048, 1), (683, 3), (4096, 1), (100, 40), (4097, 1), (3000, 2)])
+@pytest.mark.parametrize("flat", [0, 1, 2])
+@pytest.mark.parametrize("B,P", [(1, 1), (5, 3), (2048, 1), (683, 3), (4096, 1), (100, 40), (4097, 1), (3000, 2), (333, 1)])
 @pytest.mark.parametrize("dtype,base", [(np.int32, 0), (np.int64, 1)])
-def test_lookup_sort_fused_launch_equals_separate_launches(B, P, dtype, base):
+def test_lookup_sort_fused_launch_equals_separate_launches(B, P, dtype, base, flat, lib_options):
     """dlrmb_embedding_fwd_sort (the sort rides in extra CTAs of the lookup launch for B*P <= 4096, two
     launches above) == dlrmb_embedding_fwd + dlrmb_embedding_sort: pooled rows and the exported
-    dedup, bit for bit, and against the oracle."""
+    dedup, bit for bit, and against the oracle.  `lookup_flat`: the gather CTAs of the fused launch as one
+    persistent wave over all tables (1 = always, 0 = by batch size, 2 = never)."""
     from dlrm_jl_b200.embedding import EmbeddingTables
+    if flat != 0 and (P != 1 or B * P > 4096):
+        pytest.skip("the persistent gather only exists in the fused P = 1 launch")
+    lib_options("lookup_flat", flat)
     rng = np.random.default_rng(B * 7 + P)
     rows, D = [3, 1000, 40_000_000, 513, 70000], 32
     L = B * P
@@ -1153,6 +1158,31 @@ def test_interaction_forward_one_and_two_warps_per_sample(B, F, d, mode, lib_opt
         assert np.all(out[:, d + F * (F - 1) // 2:] == 0)
     Ti = rng.integers(-4, 5, size=(64, F, d)).astype(np.float32)
     assert np.array_equal(interaction_fwd(torch.from_numpy(Ti).to(_dev())).cpu().numpy(), O.interaction_fwd(Ti))
+
+
+@pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (1, 27, 128), (301, 27, 64)])
+@pytest.mark.parametrize("rpc", [2, 4])
+def test_interaction_forward_rows_per_bulk_copy_same_bits(B, F, d, rpc, lib_options):
+    """fwd_rows_per_copy: the two-warps-per-sample forward fetches 2 or 4 feature rows per TMA bulk copy (the bank
+    stagger then follows every 2 / 4 rows).  Only the shared-memory layout changes: same bits as one row per copy,
+    with and without the fused fast_vcat."""
+    from dlrm_jl_b200.interact import interaction_fwd
+    rng = np.random.default_rng(B + F + d + rpc)
+    T = rng.standard_normal((B, F, d)).astype(np.float32)
+    x = torch.from_numpy(T[:, 0].copy()).to(_dev())
+    outs = {}
+    for r in (1, rpc):
+        lib_options("fwd_ksplit", 2)
+        lib_options("fwd_rows_per_copy", r)
+        Tz = T.copy()
+        Tz[:, 0] = 0
+        Tzd = torch.from_numpy(Tz).to(_dev())
+        a = interaction_fwd(torch.from_numpy(T).to(_dev()), pad_to_mul=16)
+        b = interaction_fwd(Tzd, x, pad_to_mul=16)
+        assert torch.equal(a, b) and np.array_equal(Tzd.cpu().numpy(), T)
+        outs[r] = a.cpu().numpy()
+    assert np.array_equal(outs[1], outs[rpc])
+    assert O.rel_err(outs[rpc], O.interaction_fwd(T, 16)) < FWD_RTOL
 
 
 @pytest.mark.parametrize("tile", [4, 12, 20, 28, 32])

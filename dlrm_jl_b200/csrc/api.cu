@@ -126,7 +126,6 @@ static std::atomic<int>* find_option(const char* name) {
     if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
     if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
     if (!strcmp(name, "fwd_ksplit")) return &g_opt.fwd_ksplit;
-    if (!strcmp(name, "fwd_rows_per_copy")) return &g_opt.fwd_rows_per_copy;
     return nullptr;
 }
 

@@ -144,7 +144,6 @@ struct Options {
                                               // 2 = FFMA2 at 128 registers (8 CTAs per SM), 3 = S stored once + scalar FMAs
     std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
     std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
-    std::atomic<int> fwd_rows_per_copy{1};    // two-warps-per-sample forward: feature rows per TMA bulk copy (1, 2 or 4)
     std::atomic<int> fwd_ksplit{1};           // tensor-core forward: 0 = one warp per sample always, 1 = two warps per sample for
                                               // one-wave batches (default), 2 = two warps per sample always
 };

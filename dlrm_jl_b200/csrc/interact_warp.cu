@@ -253,6 +253,128 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
     clock_out(clk, blockIdx.x);
 }
 
+// Output-stationary backward for one sample per warp (d = 128): the warp keeps the accumulators of HALF of the
+// output rows (14 of 27: 56 registers per lane) and streams the rows of T through a ring of R registers, consuming
+// row j (one FMA per output row and column, j ascending -- the order of the kernels above, hence the same bits)
+// while rows j + 1 .. j + R are in flight.  Two passes over T, the second from L2.  What this buys over
+// interaction_bwd_warp_kernel, whose warps hold ALL of T (108 registers) before the first FMA:
+//   * 128 registers: 4 warps per SM sub-partition, so 2048 samples are ONE wave of CTAs (8 per SM);
+//   * the FMAs of a pass run while its rows arrive, instead of after the last of the 27 loads has landed; the
+//     stores of the first half leave while the second pass computes.
+// S is the duplicated layout of the kernel above read by ROW j (S is symmetric): one broadcast LDS.128 gives the
+// (s, s) pairs of two output rows.
+template <int F, int D, int F0, int NFH, bool REFILL, int R>
+__device__ __forceinline__ void bwd_stream_pass(const float4* __restrict__ Tp, float4 (&tq)[R], const float* Srow,
+                                                float2 (&lo)[NFH], float2 (&hi)[NFH]) {
+    using G = BwdGeom<F, D>;
+    static_assert(F % R == 0, "the ring turns a whole number of times per pass");
+#pragma unroll
+    for (int q = 0; q < NFH; ++q) lo[q] = hi[q] = make_float2(0.f, 0.f);
+    // a real loop over blocks of R rows: the compiler keeps the loads of a block inside the block, so at most R rows
+    // (+ the one being consumed) are live
+#pragma unroll 1
+    for (int jb = 0; jb < F; jb += R) {
+        const float* Sj = Srow + (size_t)jb * G::FP2 * 2;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 tj = tq[r];
+            int nxt = jb + r + R;                     // the row this slot holds next; past the end = next pass, row 0 on
+            if (REFILL) {
+                if (nxt >= F) nxt -= F;
+                tq[r] = __ldg(Tp + (size_t)nxt * G::LPS);
+            } else if (nxt < F) {
+                tq[r] = __ldg(Tp + (size_t)nxt * G::LPS);
+            }
+#pragma unroll
+            for (int q = 0; q < NFH / 2; ++q) {
+                const int f = F0 + 2 * q;
+                if (f >= F) continue;
+                const float4 sv = *reinterpret_cast<const float4*>(Sj + (r * G::FP2 + f) * 2);
+                lo[2 * q] = ffma2(make_float2(sv.x, sv.y), make_float2(tj.x, tj.y), lo[2 * q]);
+                hi[2 * q] = ffma2(make_float2(sv.x, sv.y), make_float2(tj.z, tj.w), hi[2 * q]);
+                if (f + 1 < F) {
+                    lo[2 * q + 1] = ffma2(make_float2(sv.z, sv.w), make_float2(tj.x, tj.y), lo[2 * q + 1]);
+                    hi[2 * q + 1] = ffma2(make_float2(sv.z, sv.w), make_float2(tj.z, tj.w), hi[2 * q + 1]);
+                }
+            }
+        }
+    }
+}
+
+template <int F, int D>
+__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32, 8)
+interaction_bwd_stream_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
+                              float* __restrict__ dT, float* __restrict__ dx, unsigned long long* clk) {
+    using G = BwdGeom<F, D>;
+    static_assert(G::SPW == 1, "one sample per warp");
+    constexpr int R = 9;                      // rows of T in flight per lane (F = 27: the ring turns three times per pass)
+    constexpr int H = G::FP2 / 2;             // output rows per pass (the second pass may end in the padding row)
+    static_assert(H % 2 == 0 && F % R == 0, "two output rows per S load; whole turns of the ring");
+    extern __shared__ float4 smem4[];
+    clock_in(clk, blockIdx.x);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * G::WARPS + warp;
+    if (b >= B) {                             // warp-uniform
+        clock_out(clk, blockIdx.x);
+        return;
+    }
+    float* Sw = reinterpret_cast<float*>(smem4) + (size_t)warp * G::SSTRIDE;
+    const float* gb = dOut + (size_t)b * width;
+
+    unsigned short pv[G::NI];
+    float gv[G::NI];
+#pragma unroll
+    for (int i = 0; i < G::NI; ++i) {
+        const int m = lane + 32 * i;
+        pv[i] = kPairTable.v[m < G::NPAIR ? m : 0];
+        gv[i] = (m < G::NPAIR) ? __ldg(gb + D + m) : 0.f;
+    }
+    const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)b * F * G::LPS + lane;
+    float4 tq[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) tq[r] = __ldg(Tp + (size_t)r * G::LPS);
+
+    {   // duplicated S: Sd[j][f] = (S[j][f], S[j][f]), zero diagonal / padding
+        float2* Sb = reinterpret_cast<float2*>(Sw);
+#pragma unroll
+        for (int i = 0; i < G::NI; ++i) {
+            if (lane + 32 * i < G::NPAIR) {
+                const int hi = pv[i] >> 8, lo = pv[i] & 0xff;
+                Sb[hi * G::FP2 + lo] = make_float2(gv[i], gv[i]);
+                Sb[lo * G::FP2 + hi] = make_float2(gv[i], gv[i]);
+            }
+        }
+        for (int f = lane; f < F; f += 32) {
+            Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
+            if (G::FP2 > F) Sb[f * G::FP2 + F] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncwarp();
+
+    float2 lo[H], hi[H];
+    float4* dTp = reinterpret_cast<float4*>(dT) + (size_t)b * F * G::LPS + lane;
+    bwd_stream_pass<F, D, 0, H, true, R>(Tp, tq, Sw, lo, hi);
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+        const float4 r = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
+        dTp[(size_t)q * G::LPS] = r;
+        if (q == 0) {
+            const float* g = gb + 4 * lane;    // row width is odd in general: 4-byte aligned only
+            reinterpret_cast<float4*>(dx)[(size_t)b * G::LPS + lane] =
+                make_float4(__fadd_rn(__ldg(g), r.x), __fadd_rn(__ldg(g + 1), r.y),
+                            __fadd_rn(__ldg(g + 2), r.z), __fadd_rn(__ldg(g + 3), r.w));
+        }
+    }
+    bwd_stream_pass<F, D, H, H, false, R>(Tp, tq, Sw, lo, hi);
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+        if (H + q >= F) continue;
+        dTp[(size_t)(H + q) * G::LPS] = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
+    }
+    clock_out(clk, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------
 // forward on the tensor cores: 3xTF32 (error-compensated) warp-level MMA
 // ------------------------------------------------------------------------------------------
@@ -267,7 +389,7 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
 // dropped a_lo*b_lo term is 2^-20 relative).  Integer-valued inputs stay exact.  Measured against a
 // float64 Gram matrix (benchmarks/fwd_accuracy.py, B = 2048, F = 27, d = 128): relative L2 error
 // 1.2e-6 (0.15e-6 for the FP32-FMA kernels), tolerance 1e-5.
-template <int F, int D, int RPC = 1>
+template <int F, int D>
 struct MmaGeom {
     static constexpr int LDF = D + 4;                  // row pitch in floats: (D + 4) / 4 is odd, so the 8 rows x 4 k of a
                                                        // fragment load fall into 32 different banks
@@ -275,13 +397,11 @@ struct MmaGeom {
     static constexpr int RBP = 2 * MT;                 // 8-row blocks loaded per k-step
     static constexpr int NT = (F + 7) / 8;             // 8-column tiles (N)
     static constexpr int NPAIR = F * (F - 1) / 2;
-    // RPC = feature rows per TMA bulk copy.  1: every row is its own copy at the bank-staggered pitch LDF.  2 or 4: RPC
-    // rows of T (contiguous in global memory) arrive as one copy and the 16-byte stagger follows every RPC rows:
-    // 1/RPC as many bulk requests per sample for an RPC-way bank conflict on the fragment loads.
-    static __host__ __device__ constexpr int roff(int r) { return (RPC == 1) ? r * LDF : (r / RPC) * (RPC * D + 4) + (r % RPC) * D; }
-    static constexpr int NCOPY = (F + RPC - 1) / RPC;
-    static constexpr int SSZ = (RPC == 1) ? F * LDF : NCOPY * (RPC * D + 4);   // floats per sample
-    static constexpr int OS_OFF = (RPC == 1) ? LDF : D;   // output staging starts behind row 0
+    // (Measured and not kept: 2 or 4 feature rows per TMA bulk copy with the bank stagger after every 2 / 4 rows --
+    // 12.0 us either way at B = 2048, so the forward is not bound by the number of bulk requests.)
+    static __host__ __device__ constexpr int roff(int r) { return r * LDF; }
+    static constexpr int SSZ = F * LDF;                // floats per sample
+    static constexpr int OS_OFF = LDF;                 // output staging starts behind row 0
     static constexpr int WARPS = 2;
     // The last 8-column tile of the last 16-row tile holds only the pairs among the rows past 8 * (NT - 1): three
     // of its 128 entries at F = 27 (rows 24..26), a sixth of the sample's MMAs.  When there are at most three such
@@ -466,11 +586,11 @@ interaction_fwd_mma_kernel(float* __restrict__ T, const float* __restrict__ x, i
 // active, ncu); splitting k halves that chain and doubles the warps that feed the pipe, for three
 // 64-thread barriers and 3 KB of shared traffic.  At large batches (several waves, the load of one
 // sample overlapping the MMAs of another) the one-warp kernel is the faster one and stays in charge.
-template <int F, int D, int RPC>
+template <int F, int D>
 __global__ void __launch_bounds__(64)
 interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict__ x, int B, int width,
                                   float* __restrict__ out, unsigned long long* clk) {
-    using G = MmaGeom<F, D, RPC>;
+    using G = MmaGeom<F, D>;
     extern __shared__ float4 smem4[];
     clock_in(clk, blockIdx.x);
     const int lane = threadIdx.x & 31;
@@ -486,23 +606,11 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
                      ::"r"(smem_addr(bar)), "r"((unsigned)(F * D * sizeof(float))) : "memory");
     }
     __syncthreads();
-    if (warp == 0 && lane < G::NCOPY) {   // one TMA bulk copy per RPC feature rows (slot 0 from x when it is handed separately)
-        const int r = lane * RPC;
-        int nrows = min(RPC, F - r);
-        const float* src = T + ((size_t)b * F + r) * D;
-        float* dst = Ts + G::roff(r);
-        if (x != nullptr && lane == 0) {
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                         ::"r"(smem_addr(dst)), "l"(x + (size_t)b * D), "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar))
-                         : "memory");
-            src += D;
-            dst += D;
-            nrows -= 1;
-        }
-        if (nrows > 0)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                         ::"r"(smem_addr(dst)), "l"(src), "r"((unsigned)(nrows * D * sizeof(float))), "r"(smem_addr(bar))
-                         : "memory");
+    if (warp == 0 && lane < F) {   // one TMA bulk copy per feature row (slot 0 from x when it is handed separately)
+        const float* src = (x != nullptr && lane == 0) ? x + (size_t)b * D : T + ((size_t)b * F + lane) * D;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(smem_addr(Ts + lane * G::LDF)), "l"(src), "r"((unsigned)(D * sizeof(float))), "r"(smem_addr(bar))
+                     : "memory");
     }
 
     const int g = lane >> 2, t = lane & 3;
@@ -611,25 +719,16 @@ interaction_fwd_mma_ksplit_kernel(float* __restrict__ T, const float* __restrict
     clock_out(clk, blockIdx.x);
 }
 
-template <int F, int D, int RPC>
-int launch_fwd_mma_ksplit_r(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
-    using G = MmaGeom<F, D, RPC>;
-    static unsigned long long attr_done = 0;
-    const size_t smem = (size_t)G::SSZ * 4 + 16;
-    int rc = ensure_smem_attr((const void*)interaction_fwd_mma_ksplit_kernel<F, D, RPC>, (int)smem, &attr_done);
-    if (rc) return rc;
-    interaction_fwd_mma_ksplit_kernel<F, D, RPC><<<(unsigned)B, 64, smem, s>>>(T, x, B, width, out, clock_slot(CLK_IFWD));
-    DLRMB_LAUNCH_CHECK();
-    return DLRMB_OK;
-}
-
 template <int F, int D>
 int launch_fwd_mma_ksplit(float* T, const float* x, int B, int width, float* out, cudaStream_t s) {
-    switch (g_opt.fwd_rows_per_copy.load(std::memory_order_relaxed)) {   // feature rows per TMA bulk copy
-        case 2: return launch_fwd_mma_ksplit_r<F, D, 2>(T, x, B, width, out, s);
-        case 4: return launch_fwd_mma_ksplit_r<F, D, 4>(T, x, B, width, out, s);
-        default: return launch_fwd_mma_ksplit_r<F, D, 1>(T, x, B, width, out, s);
-    }
+    using G = MmaGeom<F, D>;
+    static unsigned long long attr_done = 0;
+    const size_t smem = (size_t)G::SSZ * 4 + 16;
+    int rc = ensure_smem_attr((const void*)interaction_fwd_mma_ksplit_kernel<F, D>, (int)smem, &attr_done);
+    if (rc) return rc;
+    interaction_fwd_mma_ksplit_kernel<F, D><<<(unsigned)B, 64, smem, s>>>(T, x, B, width, out, clock_slot(CLK_IFWD));
+    DLRMB_LAUNCH_CHECK();
+    return DLRMB_OK;
 }
 
 template <int F, int D>
@@ -660,6 +759,164 @@ int launch_bwd_warp_plain(const float* dOut, const float* T, int B, int width, f
     return DLRMB_OK;
 }
 
+// The same streaming backward with the ring of T rows in SHARED memory, filled by asynchronous copies
+// (cp.async: global -> shared without passing through registers).  Every lane copies and later reads back only its
+// own 16-byte column slice, so the only synchronisation is the lane's own cp.async group count.  Registers hold
+// the accumulators and little else: nothing spills at 128 registers, and the ring can be RS rows deep.
+template <int F, int D, int RS>
+struct BwdRingGeom {
+    using G = BwdGeom<F, D>;
+    static constexpr int RING = RS * D;                               // floats per warp
+    static constexpr int PER_WARP = G::SSTRIDE_DUP + RING;            // S (duplicated) + ring; SSTRIDE_DUP * 4 is a multiple of 16
+    static constexpr size_t smem_bytes() { return (size_t)G::WARPS * PER_WARP * 4; }
+};
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int F, int D, int F0, int NFH, int RS, int SLOT0, bool REFILL>
+__device__ __forceinline__ void bwd_ring_pass(const float4* __restrict__ Tp, float* ring, const float* Srow, int lane,
+                                              float2 (&lo)[NFH], float2 (&hi)[NFH]) {
+    using G = BwdGeom<F, D>;
+#pragma unroll
+    for (int q = 0; q < NFH; ++q) lo[q] = hi[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int slot = (SLOT0 + j) % RS;
+        cp_async_wait<RS - 1>();                       // all but the RS - 1 youngest groups have landed: row j is here
+        const float4 tj = *reinterpret_cast<const float4*>(ring + slot * D + 4 * lane);
+#pragma unroll
+        for (int q = 0; q < NFH / 2; ++q) {
+            const int f = F0 + 2 * q;
+            if (f >= F) continue;
+            const float4 sv = *reinterpret_cast<const float4*>(Srow + (j * G::FP2 + f) * 2);
+            lo[2 * q] = ffma2(make_float2(sv.x, sv.y), make_float2(tj.x, tj.y), lo[2 * q]);
+            hi[2 * q] = ffma2(make_float2(sv.x, sv.y), make_float2(tj.z, tj.w), hi[2 * q]);
+            if (f + 1 < F) {
+                lo[2 * q + 1] = ffma2(make_float2(sv.z, sv.w), make_float2(tj.x, tj.y), lo[2 * q + 1]);
+                hi[2 * q + 1] = ffma2(make_float2(sv.z, sv.w), make_float2(tj.z, tj.w), hi[2 * q + 1]);
+            }
+        }
+        // the slot is free (tj is in registers and consumed): the row it holds next; past the end = the next pass
+        if (j + RS < F) cp_async16(ring + slot * D + 4 * lane, Tp + (size_t)(j + RS) * G::LPS);
+        else if (REFILL) cp_async16(ring + slot * D + 4 * lane, Tp + (size_t)(j + RS - F) * G::LPS);
+        cp_async_commit();                             // one group per row consumed, empty at the end of the last pass
+    }
+}
+
+template <int F, int D, int RS>
+__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32, 8)
+interaction_bwd_ring_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
+                            float* __restrict__ dT, float* __restrict__ dx, unsigned long long* clk) {
+    using G = BwdGeom<F, D>;
+    using RG = BwdRingGeom<F, D, RS>;
+    static_assert(G::SPW == 1 && RS <= F, "one sample per warp; the ring is primed with RS rows");
+    constexpr int H = G::FP2 / 2;
+    static_assert(H % 2 == 0, "two output rows per S load");
+    extern __shared__ float4 smem4[];
+    clock_in(clk, blockIdx.x);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * G::WARPS + warp;
+    if (b >= B) {                             // warp-uniform
+        clock_out(clk, blockIdx.x);
+        return;
+    }
+    float* Sw = reinterpret_cast<float*>(smem4) + (size_t)warp * RG::PER_WARP;
+    float* ring = Sw + G::SSTRIDE_DUP;
+    const float* gb = dOut + (size_t)b * width;
+    const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)b * F * G::LPS + lane;
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {            // prime the ring: RS rows in flight before anything else
+        cp_async16(ring + r * D + 4 * lane, Tp + (size_t)r * G::LPS);
+        cp_async_commit();
+    }
+    {   // duplicated S: Sd[j][f] = (S[j][f], S[j][f]), zero diagonal / padding
+        float2* Sb = reinterpret_cast<float2*>(Sw);
+#pragma unroll
+        for (int i = 0; i < G::NI; ++i) {
+            const int m = lane + 32 * i;
+            if (m < G::NPAIR) {
+                const unsigned short p = kPairTable.v[m];
+                const float gvv = __ldg(gb + D + m);
+                const int hi = p >> 8, lo = p & 0xff;
+                Sb[hi * G::FP2 + lo] = make_float2(gvv, gvv);
+                Sb[lo * G::FP2 + hi] = make_float2(gvv, gvv);
+            }
+        }
+        for (int f = lane; f < F; f += 32) {
+            Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
+            if (G::FP2 > F) Sb[f * G::FP2 + F] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncwarp();
+
+    float2 lo[H], hi[H];
+    float4* dTp = reinterpret_cast<float4*>(dT) + (size_t)b * F * G::LPS + lane;
+    bwd_ring_pass<F, D, 0, H, RS, 0, true>(Tp, ring, Sw, lane, lo, hi);
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+        const float4 r = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
+        dTp[(size_t)q * G::LPS] = r;
+        if (q == 0) {
+            const float* g = gb + 4 * lane;    // row width is odd in general: 4-byte aligned only
+            reinterpret_cast<float4*>(dx)[(size_t)b * G::LPS + lane] =
+                make_float4(__fadd_rn(__ldg(g), r.x), __fadd_rn(__ldg(g + 1), r.y),
+                            __fadd_rn(__ldg(g + 2), r.z), __fadd_rn(__ldg(g + 3), r.w));
+        }
+    }
+    bwd_ring_pass<F, D, H, H, RS, F % RS, false>(Tp, ring, Sw, lane, lo, hi);
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+        if (H + q >= F) continue;
+        dTp[(size_t)(H + q) * G::LPS] = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
+    }
+    clock_out(clk, blockIdx.x);
+}
+
+template <int F, int D>
+int launch_bwd_ring(const float* dOut, const float* T, int B, int width, float* dT, float* dx, cudaStream_t s) {
+    using G = BwdGeom<F, D>;
+    if constexpr (G::SPW == 1 && F >= 12) {
+        constexpr int RS = 12;
+        static unsigned long long attr_done = 0;
+        const size_t smem = BwdRingGeom<F, D, RS>::smem_bytes();
+        const long long grid = ((long long)B + G::WARPS - 1) / G::WARPS;
+        int rc = ensure_smem_attr((const void*)interaction_bwd_ring_kernel<F, D, RS>, (int)smem, &attr_done);
+        if (rc) return rc;
+        interaction_bwd_ring_kernel<F, D, RS><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(dOut, T, B, width, dT, dx,
+                                                                                         clock_slot(CLK_IBWD));
+        DLRMB_LAUNCH_CHECK();
+        return DLRMB_OK;
+    } else {
+        return -1;
+    }
+}
+
+template <int F, int D>
+int launch_bwd_stream(const float* dOut, const float* T, int B, int width, float* dT, float* dx, cudaStream_t s) {
+    using G = BwdGeom<F, D>;
+    if constexpr (G::SPW == 1 && F % 9 == 0) {
+        static unsigned long long attr_done = 0;
+        const size_t smem = G::smem_bytes();
+        const long long grid = ((long long)B + G::WARPS - 1) / G::WARPS;
+        int rc = ensure_smem_attr((const void*)interaction_bwd_stream_kernel<F, D>, (int)smem, &attr_done);
+        if (rc) return rc;
+        interaction_bwd_stream_kernel<F, D><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(dOut, T, B, width, dT, dx,
+                                                                                       clock_slot(CLK_IBWD));
+        DLRMB_LAUNCH_CHECK();
+        return DLRMB_OK;
+    } else {
+        return -1;
+    }
+}
+
 template <int F, int D>
 int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
                     const void* dests, long long sample_offset, cudaStream_t s) {
@@ -678,11 +935,13 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
     }
     if (G::SPW == 1) {   // one sample per warp: see BwdGeom
         int v = g_opt.bwd_variant.load(std::memory_order_relaxed);
-        if (v < 1 || v > 3) {   // by batch: the 128-register kernel while the batch is one wave of it (8 CTAs per SM)
+        if (v < 1 || v > 5) {   // by batch: the 128-register kernel while the batch is one wave of it (8 CTAs per SM)
             int dev = 0;
             cudaGetDevice(&dev);
             v = ((long long)B <= (long long)device_sm_count(dev) * 8 * G::WARPS) ? 2 : 3;
         }
+        if (v == 4) return launch_bwd_stream<F, D>(dOut, T, B, width, dT, dx, s);
+        if (v == 5) return launch_bwd_ring<F, D>(dOut, T, B, width, dT, dx, s);
         if (v == 2) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
         if (v == 3) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
     }

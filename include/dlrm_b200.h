@@ -64,7 +64,6 @@ int64_t dlrmb_launch_count(void);
  *   "lookup_flat" 0 | 1 | 2 = gather CTAs of the fused lookup + sort launch (P = 1) as one persistent wave over all tables:
  *                     for batches of 1.2 to 4 waves / always / never
  *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
- *   "fwd_rows_per_copy" 1|2|4 = feature rows per TMA bulk copy in the two-warps-per-sample forward
  *   "fwd_ksplit" 0|1|2 = tensor-core forward with one warp per sample always / two warps per sample for one-wave
  *                        batches (default) / two warps per sample always
  * Defaults are the measured-fastest configuration; unknown names return DLRMB_EINVAL. */

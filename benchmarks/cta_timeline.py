@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--B", type=int, default=2048)
     ap.add_argument("--reps", type=int, default=8)
     ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--bwd-variants", type=int, nargs="*", default=None, help="run the backward once per listed bwd_variant")
     a = ap.parse_args()
     for kv in a.opt:
         k, v = kv.split("=")
@@ -129,7 +130,14 @@ def main():
 
     report("update", stamped(lambda i: t.update_sorted(dTs[i], 1, 0.0), 2, upd_prep), upd_extra)
     report("interaction_fwd", stamped(lambda i: interaction_fwd(Ts[i]), 4))
-    report("interaction_bwd", stamped(lambda i: interaction_bwd(gs[i], Ts[i]), 5))
+    if a.bwd_variants:
+        for v in a.bwd_variants:
+            _lib.set_option("bwd_variant", v)
+            interaction_bwd(gs[0], Ts[0])
+            report(f"interaction_bwd(variant {v})", stamped(lambda i: interaction_bwd(gs[i], Ts[i]), 5))
+        _lib.set_option("bwd_variant", 0)
+    else:
+        report("interaction_bwd", stamped(lambda i: interaction_bwd(gs[i], Ts[i]), 5))
     t.close()
 
 

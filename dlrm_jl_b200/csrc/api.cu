@@ -122,7 +122,6 @@ static std::atomic<int>* find_option(const char* name) {
     if (!strcmp(name, "update_two_launches")) return &g_opt.update_two_launches;
     if (!strcmp(name, "update_tile")) return &g_opt.update_tile;
     if (!strcmp(name, "bwd_variant")) return &g_opt.bwd_variant;
-    if (!strcmp(name, "lookup_flat")) return &g_opt.lookup_flat;
     if (!strcmp(name, "fwd_tb")) return &g_opt.fwd_tb;
     if (!strcmp(name, "fwd_ks")) return &g_opt.fwd_ks;
     if (!strcmp(name, "fwd_ksplit")) return &g_opt.fwd_ksplit;

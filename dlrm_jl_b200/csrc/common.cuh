@@ -138,10 +138,9 @@ struct Options {
     std::atomic<int> interact_general{0};     // 1: general tiled interaction kernels even for the specialised shapes
     std::atomic<int> update_two_launches{0};  // 1: separate fix-up launch at every batch size
     std::atomic<int> update_tile{0};          // 4, 8, .. 32 entries per lane group (0 = chosen per batch)
-    std::atomic<int> lookup_flat{2};          // fused lookup + sort launch, P = 1: persistent one-wave gather 0 = for batches of 1.2 to 4
-                                              // waves, 1 = always, 2 = never
-    std::atomic<int> bwd_variant{0};          // warp-per-sample backward at d = 128: 0 = by batch size, 1 = FFMA2 at 144 registers,
-                                              // 2 = FFMA2 at 128 registers (8 CTAs per SM), 3 = S stored once + scalar FMAs
+    std::atomic<int> bwd_variant{0};          // one-sample-per-warp backward (d = 128): 0 = by batch size, 1 = FFMA2 at 144 registers,
+                                              // 2 = FFMA2 at 128 registers, 3 = S stored once at 144, 5 / 6 = streaming kernels (T
+                                              // rows through a cp.async ring; 6 = S stored once, row-paired FFMA2)
     std::atomic<int> fwd_tb{0};               // tiled forward register block 3 | 6 | 9 (0 = default)
     std::atomic<int> fwd_ks{0};               // tiled forward k-split log2
     std::atomic<int> fwd_ksplit{1};           // tensor-core forward: 0 = one warp per sample always, 1 = two warps per sample for

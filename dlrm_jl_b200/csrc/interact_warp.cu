@@ -209,22 +209,19 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
                 }
             }
         } else {
-            // S[f][j] once: one 64-bit broadcast load feeds eight scalar FMAs (the S row pitch FP2 is even, so the
-            // pair (2 jp, 2 jp + 1) is 8-byte aligned)
+            // S[f][j] once: FFMA2 takes a scalar operand for both halves (SASS `FFMA2 Rd, Ra.F32, Rb.F32x2, Rc`; ptxas
+            // emits it for the pair (s, s)), so a 64-bit broadcast load of two S values feeds four FFMA2 and nothing in
+            // shared memory is duplicated (the S row pitch FP2 is even: the pair (2 jp, 2 jp + 1) is 8-byte aligned)
 #pragma unroll
             for (int jp = 0; jp < G::FP2 / 2; ++jp) {
 #pragma unroll
                 for (int q = 0; q < G::NF; ++q) {
                     const float2 sv = *reinterpret_cast<const float2*>(Srow + (f0 + q) * G::FP2 + 2 * jp);
-                    lo2[q].x = __fmaf_rn(sv.x, t[2 * jp].x, lo2[q].x);
-                    lo2[q].y = __fmaf_rn(sv.x, t[2 * jp].y, lo2[q].y);
-                    hi2[q].x = __fmaf_rn(sv.x, t[2 * jp].z, hi2[q].x);
-                    hi2[q].y = __fmaf_rn(sv.x, t[2 * jp].w, hi2[q].y);
+                    lo2[q] = ffma2(make_float2(sv.x, sv.x), make_float2(t[2 * jp].x, t[2 * jp].y), lo2[q]);
+                    hi2[q] = ffma2(make_float2(sv.x, sv.x), make_float2(t[2 * jp].z, t[2 * jp].w), hi2[q]);
                     if (2 * jp + 1 < F) {
-                        lo2[q].x = __fmaf_rn(sv.y, t[2 * jp + 1].x, lo2[q].x);
-                        lo2[q].y = __fmaf_rn(sv.y, t[2 * jp + 1].y, lo2[q].y);
-                        hi2[q].x = __fmaf_rn(sv.y, t[2 * jp + 1].z, hi2[q].x);
-                        hi2[q].y = __fmaf_rn(sv.y, t[2 * jp + 1].w, hi2[q].y);
+                        lo2[q] = ffma2(make_float2(sv.y, sv.y), make_float2(t[2 * jp + 1].x, t[2 * jp + 1].y), lo2[q]);
+                        hi2[q] = ffma2(make_float2(sv.y, sv.y), make_float2(t[2 * jp + 1].z, t[2 * jp + 1].w), hi2[q]);
                     }
                 }
             }
@@ -249,128 +246,6 @@ interaction_bwd_warp_kernel(const float* __restrict__ dOut, const float* __restr
                                 __fadd_rn(__ldg(g + 2), r.z), __fadd_rn(__ldg(g + 3), r.w));
             }
         }
-    }
-    clock_out(clk, blockIdx.x);
-}
-
-// Output-stationary backward for one sample per warp (d = 128): the warp keeps the accumulators of HALF of the
-// output rows (14 of 27: 56 registers per lane) and streams the rows of T through a ring of R registers, consuming
-// row j (one FMA per output row and column, j ascending -- the order of the kernels above, hence the same bits)
-// while rows j + 1 .. j + R are in flight.  Two passes over T, the second from L2.  What this buys over
-// interaction_bwd_warp_kernel, whose warps hold ALL of T (108 registers) before the first FMA:
-//   * 128 registers: 4 warps per SM sub-partition, so 2048 samples are ONE wave of CTAs (8 per SM);
-//   * the FMAs of a pass run while its rows arrive, instead of after the last of the 27 loads has landed; the
-//     stores of the first half leave while the second pass computes.
-// S is the duplicated layout of the kernel above read by ROW j (S is symmetric): one broadcast LDS.128 gives the
-// (s, s) pairs of two output rows.
-template <int F, int D, int F0, int NFH, bool REFILL, int R>
-__device__ __forceinline__ void bwd_stream_pass(const float4* __restrict__ Tp, float4 (&tq)[R], const float* Srow,
-                                                float2 (&lo)[NFH], float2 (&hi)[NFH]) {
-    using G = BwdGeom<F, D>;
-    static_assert(F % R == 0, "the ring turns a whole number of times per pass");
-#pragma unroll
-    for (int q = 0; q < NFH; ++q) lo[q] = hi[q] = make_float2(0.f, 0.f);
-    // a real loop over blocks of R rows: the compiler keeps the loads of a block inside the block, so at most R rows
-    // (+ the one being consumed) are live
-#pragma unroll 1
-    for (int jb = 0; jb < F; jb += R) {
-        const float* Sj = Srow + (size_t)jb * G::FP2 * 2;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float4 tj = tq[r];
-            int nxt = jb + r + R;                     // the row this slot holds next; past the end = next pass, row 0 on
-            if (REFILL) {
-                if (nxt >= F) nxt -= F;
-                tq[r] = __ldg(Tp + (size_t)nxt * G::LPS);
-            } else if (nxt < F) {
-                tq[r] = __ldg(Tp + (size_t)nxt * G::LPS);
-            }
-#pragma unroll
-            for (int q = 0; q < NFH / 2; ++q) {
-                const int f = F0 + 2 * q;
-                if (f >= F) continue;
-                const float4 sv = *reinterpret_cast<const float4*>(Sj + (r * G::FP2 + f) * 2);
-                lo[2 * q] = ffma2(make_float2(sv.x, sv.y), make_float2(tj.x, tj.y), lo[2 * q]);
-                hi[2 * q] = ffma2(make_float2(sv.x, sv.y), make_float2(tj.z, tj.w), hi[2 * q]);
-                if (f + 1 < F) {
-                    lo[2 * q + 1] = ffma2(make_float2(sv.z, sv.w), make_float2(tj.x, tj.y), lo[2 * q + 1]);
-                    hi[2 * q + 1] = ffma2(make_float2(sv.z, sv.w), make_float2(tj.z, tj.w), hi[2 * q + 1]);
-                }
-            }
-        }
-    }
-}
-
-template <int F, int D>
-__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32, 8)
-interaction_bwd_stream_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
-                              float* __restrict__ dT, float* __restrict__ dx, unsigned long long* clk) {
-    using G = BwdGeom<F, D>;
-    static_assert(G::SPW == 1, "one sample per warp");
-    constexpr int R = 9;                      // rows of T in flight per lane (F = 27: the ring turns three times per pass)
-    constexpr int H = G::FP2 / 2;             // output rows per pass (the second pass may end in the padding row)
-    static_assert(H % 2 == 0 && F % R == 0, "two output rows per S load; whole turns of the ring");
-    extern __shared__ float4 smem4[];
-    clock_in(clk, blockIdx.x);
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long b = (long long)blockIdx.x * G::WARPS + warp;
-    if (b >= B) {                             // warp-uniform
-        clock_out(clk, blockIdx.x);
-        return;
-    }
-    float* Sw = reinterpret_cast<float*>(smem4) + (size_t)warp * G::SSTRIDE;
-    const float* gb = dOut + (size_t)b * width;
-
-    unsigned short pv[G::NI];
-    float gv[G::NI];
-#pragma unroll
-    for (int i = 0; i < G::NI; ++i) {
-        const int m = lane + 32 * i;
-        pv[i] = kPairTable.v[m < G::NPAIR ? m : 0];
-        gv[i] = (m < G::NPAIR) ? __ldg(gb + D + m) : 0.f;
-    }
-    const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)b * F * G::LPS + lane;
-    float4 tq[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) tq[r] = __ldg(Tp + (size_t)r * G::LPS);
-
-    {   // duplicated S: Sd[j][f] = (S[j][f], S[j][f]), zero diagonal / padding
-        float2* Sb = reinterpret_cast<float2*>(Sw);
-#pragma unroll
-        for (int i = 0; i < G::NI; ++i) {
-            if (lane + 32 * i < G::NPAIR) {
-                const int hi = pv[i] >> 8, lo = pv[i] & 0xff;
-                Sb[hi * G::FP2 + lo] = make_float2(gv[i], gv[i]);
-                Sb[lo * G::FP2 + hi] = make_float2(gv[i], gv[i]);
-            }
-        }
-        for (int f = lane; f < F; f += 32) {
-            Sb[f * G::FP2 + f] = make_float2(0.f, 0.f);
-            if (G::FP2 > F) Sb[f * G::FP2 + F] = make_float2(0.f, 0.f);
-        }
-    }
-    __syncwarp();
-
-    float2 lo[H], hi[H];
-    float4* dTp = reinterpret_cast<float4*>(dT) + (size_t)b * F * G::LPS + lane;
-    bwd_stream_pass<F, D, 0, H, true, R>(Tp, tq, Sw, lo, hi);
-#pragma unroll
-    for (int q = 0; q < H; ++q) {
-        const float4 r = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
-        dTp[(size_t)q * G::LPS] = r;
-        if (q == 0) {
-            const float* g = gb + 4 * lane;    // row width is odd in general: 4-byte aligned only
-            reinterpret_cast<float4*>(dx)[(size_t)b * G::LPS + lane] =
-                make_float4(__fadd_rn(__ldg(g), r.x), __fadd_rn(__ldg(g + 1), r.y),
-                            __fadd_rn(__ldg(g + 2), r.z), __fadd_rn(__ldg(g + 3), r.w));
-        }
-    }
-    bwd_stream_pass<F, D, H, H, false, R>(Tp, tq, Sw, lo, hi);
-#pragma unroll
-    for (int q = 0; q < H; ++q) {
-        if (H + q >= F) continue;
-        dTp[(size_t)(H + q) * G::LPS] = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
     }
     clock_out(clk, blockIdx.x);
 }
@@ -759,8 +634,17 @@ int launch_bwd_warp_plain(const float* dOut, const float* T, int B, int width, f
     return DLRMB_OK;
 }
 
-// The same streaming backward with the ring of T rows in SHARED memory, filled by asynchronous copies
-// (cp.async: global -> shared without passing through registers).  Every lane copies and later reads back only its
+// Output-stationary ("streaming") backward for one sample per warp (d = 128): the warp keeps the accumulators of about
+// HALF of the output rows and streams the rows of T through a ring, consuming row j (one FMA per output row and
+// column, j ascending -- the order of the kernels above, hence the same bits) while the next rows are in flight.
+// Two passes over T, the second from L2.  What this buys over interaction_bwd_warp_kernel, whose warps hold ALL of T
+// (108 registers) before the first FMA:
+//   * 128 registers: 4 warps per SM sub-partition, so 2048 samples are ONE wave of CTAs (8 per SM);
+//   * the FMAs of a pass run while its rows arrive, instead of after the last of the 27 loads has landed; the
+//     stores of the first half leave while the second pass computes.
+// The ring of T rows lives in SHARED memory, filled by asynchronous copies (cp.async: global -> shared without
+// passing through registers; a ring in registers was measured first: ptxas spills it to local memory at 128
+// registers, 25.8 us against 15.9 us at B = 2048).  Every lane copies and later reads back only its
 // own 16-byte column slice, so the only synchronisation is the lane's own cp.async group count.  Registers hold
 // the accumulators and little else: nothing spills at 128 registers, and the ring can be RS rows deep.
 template <int F, int D, int RS>
@@ -880,6 +764,154 @@ interaction_bwd_ring_kernel(const float* __restrict__ dOut, const float* __restr
     clock_out(clk, blockIdx.x);
 }
 
+// Row-paired form of the ring kernel: an FFMA2 computes the SAME column of TWO output rows,
+//     (acc[f][c], acc[f+1][c]) += (S[j][f], S[j][f+1]) * (T[j][c], T[j][c]),
+// so S is stored once (consecutive f are consecutive in memory: one LDS.128 = four output rows, no duplicated
+// entries) and the broadcast operand is the streamed value of T: FFMA2 takes a scalar for both halves (SASS
+// `FFMA2 Rd, Ra.F32x2, Rb.F32, Rc`; ptxas emits it for the pair (t, t)), so nothing is duplicated anywhere.
+// 243 instead of 432 shared-memory loads per sample; the same products in the same order (j ascending), hence
+// the same bits.
+template <int F, int D, int F0, int NFH, int RS, int SLOT0, bool REFILL>
+__device__ __forceinline__ void bwd_ring2_pass(const float4* __restrict__ Tp, float* ring, const float* S1, int lane,
+                                               float2 (&acc)[NFH / 2][4]) {
+    using G = BwdGeom<F, D>;
+    constexpr int FP4 = (F + 3) & ~3;
+    static_assert(NFH % 4 == 0 && F0 % 4 == 0 && F0 + NFH <= FP4, "four output rows per S load");
+#pragma unroll
+    for (int p = 0; p < NFH / 2; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[p][c] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+        const int slot = (SLOT0 + j) % RS;
+        cp_async_wait<RS - 1>();                       // row j has landed (see bwd_ring_pass)
+        const float4 tj = *reinterpret_cast<const float4*>(ring + slot * D + 4 * lane);
+        const float2 tx = make_float2(tj.x, tj.x), ty = make_float2(tj.y, tj.y);
+        const float2 tz = make_float2(tj.z, tj.z), tw = make_float2(tj.w, tj.w);
+#pragma unroll
+        for (int q = 0; q < NFH / 4; ++q) {
+            const int f = F0 + 4 * q;
+            if (f >= F) continue;
+            const float4 sv = *reinterpret_cast<const float4*>(S1 + j * FP4 + f);
+            const float2 s01 = make_float2(sv.x, sv.y);
+            acc[2 * q][0] = ffma2(s01, tx, acc[2 * q][0]);
+            acc[2 * q][1] = ffma2(s01, ty, acc[2 * q][1]);
+            acc[2 * q][2] = ffma2(s01, tz, acc[2 * q][2]);
+            acc[2 * q][3] = ffma2(s01, tw, acc[2 * q][3]);
+            if (f + 2 < F) {
+                const float2 s23 = make_float2(sv.z, sv.w);
+                acc[2 * q + 1][0] = ffma2(s23, tx, acc[2 * q + 1][0]);
+                acc[2 * q + 1][1] = ffma2(s23, ty, acc[2 * q + 1][1]);
+                acc[2 * q + 1][2] = ffma2(s23, tz, acc[2 * q + 1][2]);
+                acc[2 * q + 1][3] = ffma2(s23, tw, acc[2 * q + 1][3]);
+            }
+        }
+        if (j + RS < F) cp_async16(ring + slot * D + 4 * lane, Tp + (size_t)(j + RS) * G::LPS);
+        else if (REFILL) cp_async16(ring + slot * D + 4 * lane, Tp + (size_t)(j + RS - F) * G::LPS);
+        cp_async_commit();
+    }
+}
+
+template <int F, int D, int RS>
+__global__ void __launch_bounds__(BwdGeom<F, D>::WARPS * 32, 8)
+interaction_bwd_ring2_kernel(const float* __restrict__ dOut, const float* __restrict__ T, int B, int width,
+                             float* __restrict__ dT, float* __restrict__ dx, unsigned long long* clk) {
+    using G = BwdGeom<F, D>;
+    static_assert(G::SPW == 1 && RS <= F, "one sample per warp; the ring is primed with RS rows");
+    constexpr int FP4 = (F + 3) & ~3;                      // S row pitch
+    constexpr int H1 = ((FP4 / 2) + 3) & ~3;               // output rows of the first pass (16 of 27)
+    constexpr int H2 = FP4 - H1;                           // second pass, padding rows included (12)
+    constexpr int SSZ1 = F * FP4 + 4;                      // floats of S per warp (+16 B: keeps the ring 16-byte aligned)
+    constexpr int PER_WARP = SSZ1 + RS * D;
+    extern __shared__ float4 smem4[];
+    clock_in(clk, blockIdx.x);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * G::WARPS + warp;
+    if (b >= B) {                             // warp-uniform
+        clock_out(clk, blockIdx.x);
+        return;
+    }
+    float* S1 = reinterpret_cast<float*>(smem4) + (size_t)warp * PER_WARP;
+    float* ring = S1 + SSZ1;
+    const float* gb = dOut + (size_t)b * width;
+    const float4* Tp = reinterpret_cast<const float4*>(T) + (size_t)b * F * G::LPS + lane;
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {            // prime the ring
+        cp_async16(ring + r * D + 4 * lane, Tp + (size_t)r * G::LPS);
+        cp_async_commit();
+    }
+    {   // S1[j][f] = S[j][f], zero diagonal and padding columns
+#pragma unroll
+        for (int i = 0; i < G::NI; ++i) {
+            const int m = lane + 32 * i;
+            if (m < G::NPAIR) {
+                const unsigned short p = kPairTable.v[m];
+                const float gvv = __ldg(gb + D + m);
+                const int hi = p >> 8, lo = p & 0xff;
+                S1[hi * FP4 + lo] = gvv;
+                S1[lo * FP4 + hi] = gvv;
+            }
+        }
+        for (int f = lane; f < F; f += 32) {
+            S1[f * FP4 + f] = 0.f;
+#pragma unroll
+            for (int c = F; c < FP4; ++c) S1[f * FP4 + c] = 0.f;
+        }
+    }
+    __syncwarp();
+
+    float4* dTp = reinterpret_cast<float4*>(dT) + (size_t)b * F * G::LPS + lane;
+    {
+        float2 acc[H1 / 2][4];
+        bwd_ring2_pass<F, D, 0, H1, RS, 0, true>(Tp, ring, S1, lane, acc);
+#pragma unroll
+        for (int p = 0; p < H1 / 2; ++p) {
+            const float4 r0 = make_float4(acc[p][0].x, acc[p][1].x, acc[p][2].x, acc[p][3].x);
+            const float4 r1 = make_float4(acc[p][0].y, acc[p][1].y, acc[p][2].y, acc[p][3].y);
+            if (2 * p < F) dTp[(size_t)(2 * p) * G::LPS] = r0;
+            if (2 * p + 1 < F) dTp[(size_t)(2 * p + 1) * G::LPS] = r1;
+            if (p == 0) {
+                const float* g = gb + 4 * lane;    // row width is odd in general: 4-byte aligned only
+                reinterpret_cast<float4*>(dx)[(size_t)b * G::LPS + lane] =
+                    make_float4(__fadd_rn(__ldg(g), r0.x), __fadd_rn(__ldg(g + 1), r0.y),
+                                __fadd_rn(__ldg(g + 2), r0.z), __fadd_rn(__ldg(g + 3), r0.w));
+            }
+        }
+    }
+    {
+        float2 acc[H2 / 2][4];
+        bwd_ring2_pass<F, D, H1, H2, RS, F % RS, false>(Tp, ring, S1, lane, acc);
+#pragma unroll
+        for (int p = 0; p < H2 / 2; ++p) {
+            const int f = H1 + 2 * p;
+            if (f < F) dTp[(size_t)f * G::LPS] = make_float4(acc[p][0].x, acc[p][1].x, acc[p][2].x, acc[p][3].x);
+            if (f + 1 < F) dTp[(size_t)(f + 1) * G::LPS] = make_float4(acc[p][0].y, acc[p][1].y, acc[p][2].y, acc[p][3].y);
+        }
+    }
+    clock_out(clk, blockIdx.x);
+}
+
+template <int F, int D>
+int launch_bwd_ring2(const float* dOut, const float* T, int B, int width, float* dT, float* dx, cudaStream_t s) {
+    using G = BwdGeom<F, D>;
+    if constexpr (G::SPW == 1 && F >= 12) {
+        constexpr int RS = 12;
+        constexpr int FP4 = (F + 3) & ~3;
+        static unsigned long long attr_done = 0;
+        const size_t smem = (size_t)G::WARPS * (F * FP4 + 4 + RS * D) * 4;
+        const long long grid = ((long long)B + G::WARPS - 1) / G::WARPS;
+        int rc = ensure_smem_attr((const void*)interaction_bwd_ring2_kernel<F, D, RS>, (int)smem, &attr_done);
+        if (rc) return rc;
+        interaction_bwd_ring2_kernel<F, D, RS><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(dOut, T, B, width, dT, dx,
+                                                                                          clock_slot(CLK_IBWD));
+        DLRMB_LAUNCH_CHECK();
+        return DLRMB_OK;
+    } else {
+        return -1;
+    }
+}
+
 template <int F, int D>
 int launch_bwd_ring(const float* dOut, const float* T, int B, int width, float* dT, float* dx, cudaStream_t s) {
     using G = BwdGeom<F, D>;
@@ -892,24 +924,6 @@ int launch_bwd_ring(const float* dOut, const float* T, int B, int width, float* 
         if (rc) return rc;
         interaction_bwd_ring_kernel<F, D, RS><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(dOut, T, B, width, dT, dx,
                                                                                          clock_slot(CLK_IBWD));
-        DLRMB_LAUNCH_CHECK();
-        return DLRMB_OK;
-    } else {
-        return -1;
-    }
-}
-
-template <int F, int D>
-int launch_bwd_stream(const float* dOut, const float* T, int B, int width, float* dT, float* dx, cudaStream_t s) {
-    using G = BwdGeom<F, D>;
-    if constexpr (G::SPW == 1 && F % 9 == 0) {
-        static unsigned long long attr_done = 0;
-        const size_t smem = G::smem_bytes();
-        const long long grid = ((long long)B + G::WARPS - 1) / G::WARPS;
-        int rc = ensure_smem_attr((const void*)interaction_bwd_stream_kernel<F, D>, (int)smem, &attr_done);
-        if (rc) return rc;
-        interaction_bwd_stream_kernel<F, D><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(dOut, T, B, width, dT, dx,
-                                                                                       clock_slot(CLK_IBWD));
         DLRMB_LAUNCH_CHECK();
         return DLRMB_OK;
     } else {
@@ -935,13 +949,13 @@ int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* 
     }
     if (G::SPW == 1) {   // one sample per warp: see BwdGeom
         int v = g_opt.bwd_variant.load(std::memory_order_relaxed);
-        if (v < 1 || v > 5) {   // by batch: the 128-register kernel while the batch is one wave of it (8 CTAs per SM)
+        if (v < 1 || v > 6) {   // by batch: the 128-register kernel while the batch is one wave of it (8 CTAs per SM)
             int dev = 0;
             cudaGetDevice(&dev);
             v = ((long long)B <= (long long)device_sm_count(dev) * 8 * G::WARPS) ? 2 : 3;
         }
-        if (v == 4) return launch_bwd_stream<F, D>(dOut, T, B, width, dT, dx, s);
         if (v == 5) return launch_bwd_ring<F, D>(dOut, T, B, width, dT, dx, s);
+        if (v == 6) return launch_bwd_ring2<F, D>(dOut, T, B, width, dT, dx, s);
         if (v == 2) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
         if (v == 3) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
     }

@@ -75,64 +75,6 @@ __device__ __forceinline__ void lookup_gather_body(const TableDesc* __restrict__
     }
 }
 
-// P == 1, persistent form for batches whose gather is only a few waves of CTAs (DLRM batch sizes): the launch is ONE
-// wave of CTAs, the (table, sample, chunk) items of ALL tables are split evenly over them (table-major, so idx[]
-// is indexed by the flat row number), and a thread walks its CTA's range U items at a time with the NEXT
-// round's indices requested before the current round's rows are stored -- no CTA launch gaps between the
-// waves, no index round trip on the critical path after the first round, every CTA the same amount of work.
-// C (16-byte chunks per row) must be a power of two.
-template <typename IdxT, int U, typename RowT>
-__device__ __forceinline__ void lookup_gather_flat_body(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx,
-                                                        int idx_base, uint32_t B, int cshift, float* __restrict__ out,
-                                                        int slots, int slot0, int ntab, uint32_t cta, uint32_t nctas) {
-    const uint32_t C = 1u << cshift;
-    const size_t D = (size_t)C * 4;
-    const size_t ostride = (size_t)slots * D;
-    const uint32_t total = (uint32_t)ntab * B * C;                       // < 2^31 (checked by the launcher)
-    uint32_t per_cta = (total + nctas - 1) / nctas;
-    per_cta = (per_cta + 255u) & ~255u;                                   // whole rounds of the 256 threads
-    const uint32_t begin = min(total, cta * per_cta);
-    const uint32_t end = min(total, begin + per_cta);
-    constexpr uint32_t ROUND = 256 * U;
-
-    int64_t rown[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint32_t i = begin + (uint32_t)u * 256 + threadIdx.x;
-        rown[u] = (i < end) ? (int64_t)__ldg(idx + (i >> cshift)) - idx_base : 0;
-    }
-#pragma unroll 1
-    for (uint32_t base = begin; base < end; base += ROUND) {
-        float4 v[U];
-        uint32_t r[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t i = base + (uint32_t)u * 256 + threadIdx.x;
-            r[u] = i >> cshift;                                           // flat row = k * B + b
-            if (i < end) {
-                const uint32_t k = r[u] / B;
-                v[u] = Vec<4>::template ldrow<RowT>(desc[k].base, (size_t)rown[u], D, (int)(i & (C - 1)));
-            }
-        }
-        if (base + ROUND < end) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t i = base + ROUND + (uint32_t)u * 256 + threadIdx.x;
-                rown[u] = (i < end) ? (int64_t)__ldg(idx + (i >> cshift)) - idx_base : 0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t i = base + (uint32_t)u * 256 + threadIdx.x;
-            if (i < end) {
-                const uint32_t k = r[u] / B;
-                const uint32_t b = r[u] - k * B;
-                reinterpret_cast<float4*>(out + (size_t)b * ostride + (size_t)(slot0 + k) * D)[i & (C - 1)] = v[u];
-            }
-        }
-    }
-}
-
 // P > 1: gather + sum-pool, ascending p.
 template <typename IdxT, int VEC, typename RowT>
 __device__ __forceinline__ void lookup_pool_body(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx,
@@ -204,7 +146,10 @@ lookup_pool_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
 // The sort needs the indices only, and one CTA per table sorts that table's B*P keys in shared
 // memory (sort_small.cuh) in less time than the gather takes, so the first `ntab` CTAs of the grid
 // are sort CTAs and the rest gather: the sort costs no launch of its own and no time on the stream.
-template <typename IdxT, int U, typename RowT, int ITEMS, bool POOL, bool FLAT = false>
+// (Measured and not kept: the gather CTAs as ONE persistent wave over all tables, every thread walking its CTA's
+// share 5 rows at a time with the next round's indices prefetched -- 10.6 vs 12.3 us with L2 flushed before the
+// launch, but 10.2 vs 9.6 us back to back and no change in the training step, profiles/r02_lookup_flat.txt.)
+template <typename IdxT, int U, typename RowT, int ITEMS, bool POOL>
 __global__ void __launch_bounds__(256, 5)
 lookup_sort_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ idx, int idx_base, uint32_t B,
                    uint32_t P, uint32_t C, int cshift, float* __restrict__ out, int slots, int slot0, int ntab,
@@ -221,11 +166,6 @@ lookup_sort_kernel(const TableDesc* __restrict__ desc, const IdxT* __restrict__ 
         return;
     }
     const uint32_t lin = blockIdx.x - ntab;
-    if (FLAT) {   // bx = number of gather CTAs of the whole launch
-        lookup_gather_flat_body<IdxT, U, RowT>(desc, idx, idx_base, B, cshift, out, slots, slot0, ntab, lin, bx);
-        clock_out(clk, blockIdx.x);
-        return;
-    }
     const int k = (int)(lin / bx);
     const uint32_t cx = lin - (uint32_t)k * bx;
     if (POOL) lookup_pool_body<IdxT, 4, RowT>(desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, k, cx, bx);
@@ -299,28 +239,6 @@ static int launch_lookup_sort_i(dlrmb_tables* t, const IdxT* idx, int idx_base, 
     int cshift;
     lookup_grid(t, n, P, &bx, &cshift, C);
     constexpr size_t smem = SmallSortGeom<ITEMS, 256>::smem_bytes();
-    if (!POOL) {
-        // persistent one-wave gather ("lookup_flat": 0 = when the multi-wave grid would be 1.2 to 4 waves, 1 = always, 2 = never)
-        constexpr int UF = 5;
-        const int mode = g_opt.lookup_flat.load(std::memory_order_relaxed);
-        const int64_t wave = (int64_t)t->sm_count * 5;                   // resident CTAs (launch bound 256 x 5)
-        const int64_t multi = t->ntab + bx * t->ntab;
-        const bool fits = cshift >= 0 && (int64_t)t->ntab * n < (1ll << 31) && wave > t->ntab;
-        if (fits && mode != 2 && (mode == 1 || (multi * 5 > wave * 6 && multi <= wave * 4))) {
-            static unsigned long long attr_flat = 0;
-            int rc = ensure_smem_attr((const void*)lookup_sort_kernel<IdxT, UF, RowT, ITEMS, false, true>, (int)smem, &attr_flat);
-            if (rc) return rc;
-            int64_t gather = wave - t->ntab;
-            const int64_t need = ceil_div64((int64_t)t->ntab * n, 256);   // at least one round of 256 items per CTA
-            if (gather > need) gather = need;
-            lookup_sort_kernel<IdxT, UF, RowT, ITEMS, false, true><<<(unsigned)(t->ntab + gather), 256, smem, s>>>(
-                t->d_desc, idx, idx_base, B, P, C, cshift, out, slots, slot0, t->ntab, (uint32_t)gather, t->keys[0], t->pos[0],
-                t->cap, clock_slot(CLK_LOOKUP));
-            DLRMB_LAUNCH_CHECK();
-            t->sorted_buf = 0;
-            return DLRMB_OK;
-        }
-    }
     static unsigned long long attr_done = 0;
     int rc = ensure_smem_attr((const void*)lookup_sort_kernel<IdxT, U, RowT, ITEMS, POOL>, (int)smem, &attr_done);
     if (rc) return rc;

@@ -59,10 +59,10 @@ int64_t dlrmb_launch_count(void);
  *   "interact_general" 1 = run the general tiled interaction kernels even for the specialised shapes
  *   "update_two_launches" 1 = separate fix-up launch of the sparse update at every batch size
  *   "update_tile" 4, 8, .. 32 = entries per lane group of the sparse update (0 = chosen per batch)
- *   "bwd_variant" 0 = by batch size (default), 1 | 2 | 3 = warp-per-sample interaction backward (d = 128) with FFMA2 at 144
- *                     registers / FFMA2 at 128 registers (one wave of CTAs up to 2368 samples) / S stored once + scalar FMAs
- *   "lookup_flat" 0 | 1 | 2 = gather CTAs of the fused lookup + sort launch (P = 1) as one persistent wave over all tables:
- *                     for batches of 1.2 to 4 waves / always / never
+ *   "bwd_variant" 0 = by batch size (default); 1 | 2 | 3 = one-sample-per-warp interaction backward (d = 128) holding all of T in
+ *                     registers: FFMA2 with duplicated S at 144 registers / the same at 128 registers (one wave of CTAs up
+ *                     to 2368 samples) / S stored once (FFMA2 with a scalar operand); 5 | 6 = streaming kernels (half of the
+ *                     output rows per pass, T rows through a cp.async ring): duplicated S / S stored once, row-paired FFMA2
  *   "fwd_tb" 3|6|9, "fwd_ks" 0..3 = register block / k-split of the general tiled forward
  *   "fwd_ksplit" 0|1|2 = tensor-core forward with one warp per sample always / two warps per sample for one-wave
  *                        batches (default) / two warps per sample always

@@ -286,11 +286,12 @@ def test_interaction_warp_kernels_vs_oracle_and_tiled_kernels(B, F, d, lib_optio
         assert np.array_equal(dT_w, dT_t) and np.array_equal(dx_w, dx_t)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 2, 3, 5, 6])
 @pytest.mark.parametrize("B,F,d", [(2049, 27, 128), (1, 27, 128), (301, 27, 64), (131, 8, 16)])
 def test_interaction_backward_register_variants_bit_equal(B, F, d, variant, lib_options):
-    """bwd_variant: the warp-per-sample backward with FFMA2 at 128 registers (2; one wave of CTAs at B = 2048, d = 128),
-    with S stored once and scalar FMAs (3), or chosen by batch size (0).  The per-output summation order does not
+    """bwd_variant: the one-sample-per-warp backward with FFMA2 at 128 registers (2), with S stored once (3), as a
+    streaming kernel -- half of the output rows per pass, T rows through a cp.async ring -- with duplicated S (5) or
+    S stored once and row-paired FFMA2 (6), or chosen by batch size (0).  The per-output summation order does not
     depend on it: same bits as the 144-register FFMA2 kernel (1), which is pinned to the oracle here."""
     from dlrm_jl_b200.interact import interaction_bwd, interaction_width
     rng = np.random.default_rng(B + F + d + variant)
@@ -851,18 +852,13 @@ def zipf_indices(rng, rows, size, alpha):
     return (r * 2654435761 + 12345) % rows
 
 
-@pytest.mark.parametrize("flat", [0, 1, 2])
 @pytest.mark.parametrize("B,P", [(1, 1), (5, 3), (2048, 1), (683, 3), (4096, 1), (100, 40), (4097, 1), (3000, 2), (333, 1)])
 @pytest.mark.parametrize("dtype,base", [(np.int32, 0), (np.int64, 1)])
-def test_lookup_sort_fused_launch_equals_separate_launches(B, P, dtype, base, flat, lib_options):
+def test_lookup_sort_fused_launch_equals_separate_launches(B, P, dtype, base):
     """dlrmb_embedding_fwd_sort (the sort rides in extra CTAs of the lookup launch for B*P <= 4096, two
     launches above) == dlrmb_embedding_fwd + dlrmb_embedding_sort: pooled rows and the exported
-    dedup, bit for bit, and against the oracle.  `lookup_flat`: the gather CTAs of the fused launch as one
-    persistent wave over all tables (1 = always, 0 = by batch size, 2 = never)."""
+    dedup, bit for bit, and against the oracle."""
     from dlrm_jl_b200.embedding import EmbeddingTables
-    if flat != 0 and (P != 1 or B * P > 4096):
-        pytest.skip("the persistent gather only exists in the fused P = 1 launch")
-    lib_options("lookup_flat", flat)
     rng = np.random.default_rng(B * 7 + P)
     rows, D = [3, 1000, 40_000_000, 513, 70000], 32
     L = B * P

@@ -1152,7 +1152,7 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
         out["embedding"] = {"algorithmic_bytes": int(emb_bytes), "us": emb_us,
                             "gbs": emb_bytes / (emb_us * 1e-6) / 1e9,
                             "frac_hbm": emb_bytes / (emb_us * 1e-6) / 1e9 / hbm_peak,
-                            "clock": "in_step_us (serialised step, eager event pairs), summed over the launches below",
+                            "clock": "in_step_us (kernels.<name>.in_step_clock: the kernels' own %globaltimer stamps inside the replayed step graph; CUDA-event pairs of the serialised eager step when the step does not run as a graph), summed over the launches below",
                             "includes": " + ".join(emb_names) + " launches (gather, index sort / dedup, scatter-add + SGD)"}
         if replay and "embedding_chain" in replay:
             out["embedding"]["back_to_back_us"] = float(replay["embedding_chain"])
@@ -1167,8 +1167,8 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
                         tj = json.load(fh)
                     if world == 1 and dom in tj["kernels"]:
                         traffic = tj["kernels"][dom]["dram_bytes_read"] + tj["kernels"][dom]["dram_bytes_write"]
-                        traffic_src = (f"constant: profiles/{tag}_ncu_traffic_{wl['name']}.json ({tj['report']}), an ncu --set full "
-                                       "capture of this command, not measured in this run")
+                        traffic_src = (f"constant: profiles/{tag}_ncu_traffic_{wl['name']}.json ({tj['report']}): "
+                                       + tj.get("note", "an ncu --set full capture of this command") + "; not measured in this run")
                     break
         except Exception:
             pass
@@ -1179,9 +1179,9 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
                            "achieved_back_to_back": (kd["algorithmic_bytes"] / (kd["back_to_back_us"] * 1e-6) / 1e9
                                                      if "back_to_back_us" in kd else None),
                            "note": ("dominant kernel of this repo by in-step time; achieved = algorithmic bytes per launch / "
-                                    "in-step device time (CUDA event pair around the launch in the step's own launch sequence, "
-                                    "serialised on one stream, averaged over the timed batches); achieved_back_to_back = same "
-                                    "bytes / back-to-back launch time")}
+                                    "in-step device time (kernels.<name>.in_step_us and its in_step_clock: the kernel's own "
+                                    "%globaltimer stamps inside the replayed step graph, averaged over the timed batches); "
+                                    "achieved_back_to_back = same bytes / back-to-back launch time")}
     return out
 
 

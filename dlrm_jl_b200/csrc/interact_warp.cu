@@ -73,22 +73,23 @@ struct BwdGeom {
     static constexpr int NI = (NPAIR + 31) / 32; // pair entries per lane
     static constexpr int SSTRIDE_DUP = F * FP2 * 2 + 4;   // floats per sample of duplicated S (+16 B bank stagger)
     static constexpr int NF0 = (F % 3 == 0) ? 3 : ((F % 2 == 0) ? 2 : 1);
-    // Variants of the one-sample-per-warp kernel with plain stores (d = 128; `bwd_variant` picks one, 0 = by batch):
-    //   VAR 0  FFMA2, NF0 output rows per pass, 144 registers (the round-1 kernel; also every other geometry)
-    //   VAR 1  FFMA2, nine rows per pass, 128 registers: the compiler walks the nine rows one after another, nothing
-    //          spills, and 8 CTAs fit per SM -- registers are allocated per SM sub-partition (16384 each), so a
-    //          32-thread warp at 144 or 168 registers leaves room for 3 warps per sub-partition = 6 CTAs per SM, and
-    //          2048 samples (1024 CTAs) were 888 CTAs + a second wave of 136 that started when the first ended
-    //          (per-CTA %globaltimer stamps, benchmarks/cta_timeline.py: 13 % of the CTAs entered 12 us late).
-    //          One wave: 16.2 vs 18.0 us at B = 2048, but 105 vs 100 us at B = 16384 (many waves either way).
-    //   VAR 2  S stored ONCE, scalar FMAs, NF0 rows, 144 registers.  The shared-memory -> register path returns
-    //          128 bytes per clock per SM whatever the address pattern, so a broadcast LDS.128 costs a warp 4 clocks:
-    //          2 clocks per S value with duplicated entries, 1 with plain entries, at the price of twice the FMA issue
-    //          slots (FFMA instead of FFMA2, same flops per clock): 93 vs 100 us at B = 16384 (0.82 of the HBM peak),
-    //          17.1 vs 18.0 us at B = 2048.
-    // Same products in the same order in all three: same bits (tests/test_gpu_parity.py).  Measured and not kept:
-    // FFMA2 at 128 registers with NF0 rows (84 bytes of spills) or one row per pass, scalar FMAs at 128 registers --
-    // one wave, but every CTA lives 15-20 us (profiles/r02_bwd_variants.txt).
+    // Variants of this kernel for one sample per warp (d = 128), selected by `bwd_variant` (the default is the streaming
+    // kernel further down; B = 2048 / 16384, cold inputs, profiles/r02_bwd_variants.txt):
+    //   VAR 0  FFMA2, S duplicated in shared memory, NF0 output rows per pass, 144 registers (the round-1 kernel; also
+    //          every geometry with several samples per warp): 18.0 / 100 us.
+    //   VAR 1  the same at 128 registers with nine rows per pass (the compiler walks them one after another, nothing
+    //          spills): 8 CTAs fit per SM -- registers are allocated per SM sub-partition (16384 each), so a 32-thread
+    //          warp at 144 or 168 registers leaves room for 3 warps per sub-partition = 6 CTAs per SM, and 2048 samples
+    //          (1024 CTAs) were 888 CTAs + a second wave of 136 that started when the first ended (per-CTA %globaltimer
+    //          stamps, benchmarks/cta_timeline.py: 13 % of the CTAs entered 12 us late).  One wave: 16.2 us, but 105 us
+    //          at B = 16384 (many waves either way).
+    //   VAR 2  S stored ONCE: FFMA2 takes a scalar operand for both halves (SASS `FFMA2 Rd, Ra.F32, Rb.F32x2, Rc`), so
+    //          the duplicate only ever existed to please the PTX form fma.rn.f32x2 -- ptxas folds the pair (s, s) into
+    //          the scalar form.  Half the shared-memory loads per FMA: 14.9 / 84 us (0.64 / 0.91 of the HBM peak).  Also
+    //          the kernel behind the peer-store epilogue (168 registers).
+    // Same products in the same order in all of them: same bits (tests/test_gpu_parity.py).  Measured and not kept:
+    // FFMA2 at 128 registers with NF0 rows (84 bytes of spills) or one row per pass, scalar FFMA instead of FFMA2 for
+    // VAR 2 (17.0 / 93 us: twice the issue slots).
     static constexpr int NF = (VAR == 1 && F % 9 == 0) ? 9 : NF0;
     static constexpr bool DUP = VAR != 2;
     static constexpr int SSTRIDE = DUP ? SSTRIDE_DUP : F * FP2 + 4;
@@ -935,27 +936,30 @@ template <int F, int D>
 int launch_bwd_warp(const float* dOut, const float* T, int B, int width, float* dT, float* dx,
                     const void* dests, long long sample_offset, cudaStream_t s) {
     using G = BwdGeom<F, D>;
-    if (dests) {
+    if (dests) {   // peer-store epilogue: the resident kernel, with S stored once (VAR 2) for one sample per warp
+        constexpr int SV = (G::SPW == 1) ? 2 : 0;
         static unsigned long long attr_done = 0;
-        const size_t smem = G::smem_bytes();
+        const size_t smem = BwdGeom<F, D, SV>::smem_bytes();
         const long long groups = ((long long)B + G::SPW - 1) / G::SPW;
         const long long grid = (groups + G::WARPS - 1) / G::WARPS;
-        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, true, 0>, (int)smem, &attr_done);
+        int rc = ensure_smem_attr((const void*)interaction_bwd_warp_kernel<F, D, true, SV>, (int)smem, &attr_done);
         if (rc) return rc;
-        interaction_bwd_warp_kernel<F, D, true, 0><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
+        interaction_bwd_warp_kernel<F, D, true, SV><<<(unsigned)grid, G::WARPS * 32, smem, s>>>(
             dOut, T, B, width, dT, dx, static_cast<const SlotDestW*>(dests), sample_offset, clock_slot(CLK_IBWD));
         DLRMB_LAUNCH_CHECK();
         return DLRMB_OK;
     }
     if (G::SPW == 1) {   // one sample per warp: see BwdGeom
         int v = g_opt.bwd_variant.load(std::memory_order_relaxed);
-        if (v < 1 || v > 6) {   // by batch: the 128-register kernel while the batch is one wave of it (8 CTAs per SM)
-            int dev = 0;
-            cudaGetDevice(&dev);
-            v = ((long long)B <= (long long)device_sm_count(dev) * 8 * G::WARPS) ? 2 : 3;
+        // default: the streaming kernel with S stored once (fastest at every batch size measured, 2048 .. 16384:
+        // profiles/r02_bwd_variants.txt); the others stay selectable for the parity tests and A/B runs
+        if (v < 1 || v > 6) v = 6;
+        if (v == 5 || v == 6) {
+            const int rc = (v == 5) ? launch_bwd_ring<F, D>(dOut, T, B, width, dT, dx, s)
+                                    : launch_bwd_ring2<F, D>(dOut, T, B, width, dT, dx, s);
+            if (rc != -1) return rc;
+            v = 3;   // no streaming kernel for this F: the resident kernel with S stored once
         }
-        if (v == 5) return launch_bwd_ring<F, D>(dOut, T, B, width, dT, dx, s);
-        if (v == 6) return launch_bwd_ring2<F, D>(dOut, T, B, width, dT, dx, s);
         if (v == 2) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 1 : 0>(dOut, T, B, width, dT, dx, s);
         if (v == 3) return launch_bwd_warp_plain<F, D, (G::SPW == 1) ? 2 : 0>(dOut, T, B, width, dT, dx, s);
     }

@@ -1,5 +1,5 @@
 """Extract per-kernel DRAM traffic + duration from an ncu report into a small JSON that bench.py
-reads for `roofline.traffic`.  usage: python profiles/ncu_traffic.py report.ncu-rep out.json workload"""
+reads for `roofline.traffic`.  usage: python profiles/ncu_traffic.py report.ncu-rep out.json workload [note]"""
 import csv
 import io
 import json
@@ -12,10 +12,11 @@ NAMES = {"lookup_sort_kernel": "lookup", "lookup_gather_kernel": "lookup", "look
          "update_fixup_kernel": "update_fixup", "interaction_fwd_kernel": "interaction_fwd",
          "interaction_bwd_kernel": "interaction_bwd",
          "interaction_fwd_mma_kernel": "interaction_fwd", "interaction_fwd_mma_ksplit_kernel": "interaction_fwd",
-         "interaction_fwd_warp_kernel": "interaction_fwd", "interaction_bwd_warp_kernel": "interaction_bwd", "sort_small_kernel": "sort"}
+         "interaction_fwd_warp_kernel": "interaction_fwd", "interaction_bwd_warp_kernel": "interaction_bwd", "sort_small_kernel": "sort",
+         "interaction_bwd_ring_kernel": "interaction_bwd", "interaction_bwd_ring2_kernel": "interaction_bwd"}
 
 
-def main(path, out, workload):
+def main(path, out, workload, note=None):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -36,9 +37,12 @@ def main(path, out, workload):
             "dram_bytes_write": val(r, "dram__bytes_write.sum"),
             "duration_us_under_ncu": val(r, "gpu__time_duration.sum"),
         }
-    json.dump({"workload": workload, "report": path.split("/")[-1], "kernels": res}, open(out, "w"), indent=1)
+    doc = {"workload": workload, "report": path.split("/")[-1], "kernels": res}
+    if note:
+        doc["note"] = note
+    json.dump(doc, open(out, "w"), indent=1)
     print(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])

@@ -91,7 +91,7 @@ struct BwdGeom {
     // FFMA2 at 128 registers with NF0 rows (84 bytes of spills) or one row per pass, scalar FFMA instead of FFMA2 for
     // VAR 2 (17.0 / 93 us: twice the issue slots).
     static constexpr int NF = (VAR == 1 && F % 9 == 0) ? 9 : NF0;
-    static constexpr bool DUP = VAR != 2;
+    static constexpr bool DUP = (VAR == 1) || (VAR == 0 && SPW == 1);   // several samples per warp: S stored once as well
     static constexpr int SSTRIDE = DUP ? SSTRIDE_DUP : F * FP2 + 4;
     static constexpr int WARPS = 2;
     static constexpr int max_regs(bool scatter) { return (SPW == 1 && !scatter) ? (VAR == 1 ? 128 : 144) : 168; }

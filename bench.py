@@ -1165,7 +1165,7 @@ def hot_path_report(wl, world, rank, se, prof, ms_step, replay):
                 if os.path.exists(path):
                     with open(path) as fh:
                         tj = json.load(fh)
-                    if world == 1 and dom in tj["kernels"]:
+                    if world == 1 and dom in tj["kernels"] and tj.get("batch_per_gpu", 2048) == wl["B"]:
                         traffic = tj["kernels"][dom]["dram_bytes_read"] + tj["kernels"][dom]["dram_bytes_write"]
                         traffic_src = (f"constant: profiles/{tag}_ncu_traffic_{wl['name']}.json ({tj['report']}): "
                                        + tj.get("note", "an ncu --set full capture of this command") + "; not measured in this run")

@@ -91,6 +91,32 @@ def test_argument_validation_needs_no_gpu(built_lib):
         _lib.check(rc)
 
 
+def test_library_switches_match_the_header(built_lib):
+    """dlrmb_set_option / dlrmb_get_option (host-side state, no GPU): every switch the header documents exists and
+    round-trips, defaults are what the header says, unknown names are refused, and bench.py records real names."""
+    import re
+    from dlrm_jl_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dlrm_b200.h")).read()
+    block = header[header.index("Process-wide tuning / test switches"):header.index("int32_t dlrmb_set_option")]
+    names = re.findall(r'^ \*   "([a-z_0-9]+)"', block, flags=re.M)
+    names += re.findall(r', "([a-z_0-9]+)" [0-9]', block)          # second switch documented on the same line
+    assert {"interact_general", "update_two_launches", "update_tile", "bwd_variant", "fwd_tb", "fwd_ks", "fwd_ksplit"} <= set(names)
+    defaults = {"fwd_ksplit": 1}
+    for n in names:
+        before = _lib.get_option(n)
+        assert before == defaults.get(n, 0), (n, before)
+        _lib.set_option(n, 3)
+        assert _lib.get_option(n) == 3
+        _lib.set_option(n, before)
+    for bad in ("update_prefetch", "lookup_flat", "fwd_rows_per_copy", "no_such_switch"):   # measured and removed / never existed
+        with pytest.raises(_lib.DLRMB200Error, match="unknown option"):
+            _lib.set_option(bad, 1)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    recorded = re.search(r'for k in \(([^)]*)\)\}', bench[bench.index("def library_options"):]).group(1)
+    for n in re.findall(r'"([a-z_0-9]+)"', recorded):
+        assert n in names, n
+
+
 def test_product_path_has_no_cpu_fallback(built_lib):
     from dlrm_jl_b200 import DLRMB200Error
     from dlrm_jl_b200.embedding import EmbeddingTables

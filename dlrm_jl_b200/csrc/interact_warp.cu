@@ -12,13 +12,19 @@
 //     the DRAM stream, the FMA pipe and the store stream overlap;
 //   * all FMAs are FFMA2 (PTX fma.rn.f32x2, sm_100+): two IEEE fp32 FMAs per issue slot, operands
 //     taken as the natural 64-bit halves of 128-bit loads;
-//   * backward: a lane keeps its float4 column slice of ALL F rows of T in registers (F LDG.128 in
-//     flight per lane, no shared-memory staging of T at all); S is expanded once per sample into
-//     shared memory with every entry duplicated, so one broadcast LDS.128 feeds four FFMA2.  The
-//     per-output summation order (j ascending, one fused multiply-add per term) is the tiled
-//     kernel's, so both produce the same bits.  (Measured and not kept in round 2: S stored once with
-//     the FFMA2 halves carrying two different j -- half the S wavefronts, but F*d/2 register moves per
-//     sample: 23.8 vs 16.2 us at B = 2048; profiles/r02_interaction_variants.txt.)
+//   * backward, d = 128 (interaction_bwd_ring2_kernel, the default): output-stationary and streaming -- the warp
+//     keeps the accumulators of about half of the output rows and streams the rows of T through a ring in shared
+//     memory filled by cp.async, consuming row j while the next twelve are in flight; S is stored once and an FFMA2
+//     computes the same column of two output rows with the streamed T value as its SCALAR operand (the hardware
+//     broadcasts it).  Other geometries and the peer-store epilogue (interaction_bwd_warp_kernel): a lane keeps its
+//     float4 column slice of ALL F rows of T in registers (F LDG.128 in flight per lane, no shared-memory staging
+//     of T at all); S in shared memory, stored once, one broadcast load of two S values feeding four FFMA2 (scalar
+//     operand again).  The per-output summation order (j ascending, one fused multiply-add per term) is the tiled
+//     kernel's in all of them, so they produce the same bits.  (Round 1 duplicated every S entry in shared memory
+//     to build the (s, s) pair fma.rn.f32x2 asks for; ptxas folds that pair into FFMA2's scalar operand, so the
+//     duplicate was never needed.  Measured and not kept in round 2: S stored once with the FFMA2 halves carrying
+//     two different j -- F*d/2 register moves per sample: 23.8 vs 16.2 us at B = 2048;
+//     profiles/r02_interaction_variants.txt, r02_bwd_variants.txt.)
 //   * forward: T rows arrive by TMA bulk copies (cp.async.bulk, one per row, one mbarrier per
 //     warp) at bank-staggered row addresses and the Gram matrix is computed on the tensor cores in
 //     3xTF32 form (see interaction_fwd_mma_kernel); the sample's output row is assembled in the dead

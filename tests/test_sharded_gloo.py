@@ -37,6 +37,26 @@ def test_partition_balances_lookups_then_bytes():
         assert max(c) - min(c) <= 1
 
 
+def test_c_abi_shard_plan_equals_the_python_plan():
+    """dlrmb_shard_plan (host logic of libdlrm_b200.so, what a non-Python host calls) deals the tables exactly as
+    TableSharding.build does -- descending rows, ties by table id, snake order -- for the Criteo geometries, for
+    ties and for more ranks than tables; bad arguments are refused."""
+    import ctypes as C
+    from dlrm_jl_b200 import _lib
+    from dlrm_jl_b200.model import KAGGLE_EMBEDDING_SIZES, TERABYTE_EMBEDDING_SIZES
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    cases = [list(KAGGLE_EMBEDDING_SIZES), [min(r, 40_000_000) for r in TERABYTE_EMBEDDING_SIZES], [7, 7, 7, 7, 7],
+             [1], [5, 1000, 5, 1000, 3]] + [list(rng.integers(1, 10 ** 7, size=int(n))) for n in rng.integers(1, 40, size=6)]
+    for rows in cases:
+        for world in (1, 2, 3, 4, 8, 16):
+            owner = (C.c_int32 * len(rows))()
+            _lib.check(lib.dlrmb_shard_plan(len(rows), (C.c_int64 * len(rows))(*[int(r) for r in rows]), world, owner))
+            assert list(owner) == TableSharding.build(rows, world).owner, (rows, world)
+    assert lib.dlrmb_shard_plan(0, None, 2, None) == _lib.EINVAL
+    assert lib.dlrmb_shard_plan(3, (C.c_int64 * 3)(1, 2, 3), 0, (C.c_int32 * 3)()) == _lib.EINVAL
+
+
 def _worker(rank, world, port, q):
     from oracle import oracle as O
     os.environ["MASTER_ADDR"] = "127.0.0.1"
